@@ -1,0 +1,95 @@
+"""GPU parity tests, closed loop: dabb_process() (time sync -> OFDM -> FIC -> MSC -> RS) frame by frame for several
+streams against the CPU oracle's closed-loop receiver (oracle.rx_run, itself pinned bit-exact against the reference's
+RadioReceiver in tests/test_oracle_vs_ref.py).  FIBs, logical-frame bytes, RS statistics, startIndex and the fine
+corrector must be identical; the softbits of every frame too (DABB_FFT_EXACT)."""
+import numpy as np
+import pytest
+
+import dabtx
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+TF = 196608
+
+
+def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0):
+    S = len(sigs)
+    n = max(len(s) for s in sigs)
+    buf = np.zeros((S, n), np.complex64)
+    for i, s in enumerate(sigs):
+        buf[i, :len(s)] = s
+    ctx = pkg.Context(n_streams=S, keep_taps=True, n_subch_slots=n_slots, fft_mode=fft_mode)
+    d = ctx.dev(buf)
+    res = [dict(info=[], fibs=[], crc=[], msc=[], rs=[], soft=[], sf=[]) for _ in range(S)]
+    selected = False
+    lens = [len(s) for s in sigs]
+    for step in range(200):
+        out = ctx.process(d, n, np.zeros(S, np.int64), n, msc_stride=3 * bitrate, sf_stride=15 * bitrate)
+        r = out["results"]
+        soft = ctx.read_tap(0)
+        decoded = 0
+        for i in range(S):
+            if r["status"][i] != pkg.FRAME_DECODED:
+                continue
+            if r["next_pos"][i] > lens[i]:
+                continue          # ran into the zero padding: the oracle stops before this frame too
+            decoded += 1
+            res[i]["info"].append((int(r["start_index"][i]), int(r["fine_corr"][i]), int(r["coarse_corr"][i])))
+            res[i]["fibs"].append(out["fibs"][i].copy()); res[i]["crc"].append(int(r["fib_crc_mask"][i]))
+            res[i]["soft"].append(soft[i].copy())
+            nl = int(r["n_logical"][i][0])
+            # logical frames are produced by the last nl CIFs of the frame
+            for c in range(4 - nl, 4):
+                res[i]["msc"].append(out["msc"][i, 0, c, :3 * bitrate].copy())
+            for e in range(int(r["n_rs_events"][i][0])):
+                res[i]["rs"].append(((int(r["rs_uncorr_mask"][i][0]) >> e) & 1, int(r["rs_corr"][i][0][e])))
+            if r["sf_ready"][i][0]:
+                res[i]["sf"].append((out["sf"][i, 0, :15 * bitrate].copy(), int(r["sf_au_count"][i][0]), int(r["sf_au_crc_mask"][i][0])))
+        if not selected and decoded:
+            ctx.select_subchannel(0, cu, bitrate, eep_profile_a=True, eep_level=level)
+            selected = True
+        if decoded == 0 and step > 3:
+            break
+    ctx.close()
+    return res
+
+
+def compare(res, orc, name):
+    n = min(len(res["info"]), orc["frames"])
+    assert n >= orc["frames"] - 1 and n > 5, (name, len(res["info"]), orc["frames"])
+    for f in range(n):
+        assert res["info"][f][0] == orc["info"][f]["start_index"], (name, f, res["info"][f], orc["info"][f])
+        assert res["info"][f][1] == orc["info"][f]["fine"], (name, f, res["info"][f], orc["info"][f])
+        if "soft" in orc and f < len(orc["soft"]):
+            assert np.array_equal(res["soft"][f], orc["soft"][f]), (name, f, int((res["soft"][f] != orc["soft"][f]).sum()))
+        ofib = orc["fibs"][12 * f: 12 * f + 12]
+        assert np.array_equal(res["fibs"][f], ofib[:, 1:]), (name, f)
+        assert res["crc"][f] == int(sum(int(o) << k for k, o in enumerate(ofib[:, 0]))), (name, f)
+    msc = np.concatenate(res["msc"]) if res["msc"] else np.zeros(0, np.uint8)
+    m = min(len(msc), len(orc["msc"]))
+    assert m > 0 and np.array_equal(msc[:m], orc["msc"][:m]), name
+    k = min(len(res["rs"]), len(orc["rs"]))
+    assert k > 0 and [tuple(x) for x in orc["rs"][:k].tolist()] == [tuple(x) for x in res["rs"][:k]], name
+
+
+def test_closed_loop_matches_oracle(oracle):
+    pkg = load_pkg()
+    prot = oracle.prot_eep(96, 1, 3)
+    sigs = []
+    tx0 = dabtx.DabTx(seed=0xDAB); sigs.append(tx0.frames(26))
+    tx1 = dabtx.DabTx(seed=0xDAC); s1 = tx1.frames(26); sigs.append(dabtx.add_awgn(s1, 14.0, seed=0x5EED, signal_power=float(np.mean(np.abs(s1[3000:190000]) ** 2))))
+    tx2 = dabtx.DabTx(seed=0xDAD); s2 = tx2.frames(26); sigs.append(np.concatenate([np.zeros(1000, np.complex64) + 1e-6, s2])[:len(s2)])   # time offset
+    res = run_gpu(pkg, sigs)
+    for i, sig in enumerate(sigs):
+        orc = oracle.rx_run(sig, prot=prot, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True, want_soft=30)
+        compare(res[i], orc, f"stream{i}")
+    # the clean stream must also reproduce what was transmitted
+    lf = np.concatenate(tx0.logical)
+    msc = np.concatenate(res[0]["msc"])
+    hits = [k for k in range(0, 40) if np.array_equal(msc[:288], lf[k * 288:(k + 1) * 288])]
+    assert hits and np.array_equal(msc, lf[hits[0] * 288: hits[0] * 288 + len(msc)])
+    assert all(c == 0xFFF for c in res[0]["crc"])
+    assert len(res[0]["sf"]) >= 2 and all(m == 0x3F and n == 6 for _, n, m in res[0]["sf"])
+    sf_bytes = [s for s, _, _ in res[0]["sf"]]
+    txsf = [bytes(s) for s in tx0.superframes]
+    assert all(bytes(s) in txsf for s in sf_bytes)

@@ -1,0 +1,173 @@
+"""GPU parity tests, stage level: every CUDA stage through the C ABI against the CPU oracle on the same seeded inputs.
+Bar: bit-exact for integer/byte work; the float OFDM stage is bit-exact too in DABB_FFT_EXACT mode (and within 1e-4
+relative in DABB_FFT_FMA mode)."""
+import numpy as np
+import pytest
+
+import dabtx
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+TU, TS, TF, TNULL, TG, K = 2048, 2552, 196608, 2656, 504, 1536
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    pkg = load_pkg()
+    c = pkg.Context(n_streams=4, keep_taps=True)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def iq12():
+    tx = dabtx.DabTx(seed=0xDAB)
+    return tx, tx.frames(6)
+
+
+def test_ofdm_demod_bit_exact(ctx, oracle, iq12):
+    tx, iq = iq12
+    frames = np.stack([iq[f * TF: (f + 1) * TF + 4096] for f in range(1, 5)])
+    prs = np.full(4, TNULL + 305, np.int64)          # the reference's steady-state window
+    soft, r1, fc = ctx.ofdm_demod(frames, prs, want_r1=True, want_fc=True)
+    for f in range(4):
+        st = TNULL + 305
+        s_o, r_o = oracle.demod_frame(frames[f, st: st + TU], frames[f, st + TU: st + TU + 75 * TS], True)
+        assert np.array_equal(soft[f], s_o), f"softbits differ in frame {f}: {(soft[f] != s_o).sum()}"
+        assert np.array_equal(r1[f].view(np.uint32), r_o.view(np.uint32)), "pre-quantisation products not bit-equal"
+        # CP correlation: float sum in a different order -> relative tolerance
+        x = frames[f, st + TU: st + TU + 75 * TS].reshape(75, TS).astype(np.complex128)
+        ref = (x[:, TU:] * np.conj(x[:, :TG])).sum()
+        assert abs(fc[f] - ref) <= 1e-4 * abs(ref)
+
+
+def test_ofdm_demod_fma_mode_within_tolerance(oracle, iq12):
+    pkg = load_pkg()
+    c = pkg.Context(n_streams=1, fft_mode=pkg.FFT_FMA)
+    tx, iq = iq12
+    frames = np.stack([iq[TF: 2 * TF + 4096]])
+    soft, r1 = c.ofdm_demod(frames, np.array([TNULL + 305], np.int64), want_r1=True)
+    st = TNULL + 305
+    s_o, r_o = oracle.demod_frame(frames[0, st: st + TU], frames[0, st + TU: st + TU + 75 * TS], True)
+    rel = np.abs(r1[0] - r_o) / np.abs(r_o)
+    assert rel.max() <= 1e-4          # north_star tolerance for soft-decision intermediates
+    assert np.array_equal(np.sign(soft[0]), np.sign(s_o)) or (np.sign(soft[0]) != np.sign(s_o)).mean() < 1e-4
+    assert np.abs(soft[0].astype(int) - s_o.astype(int)).max() <= 1
+    c.close()
+
+
+def test_ofdm_demod_with_nco(ctx, oracle, iq12):
+    tx, iq = iq12
+    shifted = dabtx.freq_shift(iq, 1234.0)
+    frames = np.stack([shifted[TF: 2 * TF + 4096]])
+    st = TNULL + 305
+    lp0, ph = 777, 1234
+    nco = np.array([[lp0, ph]], np.int32)
+    soft = ctx.ofdm_demod(frames, np.array([st], np.int64), nco=nco)
+    # oracle: mix on the CPU exactly like OFDMProcessor::getSamples, then demod
+    n = np.arange(TU + 75 * TS, dtype=np.int64)
+    lp = (lp0 - n * ph) % 2048000
+    osc = (np.cos(2.0 * np.pi * lp / 2048000).astype(np.float32) + 1j * np.sin(2.0 * np.pi * lp / 2048000).astype(np.float32)).astype(np.complex64)
+    x = frames[0, st: st + TU + 75 * TS]
+    re = (x.real * osc.real).astype(np.float32) - (x.imag * osc.imag).astype(np.float32)
+    im = (x.real * osc.imag).astype(np.float32) + (x.imag * osc.real).astype(np.float32)
+    mixed = (re + 1j * im).astype(np.complex64)
+    s_o = oracle.demod_frame(mixed[:TU], mixed[TU:])
+    assert np.array_equal(soft[0], s_o)
+    fibs, crc = oracle.fic_decode(s_o[:3].reshape(-1))
+    assert crc.all()
+
+
+def test_find_index(ctx, oracle, iq12):
+    tx, iq = iq12
+    starts = np.array([TNULL - 199, TNULL - 100, TNULL - 400, TNULL + 3000], np.int64)   # last one: no PRS inside -> -1 or garbage-consistent
+    frames = np.stack([iq[2 * TF: 3 * TF]] * 4)
+    idx, cir = ctx.find_index(frames, starts, want_cir=True)
+    for i, s in enumerate(starts):
+        i_o, c_o = oracle.find_index(frames[i, s: s + TU])
+        assert idx[i] == i_o, (i, idx[i], i_o)
+        assert np.array_equal(cir[i].view(np.uint32), c_o.view(np.uint32)), f"CIR not bit-equal ({np.abs(cir[i]-c_o).max()})"
+    assert idx[0] == 504
+
+
+@pytest.mark.parametrize("nbits", [768, 2304, 192])
+def test_viterbi_bit_exact(ctx, oracle, nbits):
+    rng = np.random.default_rng(nbits)
+    n = 200
+    soft = rng.integers(-128, 128, (n, (nbits + 6) * 4)).astype(np.int8)
+    for i in range(0, n, 2):   # half of them: real codewords with noise and punctures
+        bits = rng.integers(0, 2, nbits).astype(np.uint8)
+        enc = oracle.conv_encode(bits).astype(np.float32) * 2 - 1
+        s = np.clip(enc * 35 + rng.standard_normal(enc.size) * 50, -127, 127).astype(np.int8)
+        s[rng.random(s.size) < 0.25] = 0
+        soft[i] = s
+    out = ctx.viterbi(soft, nbits)
+    for i in range(n):
+        assert np.array_equal(out[i], oracle.viterbi(soft[i], nbits)), f"codeword {i}"
+
+
+def test_fic_decode(ctx, oracle, iq12):
+    tx, iq = iq12
+    rng = np.random.default_rng(5)
+    frames = np.stack([iq[f * TF: (f + 1) * TF + 4096] for f in range(1, 4)])
+    soft = ctx.ofdm_demod(frames, np.full(3, TNULL + 305, np.int64))
+    fic_soft = soft[:, :3].reshape(3, 9216).copy()
+    noisy = np.clip(fic_soft.astype(int) + rng.integers(-90, 91, fic_soft.shape), -127, 127).astype(np.int8)
+    allsoft = np.concatenate([fic_soft, noisy, rng.integers(-127, 128, (2, 9216)).astype(np.int8)])
+    fibs, crc = ctx.fic_decode(allsoft)
+    for i in range(len(allsoft)):
+        fb, ok = oracle.fic_decode(allsoft[i])
+        assert np.array_equal(fibs[i], np.packbits(fb, axis=1)), i
+        assert crc[i] == int(sum(int(o) << k for k, o in enumerate(ok))), i
+    assert crc[0] == 0xFFF and np.array_equal(fibs[0, 0], dabtx.fib_bytes(tx))
+
+
+@pytest.mark.parametrize("cfg", [(96, True, 3), (64, True, 1), (8, True, 2), (32, True, 2), (128, True, 4), (32, False, 1), (96, False, 3), (128, False, 4)])
+def test_msc_decode_eep(ctx, oracle, cfg):
+    br, pa, lv = cfg
+    rng = np.random.default_rng(br + lv)
+    prot = oracle.prot_eep(br, pa, lv)
+    cu = dabtx.eep_cu(br, pa, lv)
+    n = 20
+    soft = rng.integers(-127, 128, (n, cu * 64)).astype(np.int8)
+    out = ctx.msc_decode(soft, cu, br, eep_profile_a=pa, eep_level=lv)
+    for i in range(n):
+        bits = oracle.msc_deconvolve(prot, soft[i, :prot.in_bits], True)
+        assert np.array_equal(out[i], oracle.pack_bits(bits)), i
+
+
+@pytest.mark.parametrize("cfg", [(32, 5), (48, 3), (128, 1), (192, 2), (80, 1)])
+def test_msc_decode_uep(ctx, oracle, cfg):
+    br, lv = cfg
+    rng = np.random.default_rng(br * 7 + lv)
+    prot = oracle.prot_uep(br, lv)
+    cu = (prot.in_bits + 63) // 64
+    soft = rng.integers(-127, 128, (8, cu * 64)).astype(np.int8)
+    out = ctx.msc_decode(soft, cu, br, short_form=True, uep_level=lv)
+    for i in range(8):
+        bits = oracle.msc_deconvolve(prot, soft[i, :prot.in_bits], True)
+        assert np.array_equal(out[i], oracle.pack_bits(bits)), i
+
+
+def test_rs_superframes(ctx, oracle):
+    rng = np.random.default_rng(9)
+    tx = dabtx.DabTx(seed=4)
+    sfs = []
+    for i in range(40):
+        sf = tx.superframe(bad_au=(i % 6 if i % 5 == 0 else None))
+        ne = [0, 3, 20, 60, 200, 1440][i % 6]
+        if ne:
+            pos = rng.choice(len(sf), ne, replace=False)
+            sf = sf.copy(); sf[pos] ^= rng.integers(1, 256, ne).astype(np.uint8)
+        sfs.append(sf)
+    sfs.append(np.zeros(1440, np.uint8))
+    sfs = np.stack(sfs)
+    out, info = ctx.rs_superframes(sfs)
+    for i in range(len(sfs)):
+        o_sf, corr, unc = oracle.rs_decode_superframe(sfs[i])
+        assert np.array_equal(out[i], o_sf), i
+        assert (info[i, 0], info[i, 1]) == (corr, unc), (i, info[i], corr, unc)
+        ev, _ = oracle.superframe_filter(np.concatenate([sfs[i].reshape(5, -1)]))
+        assert info[i, 2] == ev[0]["sync"]
+        if ev[0]["sync"]:
+            assert (info[i, 3] & 0xFF) == ev[0]["au_ok"] and (info[i, 3] >> 8) == ev[0]["num_aus"]

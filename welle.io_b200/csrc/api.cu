@@ -1,0 +1,695 @@
+// api.cu — the C ABI of include/dab_b200.h: context, per-stream receiver state, the per-frame pipeline and the
+// stage-level entry points.  Host code here only sequences kernels on the context's stream; all signal processing
+// is in ofdm.cu / viterbi.cu / rs.cu and the small state-machine kernels below.  There is no CPU fallback.
+#include "../../include/dab_b200.h"
+#include "common.cuh"
+#include "viterbi.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dabb;
+
+namespace {
+
+// per-stream receiver state (device resident), the variables OFDMProcessor carries between frames
+// (ofdm-processor.h: coarseCorrector, fineCorrector, localPhase, sLevel) + FicHandler::fic_decode_success_ratio
+struct StreamState {
+    int64_t pos;            // logical sample index of the next sample to read
+    int32_t coarse, fine;   // Hz; fine has int16 semantics
+    int32_t local_phase;    // localPhase after the last sample read
+    int32_t fic_ratio;      // 0..10
+    int32_t acquired;       // 0: null search needed, 1: tracking
+    int32_t started;        // 0: sLevel warm-up (T_F/2 samples) not done yet
+    float slevel;
+    int32_t start_index;    // last findIndex
+    int64_t nframes;
+};
+
+struct StepScratch {        // per stream, rewritten every step
+    int64_t win_start;      // T_u window for findIndex, relative to the stream buffer
+    int64_t prs_start;
+    int32_t nco_sync[2];
+    int32_t nco_frame[4];
+    int32_t active;         // this stream decodes a frame in this step
+    int32_t status;
+};
+
+std::string g_create_error;
+
+} // namespace
+
+struct dabb_ctx {
+    int device = 0; cudaStream_t stream = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
+    int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
+    std::string err; int64_t launches = 0;
+    HostTables* host = nullptr; DevTables dev{};
+    std::vector<void*> allocs;
+    StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
+    int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr;
+    int8_t* d_soft = nullptr; uint32_t* d_fic_rows = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
+    dabb_frame_result* d_results = nullptr;
+    // per slot
+    struct Slot {
+        bool configured = false; ProtProfile prof{}; int nsteps = 0, nbits = 0, row_words = 0, flen = 0;
+        int16_t* d_map = nullptr; uint32_t* d_prbs_words = nullptr; uint32_t* d_rows = nullptr; int32_t* d_valid = nullptr;
+        uint8_t* d_logical = nullptr; int8_t* d_ring = nullptr; uint8_t* d_window = nullptr; uint8_t* d_sf = nullptr; int32_t* d_info = nullptr;
+    } slot[DABB_MAX_SUBCH];
+    uint32_t* d_fic_prbs_words = nullptr;
+    std::vector<MscSlotState> h_slots;
+    float2* d_iq_stage = nullptr; size_t iq_stage_samples = 0;
+    // pinned host staging for results
+    dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
+    int groups = 1;
+    const int32_t** d_info_tab = nullptr;
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DABB_E_CUDA; } } while (0)
+
+template <typename T> int dalloc(dabb_ctx* ctx, T** p, size_t n, bool zero = true)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+    if (zero) cudaMemsetAsync(q, 0, n * sizeof(T), ctx->stream);
+    ctx->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+int check_launch(dabb_ctx* ctx, const char* what)
+{
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return DABB_E_CUDA; }
+    return 0;
+}
+
+void pack_prbs_words(const uint8_t* bits, int nbits, std::vector<uint32_t>& w)
+{
+    // same packing as the decoder output: bit t lands in byte t/8 (MSB first), bytes little-endian in the word
+    w.assign((nbits + 31) / 32, 0);
+    for (int t = 0; t < nbits; t++) if (bits[t]) w[t >> 5] |= 1u << (8 * ((t >> 3) & 3) + 7 - (t & 7));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// state-machine kernels (one thread per stream)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t mod_rate(int64_t v) { v %= INPUT_RATE; if (v < 0) v += INPUT_RATE; return (int32_t)v; }
+
+// Initial / re-acquisition: OFDMProcessor::run up to SyncOnPhase (ofdm-processor.cpp:248-323): sLevel warm-up over
+// T_F/2 samples, then the 50-sample envelope dip search.  Strictly sequential per stream, exact arithmetic order
+// (double IIR), only runs while a stream is not tracking.
+__global__ void acquire_kernel(StreamState* st, const float2* iq, int64_t stride, const int64_t* buf_start, int64_t buf_len, const float2* osc, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    StreamState z = st[s];
+    if (z.acquired) return;
+    const float2* src = iq + (int64_t)s * stride;
+    int64_t pos = z.pos - buf_start[s];            // physical index
+    const int64_t end = buf_len;
+    int32_t lp = z.local_phase; float sl = z.slevel;
+    if (pos < 0) return;
+    auto get = [&](int32_t phase, float& l1) -> bool {
+        if (pos >= end) return false;
+        float2 v = src[pos++];
+        lp -= phase; lp = (lp + INPUT_RATE) % INPUT_RATE;
+        const float2 o = osc[lp];
+        const float re = __fsub_rn(__fmul_rn(v.x, o.x), __fmul_rn(v.y, o.y)), im = __fadd_rn(__fmul_rn(v.x, o.y), __fmul_rn(v.y, o.x));
+        l1 = __fadd_rn(fabsf(re), fabsf(im));
+        sl = (float)__dadd_rn(__dmul_rn(0.00001, (double)l1), __dmul_rn(1 - 0.00001, (double)sl));
+        return true;
+    };
+    float l1;
+    int started = z.started;
+    if (!started) {
+        sl = 0.f;
+        for (int i = 0; i < TF / 2; i++) if (!get(0, l1)) return;   // not enough samples: leave the state untouched
+        started = 1;
+    }
+    const int32_t phase = z.coarse + z.fine;
+    // local ring of the last 64 envelope values is enough for the 50-tap moving sum
+    float env[64];
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int idx = 0; float cur = 0.f;
+        for (int i = 0; i < 50; i++) { if (!get(0, l1)) return; env[idx & 63] = l1; cur = __fadd_rn(cur, l1); idx++; }
+        int counter = 0; bool fail = false;
+        while ((double)__fdiv_rn(cur, 50.f) > __dmul_rn(0.50, (double)sl)) {
+            if (!get(phase, l1)) return;
+            env[idx & 63] = l1; cur = __fadd_rn(cur, __fsub_rn(l1, env[(idx - 50) & 63])); idx++;
+            if (++counter > TF) { fail = true; break; }
+        }
+        if (fail) continue;
+        counter = 0;
+        while ((double)__fdiv_rn(cur, 50.f) < __dmul_rn(0.75, (double)sl)) {
+            if (!get(phase, l1)) return;
+            env[idx & 63] = l1; cur = __fadd_rn(cur, __fsub_rn(l1, env[(idx - 50) & 63])); idx++;
+            if (++counter > TNULL + 50) { fail = true; break; }
+        }
+        if (fail) continue;
+        z.acquired = 1;
+        break;
+    }
+    if (!z.acquired) return;
+    z.started = started; z.pos = pos + buf_start[s]; z.local_phase = lp; z.slevel = sl;
+    st[s] = z;
+}
+
+__global__ void plan_kernel(StreamState* st, StepScratch* scr, const int64_t* buf_start, int64_t buf_len, int S,
+                            int64_t* win, int32_t* nco_sync, int32_t* active)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const StreamState z = st[s];
+    StepScratch c{};
+    const int64_t rel = z.pos - buf_start[s];
+    const int64_t need = (int64_t)TU + (TU - 1) + 75 * (int64_t)TS + TNULL;
+    if (!z.acquired) { c.active = 0; c.status = DABB_FRAME_ACQUIRING; }
+    else if (rel < 0 || rel + need > buf_len) { c.active = 0; c.status = DABB_FRAME_NEED_SAMPLES; }
+    else {
+        c.active = 1; c.status = DABB_FRAME_DECODED; c.win_start = rel;
+        const int32_t p1 = z.coarse + z.fine;
+        c.nco_sync[0] = mod_rate((int64_t)z.local_phase - p1); c.nco_sync[1] = p1;
+    }
+    scr[s] = c;
+    win[s] = c.win_start; nco_sync[2 * s] = c.nco_sync[0]; nco_sync[2 * s + 1] = c.nco_sync[1]; active[s] = c.active;
+}
+
+__global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_t* index, int S, int64_t* prs, int32_t* nco_frame, int32_t* active)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    StepScratch c = scr[s];
+    if (!c.active) return;
+    StreamState z = st[s];
+    const int32_t p1 = z.coarse + z.fine;
+    const int idx = index[s];
+    z.start_index = idx;
+    if (idx < 0) {
+        // SyncOnPhase failed: the T_u samples are consumed and the null search starts over (ofdm-processor.cpp:347-350)
+        z.pos += TU; z.local_phase = mod_rate((int64_t)z.local_phase - (int64_t)TU * p1); z.acquired = 0;
+        c.active = 0; c.status = DABB_FRAME_NO_SYNC;
+        st[s] = z; scr[s] = c; active[s] = 0;
+        return;
+    }
+    c.prs_start = c.win_start + idx;
+    // phase applied to PRS sample 0 (the (idx+1)-th sample read in this frame)
+    const int32_t lp_prs0 = mod_rate((int64_t)z.local_phase - (int64_t)(idx + 1) * p1);
+    const int32_t p2 = p1;   // coarse corrector update would go here (ofdm-processor.cpp:397-409)
+    // phase applied to the first data-symbol sample = lp after 2048+idx samples, minus p2; expressed at index 2048
+    const int32_t lp_after_prs = mod_rate((int64_t)z.local_phase - (int64_t)(TU + idx) * p1);
+    const int32_t lp_sym0 = mod_rate((int64_t)lp_after_prs - p2 + (int64_t)TU * p2);   // so that lp(i) = lp_sym0 - i*p2 for i >= 2048
+    c.nco_frame[0] = lp_prs0; c.nco_frame[1] = p1; c.nco_frame[2] = lp_sym0; c.nco_frame[3] = p2;
+    scr[s] = c; st[s] = z;
+    prs[s] = c.prs_start;
+    nco_frame[4 * s] = lp_prs0; nco_frame[4 * s + 1] = p1; nco_frame[4 * s + 2] = lp_sym0; nco_frame[4 * s + 3] = p2;
+}
+
+__global__ void finalize_kernel(StreamState* st, const StepScratch* scr, MscSlotState* slots, int n_slots, int S, int groups,
+                                const float2* fc_part, const int32_t* snr, const int32_t* crc, const int32_t* const* slot_info,
+                                dabb_frame_result* res)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const StepScratch c = scr[s];
+    StreamState z = st[s];
+    dabb_frame_result r;
+    memset(&r, 0, sizeof r);
+    r.status = c.status;
+    if (c.active) {
+        // FreqCorr: partial sums in group order
+        float fx = 0.f, fy = 0.f;
+        for (int g = 0; g < groups; g++) { fx += fc_part[(int64_t)s * groups + g].x; fy += fc_part[(int64_t)s * groups + g].y; }
+        const int idx = z.start_index;
+        const int32_t p1 = c.nco_frame[1], p2 = c.nco_frame[3];
+        // FIC success counter, one saturating update per FIB in order (fic-handler.cpp:214-229)
+        const int mask = crc[s];
+        for (int f = 0; f < 12; f++) { if ((mask >> f) & 1) { if (z.fic_ratio < 10) z.fic_ratio++; } else if (z.fic_ratio > 0) z.fic_ratio--; }
+        // fineCorrector += 0.1 * arg(FreqCorr) / M_PI * (carrierDiff / 2), int16 store (ofdm-processor.cpp:450-451)
+        const double upd = 0.1 * (double)(float)atan2((double)fy, (double)fx) / 3.14159265358979323846 * 500;
+        z.fine = (int32_t)(int16_t)((double)z.fine + upd);
+        const int32_t p3 = z.coarse + z.fine;
+        int64_t lp = (int64_t)z.local_phase - (int64_t)(TU + idx) * p1 - (int64_t)75 * TS * p2 - (int64_t)TNULL * p3;
+        z.local_phase = mod_rate(lp);
+        z.pos += (int64_t)TU + idx + 75 * (int64_t)TS + TNULL;
+        if (z.fine > 500) { z.coarse += 1000; z.fine -= 1000; }
+        else if (z.fine < -500) { z.coarse -= 1000; z.fine += 1000; }
+        z.nframes++;
+        r.start_index = idx; r.snr_raw = snr[s]; r.fib_crc_mask = mask;
+        r.freq_corr_re = fx; r.freq_corr_im = fy;
+        for (int k = 0; k < n_slots; k++) {
+            MscSlotState& m = slots[s * n_slots + k];
+            if (!m.enabled) continue;
+            m.cif_count += 4;
+            const int32_t* inf = slot_info[k] + (int64_t)s * 16;
+            r.n_logical[k] = inf[0]; r.n_rs_events[k] = inf[1]; r.rs_uncorr_mask[k] = inf[2];
+            for (int e = 0; e < 4; e++) r.rs_corr[k][e] = inf[3 + e];
+            r.sf_ready[k] = inf[7]; r.sf_au_count[k] = inf[8]; r.sf_au_crc_mask[k] = inf[9];
+        }
+        st[s] = z;
+    } else {
+        r.start_index = z.start_index;
+    }
+    r.fine_corr = z.fine; r.coarse_corr = z.coarse; r.fic_ratio = z.fic_ratio; r.next_pos = z.pos; r.slevel = z.slevel;
+    res[s] = r;
+}
+
+__global__ void reset_kernel(StreamState* st, MscSlotState* slots, int n_slots, int first, int count, int64_t pos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    StreamState z{}; z.pos = pos; z.start_index = -1;
+    st[first + i] = z;
+    for (int k = 0; k < n_slots; k++) { MscSlotState& m = slots[(first + i) * n_slots + k]; m.cif_count = 0; m.sf_frame_count = 0; }
+}
+
+__global__ void set_slot_kernel(MscSlotState* slots, int n_slots, int slot, int first, int count, MscSlotState v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    slots[(first + i) * n_slots + slot] = v;
+}
+
+int ensure_dec(dabb_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->dec_bytes) return 0;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(decisions): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+    ctx->allocs.push_back(q);
+    ctx->d_dec = (uint2*)q; ctx->dec_bytes = bytes;
+    return 0;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int dabb_abi_version(void) { return DABB_ABI_VERSION; }
+
+const char* dabb_last_error(const dabb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dabb_create(const dabb_config* cfg, dabb_ctx** out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return DABB_E_ARG; }
+    if (cfg->abi_version != DABB_ABI_VERSION) { g_create_error = "ABI version mismatch"; return DABB_E_ARG; }
+    if (cfg->transmission_mode != 1 && cfg->transmission_mode != 0) { g_create_error = "only transmission mode I is supported"; return DABB_E_UNSUPPORTED; }
+    if (cfg->n_streams < 1) { g_create_error = "n_streams < 1"; return DABB_E_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device: this library has no CPU fallback"; return DABB_E_NODEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return DABB_E_ARG; }
+    dabb_ctx* ctx = new dabb_ctx();
+    ctx->device = cfg->device; ctx->S = cfg->n_streams; ctx->fft_mode = cfg->fft_mode; ctx->disable_coarse = cfg->disable_coarse; ctx->keep_taps = cfg->keep_taps;
+    ctx->n_slots = cfg->n_subch_slots > 0 ? (cfg->n_subch_slots > DABB_MAX_SUBCH ? DABB_MAX_SUBCH : cfg->n_subch_slots) : 1;
+    ctx->max_cu = cfg->max_subch_cu > 0 ? cfg->max_subch_cu : 144;
+    ctx->groups = cfg->ofdm_groups > 0 ? cfg->ofdm_groups : (ctx->S >= 1024 ? 1 : (ctx->S >= 64 ? 5 : 25));
+    if (75 % ctx->groups) ctx->groups = 1;
+    auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    ctx->host = new HostTables();
+    build_host_tables(*ctx->host);
+    const int S = ctx->S;
+    int rc = 0;
+    // tables
+    float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
+    if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
+        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
+        return fail(rc);
+    {
+        std::vector<float2> h_osc(INPUT_RATE);
+        build_osc_table(h_osc.data());
+        cudaMemcpyAsync(osc, h_osc.data(), sizeof(float2) * INPUT_RATE, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(tf, ctx->host->tw_fwd, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ti, ctx->host->tw_inv, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(pr, ctx->host->prs_ref, sizeof(float2) * TU, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ip, ctx->host->invperm, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(fm, ctx->host->fic_map, sizeof(int16_t) * 3096, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ge, ctx->host->gf_exp, 512, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(gl, ctx->host->gf_log, 256, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(pb, ctx->host->prbs, sizeof ctx->host->prbs, cudaMemcpyHostToDevice, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "table upload failed"; return fail(DABB_E_CUDA); }
+    }
+    ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.fic_map = fm;
+    ctx->dev.gf_exp = ge; ctx->dev.gf_log = gl; ctx->dev.prbs = pb;
+    {
+        std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, 768, w);
+        if ((rc = dalloc(ctx, &ctx->d_fic_prbs_words, w.size()))) return fail(rc);
+        cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
+    }
+    ctx->ring_pitch = ctx->max_cu * 64;
+    if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
+        (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, S)) || (rc = dalloc(ctx, &ctx->d_prs, S)) ||
+        (rc = dalloc(ctx, &ctx->d_nco_sync, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_nco_frame, 4 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_active, S)) ||
+        (rc = dalloc(ctx, &ctx->d_index, S)) || (rc = dalloc(ctx, &ctx->d_snr, S)) || (rc = dalloc(ctx, &ctx->d_fc, (size_t)S * ctx->groups)) ||
+        (rc = dalloc(ctx, &ctx->d_soft, (size_t)S * DABB_SOFT_PER_FRAME, false)) || (rc = dalloc(ctx, &ctx->d_fic_rows, (size_t)S * 4 * vit_row_words(774), false)) ||
+        (rc = dalloc(ctx, &ctx->d_fibs, (size_t)S * 12 * 32)) || (rc = dalloc(ctx, &ctx->d_crc, S)) || (rc = dalloc(ctx, &ctx->d_results, S)) ||
+        (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)))
+        return fail(rc);
+    if (ctx->keep_taps && (rc = dalloc(ctx, &ctx->d_cir, (size_t)S * TU))) return fail(rc);
+    if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, 774)))) return fail(rc);
+    ctx->h_slots.assign((size_t)S * ctx->n_slots, MscSlotState{});
+    // info arrays of unconfigured slots are never read (finalize skips disabled slots)
+    cudaHostAlloc((void**)&ctx->h_results, sizeof(dabb_frame_result) * S, cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_fibs, (size_t)S * 12 * 32, cudaHostAllocDefault);
+    {
+        reset_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, 0, S, 0);
+        ctx->launches++;
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = std::string("init failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(DABB_E_CUDA); }
+    *out = ctx;
+    return DABB_OK;
+}
+
+void dabb_destroy(dabb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    if (ctx->h_fibs) cudaFreeHost(ctx->h_fibs);
+    if (ctx->h_msc) cudaFreeHost(ctx->h_msc);
+    if (ctx->h_sf) cudaFreeHost(ctx->h_sf);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->host;
+    delete ctx;
+}
+
+void* dabb_cuda_stream(dabb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t dabb_kernel_launches(const dabb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+int dabb_stream_reset(dabb_ctx* ctx, int32_t first, int32_t count, int64_t pos)
+{
+    if (!ctx || first < 0 || count < 0 || first + count > ctx->S) return DABB_E_ARG;
+    if (!count) return 0;
+    cudaSetDevice(ctx->device);
+    reset_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, first, count, pos);
+    for (int i = first; i < first + count; i++) for (int k = 0; k < ctx->n_slots; k++) { ctx->h_slots[(size_t)i * ctx->n_slots + k].cif_count = 0; ctx->h_slots[(size_t)i * ctx->n_slots + k].sf_frame_count = 0; }
+    return check_launch(ctx, "reset_kernel");
+}
+
+int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t slot, const dabb_subchannel* sc)
+{
+    if (!ctx || !sc || first < 0 || count < 1 || first + count > ctx->S || slot < 0 || slot >= ctx->n_slots) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    ProtProfile prof;
+    if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
+    if (sc->length_cu < 1 || sc->length_cu > ctx->max_cu || sc->start_cu < 0 || sc->start_cu + sc->length_cu > 864) { ctx->err = "sub-channel does not fit (raise dabb_config.max_subch_cu)"; return DABB_E_ARG; }
+    if (prof.in_bits > sc->length_cu * 64) { ctx->err = "protection profile needs more bits than the sub-channel holds"; return DABB_E_ARG; }
+    auto& sl = ctx->slot[slot];
+    const int S = ctx->S;
+    int rc = 0;
+    if (sl.configured && (memcmp(&sl.prof, &prof, sizeof prof) != 0)) {
+        // a slot decodes one code geometry for all its streams in one launch
+        bool others = false;
+        for (int i = 0; i < S; i++) if ((i < first || i >= first + count) && ctx->h_slots[(size_t)i * ctx->n_slots + slot].enabled) others = true;
+        if (others) { ctx->err = "streams sharing a slot must use the same bitrate/protection; use another slot"; return DABB_E_UNSUPPORTED; }
+        sl.configured = false;
+    }
+    if (!sl.configured) {
+        sl.prof = prof; sl.nbits = 24 * prof.bitrate; sl.nsteps = sl.nbits + 6; sl.row_words = vit_row_words(sl.nsteps); sl.flen = 3 * prof.bitrate;
+        std::vector<int16_t> map((size_t)sl.nsteps * 4);
+        build_msc_map(*ctx->host, prof, map.data());
+        std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, sl.nbits, w);
+        const int flen_pad = (sl.flen + 15) & ~15;
+        if ((rc = dalloc(ctx, &sl.d_map, map.size())) || (rc = dalloc(ctx, &sl.d_prbs_words, w.size())) || (rc = dalloc(ctx, &sl.d_rows, (size_t)S * 4 * sl.row_words, false)) ||
+            (rc = dalloc(ctx, &sl.d_valid, (size_t)S * 4)) || (rc = dalloc(ctx, &sl.d_logical, (size_t)S * 4 * flen_pad)) ||
+            (rc = dalloc(ctx, &sl.d_window, (size_t)S * 5 * flen_pad)) || (rc = dalloc(ctx, &sl.d_sf, (size_t)S * 5 * flen_pad)) ||
+            (rc = dalloc(ctx, &sl.d_info, (size_t)S * 16)))
+            return rc;
+        if (!sl.d_ring && (rc = dalloc(ctx, &sl.d_ring, (size_t)S * MSC_RING * ctx->ring_pitch))) return rc;
+        CK(cudaMemcpyAsync(sl.d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(sl.d_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, sl.nsteps)))) return rc;
+        sl.configured = true;
+        if (sl.flen > ctx->flen_max) ctx->flen_max = sl.flen;
+    }
+    MscSlotState v{}; v.enabled = 1; v.start_cu = sc->start_cu; v.frag = sc->length_cu * 64; v.bitrate = sc->bitrate; v.dabplus = sc->dabplus; v.cif_count = 0; v.sf_frame_count = 0;
+    set_slot_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_slots, ctx->n_slots, slot, first, count, v);
+    for (int i = first; i < first + count; i++) ctx->h_slots[(size_t)i * ctx->n_slots + slot] = v;
+    return check_launch(ctx, "set_slot_kernel");
+}
+
+int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t slot)
+{
+    if (!ctx || first < 0 || count < 1 || first + count > ctx->S || slot < 0 || slot >= ctx->n_slots) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    MscSlotState v{};
+    set_slot_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_slots, ctx->n_slots, slot, first, count, v);
+    for (int i = first; i < first + count; i++) ctx->h_slots[(size_t)i * ctx->n_slots + slot] = v;
+    return check_launch(ctx, "set_slot_kernel");
+}
+
+static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc)
+{
+    int rc;
+    launch_fic_prep(ctx->dev, soft, soft_stride, active, n_frames, ctx->d_fic_rows, ctx->stream);
+    if ((rc = check_launch(ctx, "fic_prep_kernel"))) return rc;
+    ViterbiParams vp{};
+    vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
+    vp.dec = ctx->d_dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
+    launch_viterbi(vp, ctx->stream);
+    if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
+    launch_fic_crc(fibs, active, n_frames, crc, ctx->stream);
+    return check_launch(ctx, "fic_crc_kernel");
+}
+
+int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
+{
+    if (!ctx || !io || !io->iq || !io->buf_start) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    const int S = ctx->S;
+    int rc;
+    const float2* iq = reinterpret_cast<const float2*>(io->iq);
+    int64_t stride = io->stride_samples;
+    if (io->iq_is_host) {
+        const size_t need = (size_t)S * io->buf_len;
+        if (need > ctx->iq_stage_samples) {
+            if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
+            ctx->d_iq_stage = nullptr; ctx->iq_stage_samples = 0;
+            cudaError_t e = cudaMalloc((void**)&ctx->d_iq_stage, need * sizeof(float2));
+            if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(iq staging): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+            ctx->iq_stage_samples = need;
+        }
+        CK(cudaMemcpy2DAsync(ctx->d_iq_stage, (size_t)io->buf_len * sizeof(float2), io->iq, (size_t)stride * sizeof(float2), (size_t)io->buf_len * sizeof(float2), S,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        iq = ctx->d_iq_stage; stride = io->buf_len;
+    }
+    CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+    const int tb = 128, gb = (S + tb - 1) / tb;
+    acquire_kernel<<<(S + 31) / 32, 32, 0, ctx->stream>>>(ctx->d_state, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, S);
+    if ((rc = check_launch(ctx, "acquire_kernel"))) return rc;
+    plan_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_buf_start, io->buf_len, S, ctx->d_win, ctx->d_nco_sync, ctx->d_active);
+    if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
+    SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = ctx->d_win; sp.nco = ctx->d_nco_sync; sp.active = ctx->d_active; sp.index_out = ctx->d_index; sp.cir_out = ctx->d_cir; sp.n = S;
+    launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
+    if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
+    post_sync_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_index, S, ctx->d_prs, ctx->d_nco_frame, ctx->d_active);
+    if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
+    OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = ctx->d_prs; op.nco = ctx->d_nco_frame; op.active = ctx->d_active; op.soft = ctx->d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
+    op.r1 = nullptr; op.freqcorr = ctx->d_fc; op.snr = ctx->d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, ctx->stream);
+    if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
+    if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc))) return rc;
+    const int32_t* h_info[DABB_MAX_SUBCH] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < ctx->n_slots; k++) {
+        auto& sl = ctx->slot[k];
+        h_info[k] = sl.d_info;
+        if (!sl.configured) continue;
+        const int flen_pad = (sl.flen + 15) & ~15;
+        CK(cudaMemsetAsync(sl.d_valid, 0, sizeof(int32_t) * S * 4, ctx->stream));
+        MscCollectParams cp{}; cp.soft = ctx->d_soft; cp.soft_stride = DABB_SOFT_PER_FRAME; cp.active = ctx->d_active; cp.slots = ctx->d_slots; cp.n_slots = ctx->n_slots; cp.slot = k; cp.ring = sl.d_ring; cp.ring_pitch = ctx->ring_pitch;
+        launch_msc_collect(cp, S, ctx->stream);
+        if ((rc = check_launch(ctx, "msc_collect_kernel"))) return rc;
+        MscPrepParams pp{}; pp.active = ctx->d_active; pp.slots = ctx->d_slots; pp.n_slots = ctx->n_slots; pp.slot = k; pp.ring = sl.d_ring; pp.ring_pitch = ctx->ring_pitch; pp.map = sl.d_map; pp.nsteps = sl.nsteps;
+        pp.rows = sl.d_rows; pp.row_words = sl.row_words; pp.valid = sl.d_valid;
+        launch_msc_prep(pp, S, ctx->stream);
+        if ((rc = check_launch(ctx, "msc_prep_kernel"))) return rc;
+        ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = ctx->d_dec;
+        vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
+        launch_viterbi(vp, ctx->stream);
+        if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
+        SuperframeParams fp{}; fp.active = ctx->d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;
+        fp.valid = sl.d_valid; fp.window = sl.d_window; fp.window_pitch = 5 * flen_pad; fp.sf_out = sl.d_sf; fp.sf_pitch = 5 * flen_pad; fp.info = sl.d_info; fp.gf_exp = ctx->dev.gf_exp; fp.gf_log = ctx->dev.gf_log;
+        launch_superframe(fp, ctx->stream);
+        if ((rc = check_launch(ctx, "superframe_kernel"))) return rc;
+    }
+    // slot_info pointer table lives in a small device array rewritten each call
+    CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, ctx->stream));
+    finalize_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_slots, ctx->n_slots, S, ctx->groups, ctx->d_fc, ctx->d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
+    return check_launch(ctx, "finalize_kernel");
+}
+
+int dabb_process(dabb_ctx* ctx, const dabb_io* io)
+{
+    int rc = dabb_process_async(ctx, io);
+    if (rc) return rc;
+    const int S = ctx->S;
+    if (io->results) CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(dabb_frame_result) * S, cudaMemcpyDeviceToHost, ctx->stream));
+    if (io->fibs) CK(cudaMemcpyAsync(ctx->h_fibs, ctx->d_fibs, (size_t)S * 12 * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (io->results) memcpy(io->results, ctx->h_results, sizeof(dabb_frame_result) * S);
+    if (io->fibs) memcpy(io->fibs, ctx->h_fibs, (size_t)S * 12 * 32);
+    // logical frames and superframes: strided device -> host copies (small)
+    for (int k = 0; k < ctx->n_slots; k++) {
+        auto& sl = ctx->slot[k];
+        if (!sl.configured) continue;
+        const int flen_pad = (sl.flen + 15) & ~15;
+        if (io->msc) {
+            if (io->msc_stride < sl.flen) { ctx->err = "msc_stride smaller than the logical frame"; return DABB_E_ARG; }
+            // device rows: [S*4][flen_pad] -> host [S][MAX_SUBCH][4][msc_stride]
+            for (int c = 0; c < 4; c++)
+                CK(cudaMemcpy2D(io->msc + ((size_t)k * 4 + c) * io->msc_stride, (size_t)DABB_MAX_SUBCH * 4 * io->msc_stride,
+                                sl.d_logical + (size_t)c * flen_pad, (size_t)4 * flen_pad, sl.flen, S, cudaMemcpyDeviceToHost));
+        }
+        if (io->sf) {
+            if (io->sf_stride < 5 * sl.flen) { ctx->err = "sf_stride smaller than the superframe"; return DABB_E_ARG; }
+            CK(cudaMemcpy2D(io->sf + (size_t)k * io->sf_stride, (size_t)DABB_MAX_SUBCH * io->sf_stride,
+                            sl.d_sf, (size_t)5 * flen_pad, 5 * sl.flen, S, cudaMemcpyDeviceToHost));
+        }
+    }
+    return DABB_OK;
+}
+
+int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes)
+{
+    if (!ctx || !host_out) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (what == 0) { const size_t n = (size_t)ctx->S * DABB_SOFT_PER_FRAME; CK(cudaMemcpy(host_out, ctx->d_soft, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
+    if (what == 1 && ctx->d_cir) { const size_t n = (size_t)ctx->S * TU * 4; CK(cudaMemcpy(host_out, ctx->d_cir, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
+    ctx->err = "tap not available (keep_taps = 0?)";
+    return DABB_E_STATE;
+}
+
+// ------------------------------------------------------------------------------------------------ stage-level API
+int dabb_ofdm_demod(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* prs_start, int32_t n, const int32_t* nco, int8_t* soft, float* r1, float* fc)
+{
+    if (!ctx || !iq || !prs_start || !soft || n < 1) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    OfdmParams op{}; op.iq = reinterpret_cast<const float2*>(iq); op.stride = stride; op.prs_start = prs_start; op.active = nullptr; op.soft = soft; op.soft_stride = DABB_SOFT_PER_FRAME;
+    op.r1 = reinterpret_cast<float2*>(r1); op.freqcorr = reinterpret_cast<float2*>(fc); op.snr = nullptr; op.n_frames = n;
+    op.groups = (fc || n >= 1024) ? 1 : (n >= 64 ? 5 : 25); op.sym_per_cta = 75 / op.groups;
+    int32_t* nco4 = nullptr;
+    if (nco) {
+        // expand {lp applied to PRS sample 0, Hz} to the 4-entry form of the pipeline (same increment for PRS and symbols)
+        std::vector<int32_t> h(2 * (size_t)n), h4(4 * (size_t)n);
+        CK(cudaMemcpy(h.data(), nco, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) { h4[4 * i] = h[2 * i]; h4[4 * i + 1] = h[2 * i + 1]; h4[4 * i + 2] = h[2 * i]; h4[4 * i + 3] = h[2 * i + 1]; }
+        CK(cudaMalloc((void**)&nco4, sizeof(int32_t) * 4 * n));
+        CK(cudaMemcpy(nco4, h4.data(), sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice));
+        op.nco = nco4;
+    }
+    launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, ctx->stream);
+    int rc = check_launch(ctx, "ofdm_demod_kernel");
+    if (nco4) { cudaStreamSynchronize(ctx->stream); cudaFree(nco4); }
+    return rc;
+}
+
+int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* win_start, int32_t n, int32_t* index_out, float* cir_out)
+{
+    if (!ctx || !iq || !win_start || !index_out || n < 1) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n;
+    launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
+    return check_launch(ctx, "find_index_kernel");
+}
+
+int dabb_viterbi(dabb_ctx* ctx, const int8_t* soft, int32_t n_cw, int32_t nbits, uint8_t* bits_out)
+{
+    if (!ctx || !soft || !bits_out || n_cw < 1 || nbits < 32 || (nbits % 32) || ((nbits + 6) % 6)) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    const int nsteps = nbits + 6, rw = vit_row_words(nsteps), ob = nbits / 8;
+    uint32_t* rows = nullptr; uint8_t* bytes = nullptr;
+    CK(cudaMalloc((void**)&rows, (size_t)n_cw * rw * 4));
+    CK(cudaMalloc((void**)&bytes, (size_t)n_cw * ob));
+    int rc = ensure_dec(ctx, vit_dec_bytes(n_cw, nsteps));
+    if (!rc) {
+        launch_sym_rows_from_soft(soft, n_cw, nsteps, rows, ctx->stream);
+        rc = check_launch(ctx, "sym_rows_from_soft_kernel");
+    }
+    if (!rc) {
+        ViterbiParams vp{}; vp.rows = rows; vp.row_words = rw; vp.n_cw = n_cw; vp.nsteps = nsteps; vp.nbits = nbits; vp.dec = ctx->d_dec; vp.out = bytes; vp.out_stride = ob; vp.prbs_words = nullptr; vp.valid = nullptr;
+        launch_viterbi(vp, ctx->stream);
+        rc = check_launch(ctx, "viterbi_kernel");
+    }
+    if (!rc) { launch_unpack_bits(bytes, ob, n_cw, nbits, bits_out, ctx->stream); rc = check_launch(ctx, "unpack_bits_kernel"); }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(rows); cudaFree(bytes);
+    return rc;
+}
+
+int dabb_fic_decode(dabb_ctx* ctx, const int8_t* soft, int32_t n_frames, uint8_t* fib_out, int32_t* crc_mask_out)
+{
+    if (!ctx || !soft || !fib_out || !crc_mask_out || n_frames < 1) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    uint32_t* rows = nullptr;
+    uint32_t* save = ctx->d_fic_rows;
+    if (n_frames > ctx->S) { CK(cudaMalloc((void**)&rows, (size_t)n_frames * 4 * vit_row_words(774) * 4)); ctx->d_fic_rows = rows; }
+    int rc = ensure_dec(ctx, vit_dec_bytes(n_frames * 4, 774));
+    if (!rc) rc = run_fic(ctx, soft, 9216, nullptr, n_frames, fib_out, crc_mask_out);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_fic_rows = save;
+    if (rows) cudaFree(rows);
+    return rc;
+}
+
+int dabb_msc_decode(dabb_ctx* ctx, const dabb_subchannel* sc, const int8_t* soft, int32_t n, uint8_t* bytes_out)
+{
+    if (!ctx || !sc || !soft || !bytes_out || n < 1) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    ProtProfile prof;
+    if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
+    const int frag = sc->length_cu * 64, nbits = 24 * prof.bitrate, nsteps = nbits + 6, rw = vit_row_words(nsteps), flen = 3 * prof.bitrate;
+    if (prof.in_bits > frag) { ctx->err = "protection profile needs more bits than the sub-channel holds"; return DABB_E_ARG; }
+    // de-puncture on the host side of the ABI? no: build the map, expand on the device with a gather, then the common path
+    std::vector<int16_t> map((size_t)nsteps * 4);
+    build_msc_map(*ctx->host, prof, map.data());
+    std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, nbits, w);
+    int16_t* d_map = nullptr; uint32_t* d_w = nullptr; uint32_t* rows = nullptr; int8_t* ring = nullptr; MscSlotState* d_sl = nullptr; int32_t* d_valid = nullptr;
+    CK(cudaMalloc((void**)&d_map, map.size() * 2)); CK(cudaMalloc((void**)&d_w, w.size() * 4)); CK(cudaMalloc((void**)&rows, (size_t)n * rw * 4));
+    CK(cudaMemcpy(d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    int rc = ensure_dec(ctx, vit_dec_bytes(n, nsteps));
+    // reuse the generic path: scatter the punctured softbits into mother-code order with a tiny kernel-free trick:
+    // cudaMemcpy of the map is enough because msc_prep_kernel needs ring state; instead expand here with thrust-free code
+    (void)ring; (void)d_sl; (void)d_valid;
+    if (!rc) {
+        // expand on device: one thread per (cif, step)
+        launch_msc_expand(soft, n, frag, d_map, nsteps, rows, rw, ctx->stream);
+        rc = check_launch(ctx, "msc_expand_kernel");
+    }
+    if (!rc) {
+        ViterbiParams vp{}; vp.rows = rows; vp.row_words = rw; vp.n_cw = n; vp.nsteps = nsteps; vp.nbits = nbits; vp.dec = ctx->d_dec; vp.out = bytes_out; vp.out_stride = flen; vp.prbs_words = d_w; vp.valid = nullptr;
+        launch_viterbi(vp, ctx->stream);
+        rc = check_launch(ctx, "viterbi_kernel");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_map); cudaFree(d_w); cudaFree(rows);
+    return rc;
+}
+
+int dabb_rs_superframes(dabb_ctx* ctx, uint8_t* sf, int32_t n, int32_t sf_len, int32_t* info)
+{
+    if (!ctx || !sf || !info || n < 1 || sf_len < 120 || (sf_len % 120)) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    launch_rs_superframes(sf, n, sf_len, info, ctx->dev.gf_exp, ctx->dev.gf_log, ctx->stream);
+    return check_launch(ctx, "rs_superframes_kernel");
+}
+
+int dabb_dev_alloc(dabb_ctx* ctx, size_t bytes, void** out) { if (!ctx || !out) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaMalloc(out, bytes)); return 0; }
+int dabb_dev_free(dabb_ctx* ctx, void* p) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(p)); return 0; }
+int dabb_memcpy_h2d(dabb_ctx* ctx, void* d, const void* s, size_t n) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+int dabb_memcpy_d2h(dabb_ctx* ctx, void* d, const void* s, size_t n) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost)); return 0; }
+
+} // extern "C"

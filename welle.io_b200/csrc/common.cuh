@@ -1,0 +1,66 @@
+// common.cuh — shared declarations of the libdab_b200 CUDA sources
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "ofdm_core.cuh"
+
+namespace dabb {
+
+// ---- device tables (built on the host by tables.cpp, uploaded once per context) ----
+struct DevTables {
+    const float2* tw_fwd;      // TwLayout::TOTAL entries, forward transform
+    const float2* tw_inv;      // inverse transform
+    const int16_t* invperm;    // [2048] bin -> logical carrier index 0..1535, -1 for unused bins (freq-interleaver.cpp:35-91)
+    const float2* prs_ref;     // [2048] PhaseReference::refTable (phasereference.cpp:45-51)
+    const float2* osc;         // [2 048 000] oscillator table (ofdm-processor.cpp:92-94)
+    const uint8_t* prbs;       // [9216+] energy-dispersal PRBS bits (fic-handler.cpp:62-71)
+    const int16_t* fic_map;    // [3096] mother-code position -> index into the 2304 punctured softbits or -1
+    const uint8_t* gf_exp;     // [512]
+    const uint8_t* gf_log;     // [256]
+};
+
+// ---- OFDM demod launch parameters ----
+struct OfdmParams {
+    const float2* iq; int64_t stride;            // complex samples
+    const int64_t* prs_start;                    // [n] first useful PRS sample, relative to iq + f*stride
+    const int32_t* nco;                          // [n][4] or nullptr: {phase applied to PRS sample 0, Hz (PRS), phase extrapolated to index 0 for the data symbols, Hz}
+    const int32_t* active;                       // [n] or nullptr: 0 = skip frame
+    int8_t* soft; int64_t soft_stride;           // per frame stride in bytes (>= 75*3072)
+    float2* r1;                                  // optional tap [n][75][1536]
+    float2* freqcorr;                            // optional [n][groups] partial CP correlation sums
+    int32_t* snr;                                // optional [n] get_snr value of the PRS
+    int n_frames; int groups; int sym_per_cta;   // groups * sym_per_cta == 75
+};
+
+struct SyncParams {
+    const float2* iq; int64_t stride;
+    const int64_t* win_start;                    // [n]
+    const int32_t* nco;                          // [n][2] or nullptr
+    const int32_t* active;
+    int32_t* index_out; float* cir_out; int n;
+};
+
+void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
+void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
+
+// ---- host-side table builders (tables.cpp) ----
+struct HostTables {
+    float2 tw_fwd[TwLayout::TOTAL], tw_inv[TwLayout::TOTAL];
+    int16_t perm[KC]; int16_t invperm[TU];
+    float2 prs_ref[TU];
+    uint8_t prbs[16384];
+    int16_t fic_map[3096];
+    uint8_t gf_exp[512], gf_log[256];
+    int8_t pcodes[24][32];
+};
+void build_host_tables(HostTables& t);
+void build_osc_table(float2* osc /* INPUT_RATE entries */);
+
+// protection profile -> (L, PI) blocks; returns punctured length or -1
+struct ProtProfile { int bitrate; int nblk; int L[4]; int PI[4]; int in_bits; };
+int make_prot_profile(int bitrate, int short_form, int uep_level, int eep_profile_a, int eep_level, ProtProfile& out);
+// mother-code map: for each of 4*(24*bitrate+6) positions the index into the punctured input or -1
+void build_msc_map(const HostTables& t, const ProtProfile& p, int16_t* map);
+
+} // namespace dabb

@@ -1,0 +1,334 @@
+// ofdm.cu — OFDM front-end kernels for sm_100a:
+//   ofdm_demod_kernel   NCO mix (optional) + 2048-point FFT per symbol + differential-QPSK demap with the frequency
+//                       de-interleaver scatter + guard-interval correlation (fine AFC) + PRS SNR estimate.
+//                       Replaces OFDMProcessor::getSamples mix loop (ofdm-processor.cpp:211-214), the CP correlation
+//                       (:436-442), OfdmDecoder::processPRS/decodeDataSymbol (ofdm-decoder.cpp:144-230), get_snr (:240-265)
+//   find_index_kernel   PhaseReference::findIndex, ThresholdBeforePeak (phasereference.cpp:73-97,212-253)
+//
+// HBM-bound by design: every input sample is read exactly once straight into registers with coalesced float2 loads
+// (the digit-reversed first pass makes lane-consecutive addresses), each softbit is written exactly once through a
+// 3 KB shared staging buffer with 16-byte stores.  Algorithmic bytes per frame: 76*2048*8 (+75*504*8 guard) in,
+// 75*3072 out.  One 128-thread CTA walks `sym_per_cta` consecutive symbols of one frame and keeps
+// the previous symbol's spectrum in registers (differential demodulation needs only that).
+#include "common.cuh"
+
+namespace dabb {
+
+namespace {
+
+struct __align__(16) OfdmSmem {
+    float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
+    float2 tw[TwLayout::TOTAL];      // ~16 KB per-stage twiddles
+    int8_t sbuf[3072];               // one symbol of softbits
+    float red[16];
+};
+
+template <bool NCO>
+__device__ __forceinline__ float2 fetch(const float2* __restrict__ src, int64_t idx, const float2* __restrict__ osc, int32_t lp0, int32_t ph)
+{
+    float2 v = __ldg(src + idx);
+    if (NCO) {
+        // localPhase applied to sample idx of this frame: (lp0 - idx*ph) mod 2 048 000  (ofdm-processor.cpp:211-213)
+        int64_t lp = ((int64_t)lp0 - idx * (int64_t)ph) % INPUT_RATE;
+        if (lp < 0) lp += INPUT_RATE;
+        const float2 o = __ldg(osc + lp);
+        v = cmul_<true>(v, o);   // std::complex product, separately rounded
+    }
+    return v;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red, int t)
+{
+    // fixed-order reduction: lane tree, then the four warp results added in warp order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+// FFT of the 2048 samples at src[w0 .. w0+2048) -> v[a+4b] = X[t + 128a + 512b].  Contains two __syncthreads.
+template <bool EXACT, bool INV, bool NCO>
+__device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ src, int64_t w0, float2 v[16], OfdmSmem& sm, int t,
+                                                    const float2* __restrict__ osc, int32_t lp0, int32_t ph)
+{
+    // pass A: two blocks n0 = t, t+128; loads are lane-consecutive for each c
+    float2 x[16];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[8 * h + c] = fetch<NCO>(src, w0 + t + 128 * h + 256 * c, osc, lp0, ph);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        float2 y[8];
+        passA_block<EXACT, INV>(x + 8 * h, y, sm.tw);
+        const int q = rev4x4(t + 128 * h);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm.xbuf[swz(8 * q + e)] = y[e];
+    }
+    __syncthreads();
+    // pass B
+    {
+        const int kk = t & 7, base = 128 * (t >> 3) + kk;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[swz(base + 8 * a + 32 * b)];
+        passB<EXACT, INV>(v, kk, sm.tw);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int a = 0; a < 4; a++) sm.xbuf[swz(base + 8 * a + 32 * b)] = v[a + 4 * b];
+    }
+    __syncthreads();
+    // pass C
+#pragma unroll
+    for (int c = 0; c < 16; c++) v[c] = sm.xbuf[swz(t + 128 * c)];
+    passC<EXACT, INV>(v, t, sm.tw);
+}
+
+template <bool EXACT, bool NCO>
+__global__ void __launch_bounds__(OFDM_THREADS, 4)
+ofdm_demod_kernel(DevTables tb, OfdmParams p)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    OfdmSmem& sm = *reinterpret_cast<OfdmSmem*>(smraw);
+    const int t = threadIdx.x;
+    const int f = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
+    if (p.active && !p.active[f]) return;
+
+    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.tw[i] = tb.tw_fwd[i];
+
+    const float2* src = p.iq + (int64_t)f * p.stride + p.prs_start[f];
+    // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
+    const int32_t lpP = (NCO && p.nco) ? p.nco[4 * f] : 0, phP = (NCO && p.nco) ? p.nco[4 * f + 1] : 0;
+    const int32_t lpS = (NCO && p.nco) ? p.nco[4 * f + 2] : 0, phS = (NCO && p.nco) ? p.nco[4 * f + 3] : 0;
+
+    // loop-invariant: logical carrier index of each owned bin (-1 = unused)
+    int inv[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) inv[s] = tb.invperm[t + 128 * slot_c(s)];
+    __syncthreads();
+
+    const int l_first = 1 + g * p.sym_per_cta, l_last = l_first + p.sym_per_cta;   // data symbols [l_first, l_last)
+    float2 prev[NSLOT];
+    float2 fc = make_float2(0.f, 0.f);
+
+    for (int l = l_first - 1; l < l_last; l++) {
+        // sample offsets relative to the first useful PRS sample: PRS occupies [0,2048); symbol l>=1 starts (guard
+        // first) at 2048 + (l-1)*2552 and its FFT window at +504 (ofdm-decoder.cpp:178-180)
+        const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
+        const int64_t w0 = (l == 0) ? 0 : s0 + TG;
+        const int32_t lp0 = l == 0 ? lpP : lpS, ph = l == 0 ? phP : phS;
+        float2 v[16];
+        fft2048_from_global<EXACT, false, NCO>(src, w0, v, sm, t, tb.osc, lp0, ph);
+
+        if (l >= l_first) {
+            // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
+            // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = 2048 + t + 128 r).
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int i = t + 128 * r;
+                if (i < TG) {
+                    const float2 a = fetch<NCO>(src, s0 + TU + i, tb.osc, lp0, ph), b = fetch<NCO>(src, s0 + i, tb.osc, lp0, ph);
+                    fc.x += a.x * b.x + a.y * b.y;
+                    fc.y += a.y * b.x - a.x * b.y;
+                }
+            }
+            // demap owned bins against the previous symbol, scatter softbits into logical order
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+                const float2 X = v[slot_c(s)];
+                if (inv[s] >= 0) {
+                    int8_t sre, sim; float2 r1;
+                    demap_one<EXACT>(X, prev[s], sre, sim, r1);
+                    sm.sbuf[inv[s]] = sre;
+                    sm.sbuf[KC + inv[s]] = sim;
+                    if (p.r1) p.r1[((int64_t)f * 75 + (l - 1)) * KC + inv[s]] = r1;
+                }
+                prev[s] = X;
+            }
+            __syncthreads();
+            // 3072 B -> global, 16 B per store
+            {
+                uint4* dst = reinterpret_cast<uint4*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
+                const uint4* s4 = reinterpret_cast<const uint4*>(sm.sbuf);
+                dst[t] = s4[t];
+                if (t < 64) dst[128 + t] = s4[128 + t];
+            }
+        } else {
+            // reference symbol only (the PRS when l == 0): keep its spectrum, estimate SNR from the PRS
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) prev[s] = v[slot_c(s)];
+            if (l == 0 && p.snr) {
+                // OfdmDecoder::get_snr method 1 (ofdm-decoder.cpp:246-265): noise bins 1094..1259 and 788..887,
+                // signal bins 1664..2047 and 0..383
+                float noise = 0.f, signal = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    const int bin = t + 128 * c;
+                    const float mag = (float)sqrt((double)v[c].x * (double)v[c].x + (double)v[c].y * (double)v[c].y);
+                    if ((bin >= 1094 && bin < 1260) || (bin >= 788 && bin < 888)) noise += mag;
+                    if (bin >= 1664 || bin < 384) signal += mag;
+                }
+                noise = block_sum(noise, sm.red, t);
+                signal = block_sum(signal, sm.red, t);
+                if (t == 0) {
+                    noise /= 266.f;
+                    const float dbs = 20.f * log10f((signal / 768.f + 1.0f) / 256.0f), dbn = 20.f * log10f((noise + 1.0f) / 256.0f);
+                    p.snr[f] = (int32_t)(int16_t)(dbs - dbn);
+                }
+            }
+        }
+    }
+    if (p.freqcorr) {
+        const float sx = block_sum(fc.x, sm.red, t), sy = block_sum(fc.y, sm.red, t);
+        if (t == 0) p.freqcorr[(int64_t)f * p.groups + g] = make_float2(sx, sy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// findIndex: one CTA per window.  FFT -> * conj(refTable) -> IFFT/2048 -> |.| -> 100-tap sliding maximum ->
+// threshold search.  The sum of |.| is accumulated sequentially by one thread in index order like the CPU loop
+// (phasereference.cpp:216-220) so that the `max > 3*sum/Tu` decision sees the same float.
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(16) SyncSmem {
+    OfdmSmem o;
+    float cir[TU];
+    float pk[TU];
+    float wmax[4]; int wmin[4];
+    float sum;
+};
+
+template <bool EXACT, bool NCO>
+__global__ void __launch_bounds__(OFDM_THREADS, 2)
+find_index_kernel(DevTables tb, SyncParams p)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    SyncSmem& sm = *reinterpret_cast<SyncSmem*>(smraw);
+    const int t = threadIdx.x, f = blockIdx.x;
+    if (p.active && !p.active[f]) return;
+    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_fwd[i];
+    __syncthreads();
+    const float2* src = p.iq + (int64_t)f * p.stride + p.win_start[f];
+    const int32_t lp0 = (NCO && p.nco) ? p.nco[2 * f] : 0, ph = (NCO && p.nco) ? p.nco[2 * f + 1] : 0;
+    float2 v[16];
+    fft2048_from_global<EXACT, false, NCO>(src, 0, v, sm.o, t, tb.osc, lp0, ph);
+    // res = X * conj(ref), staged to global-order in a second buffer: reuse cir/pk as a float2[2048] scratch
+    float2* scratch = reinterpret_cast<float2*>(sm.cir);   // cir+pk are contiguous: 2*2048 floats
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const int bin = t + 128 * c;
+        const float2 r = tb.prs_ref[bin];
+        const float cc = r.x, d = -r.y;
+        scratch[bin] = make_float2(fsub_<EXACT>(fmul_<EXACT>(v[c].x, cc), fmul_<EXACT>(v[c].y, d)),
+                                   fadd_<EXACT>(fmul_<EXACT>(v[c].x, d), fmul_<EXACT>(v[c].y, cc)));
+    }
+    __syncthreads();
+    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_inv[i];
+    // inverse FFT reading its input from shared memory: same pass structure (load pattern n0 + 256 c)
+    {
+        float2 x[16];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[8 * h + c] = scratch[t + 128 * h + 256 * c];
+        __syncthreads();   // twiddles loaded, scratch consumed
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float2 y[8];
+            passA_block<EXACT, true>(x + 8 * h, y, sm.o.tw);
+            const int q = rev4x4(t + 128 * h);
+#pragma unroll
+            for (int e = 0; e < 8; e++) sm.o.xbuf[swz(8 * q + e)] = y[e];
+        }
+        __syncthreads();
+        const int kk = t & 7, base = 128 * (t >> 3) + kk;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.o.xbuf[swz(base + 8 * a + 32 * b)];
+        passB<EXACT, true>(v, kk, sm.o.tw);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int a = 0; a < 4; a++) sm.o.xbuf[swz(base + 8 * a + 32 * b)] = v[a + 4 * b];
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 16; c++) v[c] = sm.o.xbuf[swz(t + 128 * c)];
+        passC<EXACT, true>(v, t, sm.o.tw);
+    }
+    // scale by 1/2048 (fft.cpp:146-158) and take the magnitude the way glibc's hypotf does (double sqrt, narrowed)
+    const float factor = 1.0f / 2048.0f;
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const float re = fmul_<true>(v[c].x, factor), im = fmul_<true>(v[c].y, factor);
+        const double m = __dsqrt_rn(__dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im)));
+        sm.cir[t + 128 * c] = (float)m;
+    }
+    __syncthreads();
+    if (p.cir_out) for (int i = t; i < TU; i += OFDM_THREADS) p.cir_out[(int64_t)f * TU + i] = sm.cir[i];
+    if (t == 0) { float s = 0.f; for (int i = 0; i < TU; i++) s = __fadd_rn(s, sm.cir[i]); sm.sum = s; }
+    // sliding maximum over 100 samples for i < 1948, 0 beyond (phasereference.cpp:222-238)
+    float gmax = -10000.f;
+    for (int i = t; i < TU; i += OFDM_THREADS) {
+        float m = 0.f;
+        if (i + 100 < TU) {
+            m = -10000.f;
+            for (int j = 0; j < 100; j++) m = fmaxf(m, sm.cir[i + j]);
+            gmax = fmaxf(gmax, m);
+        }
+        sm.pk[i] = m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
+    if ((t & 31) == 0) sm.wmax[t >> 5] = gmax;
+    __syncthreads();
+    gmax = fmaxf(fmaxf(sm.wmax[0], sm.wmax[1]), fmaxf(sm.wmax[2], sm.wmax[3]));
+    int best = 1 << 30;
+    // `3 * sum / Tu`: float 3*sum, then / (size_t Tu converted to float)
+    if (gmax > __fdiv_rn(__fmul_rn(3.0f, sm.sum), 2048.0f)) {
+        const float thresh = gmax / 2;
+        for (int i = t; i + 100 < TU; i += OFDM_THREADS) if (sm.pk[i + 100] > thresh) { best = min(best, i); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
+    if ((t & 31) == 0) sm.wmin[t >> 5] = best;
+    __syncthreads();
+    if (t == 0) {
+        best = min(min(sm.wmin[0], sm.wmin[1]), min(sm.wmin[2], sm.wmin[3]));
+        p.index_out[f] = best == (1 << 30) ? -1 : best;
+    }
+}
+
+} // namespace
+
+template <typename K> static void set_smem(K k, size_t bytes)
+{
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); done = true; }
+}
+
+void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)
+{
+    const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
+    const size_t sm = sizeof(OfdmSmem);
+    const bool nco = p.nco != nullptr;
+#define LAUNCH(E, N) do { set_smem(ofdm_demod_kernel<E, N>, sm); ofdm_demod_kernel<E, N><<<grid, block, sm, st>>>(tb, p); } while (0)
+    if (fft_mode == 0) { if (nco) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (nco) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+}
+
+void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st)
+{
+    const dim3 grid(p.n), block(OFDM_THREADS);
+    const size_t sm = sizeof(SyncSmem);
+    const bool nco = p.nco != nullptr;
+    (void)fft_mode;   // time sync always uses the exact arithmetic: its integer result feeds the closed loop
+    if (nco) { set_smem(find_index_kernel<true, true>, sm); find_index_kernel<true, true><<<grid, block, sm, st>>>(tb, p); }
+    else { set_smem(find_index_kernel<true, false>, sm); find_index_kernel<true, false><<<grid, block, sm, st>>>(tb, p); }
+}
+
+} // namespace dabb

@@ -1,0 +1,338 @@
+// viterbi.cu — batched K=7 rate-1/4 Viterbi for FIC and MSC codewords on sm_100a, plus the de-puncturing /
+// time-de-interleaving kernels that feed it.
+//
+//   fic_prep_kernel      FicHandler::processFicBlock/processFicInput de-puncturing (fic-handler.cpp:111-191)
+//   msc_collect_kernel   MscHandler::processMscBlock CIF slicing (msc-handler.cpp:129-158) into a residue-major ring
+//   msc_prep_kernel      DabAudio::run time de-interleaver (dab-audio.cpp:113-149) + EEP/UEP de-puncturing
+//                        (eep-protection.cpp:115-152, uep-protection.cpp:169-239)
+//   viterbi_kernel       Viterbi::deconvolve (viterbi.cpp:227-339) + energy de-dispersal (energy_dispersal.h:35-54,
+//                        fic-handler.cpp:199-201) + MSB-first byte pack (decoder_adapter.cpp:57-67)
+//   fic_crc_kernel       check_CRC_bits per FIB (MathHelper.h:53-80)
+//
+// viterbi_kernel: one codeword per thread, 64 path metrics packed 2x16 bit in 32 registers (viterbi_core.cuh), the
+// de-punctured symbols of 24 trellis steps per thread are staged into shared memory with cp.async.bulk (TMA, one
+// 128-byte copy per thread and stage, completion on an mbarrier, 3-stage ring), decision words go to HBM/L2 as
+// 8 bytes per step per codeword and are read back by the same thread for the traceback.
+// Issue-slot bound (integer ACS); HBM traffic is ~4+16 bytes per trellis step.
+#include "common.cuh"
+#include "viterbi_core.cuh"
+#include "viterbi.cuh"
+
+namespace dabb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t sym4(uint32_t w)   // four int8 softbits -> four clamp(s+127, 0, 255) symbols
+{
+    return __vsubus4(w ^ 0x80808080u, 0x01010101u);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ prep kernels
+// generic: soft int8 [n][nsteps*4] -> symbol rows
+__global__ void sym_rows_from_soft_kernel(const int8_t* __restrict__ soft, int n_cw, int nsteps, uint32_t* __restrict__ rows, int row_words)
+{
+    const int groups = row_words / 8;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_cw * groups) return;
+    const int cw = (int)(idx / groups), g = (int)(idx % groups);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(soft + (int64_t)cw * nsteps * 4);
+    uint32_t* dst = rows + (int64_t)cw * row_words + 8 * g;
+#pragma unroll
+    for (int s = 0; s < 6; s++) { const int st = 6 * g + s; dst[s] = st < nsteps ? sym4(src[st]) : 0x7F7F7F7Fu; }
+    dst[6] = 0; dst[7] = 0;
+}
+
+// FIC: codeword (frame f, block b) takes softbits [2304 b, 2304 b + 2304) of the frame's first three symbols
+__global__ void __launch_bounds__(128)
+fic_prep_kernel(const int8_t* __restrict__ soft, int64_t soft_stride, const int32_t* __restrict__ active,
+                const int16_t* __restrict__ fic_map, uint32_t* __restrict__ rows, int row_words)
+{
+    __shared__ __align__(16) int8_t seg[2304];
+    const int cw = blockIdx.x, f = cw >> 2, b = cw & 3, t = threadIdx.x;
+    if (active && !active[f]) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(soft + (int64_t)f * soft_stride + 2304 * b);
+    for (int i = t; i < 576; i += 128) reinterpret_cast<uint32_t*>(seg)[i] = src[i];
+    __syncthreads();
+    uint32_t* dst = rows + (int64_t)cw * row_words;
+    const int groups = row_words / 8;
+    for (int w = t; w < groups * 8; w += 128) {
+        const int g = w >> 3, s = w & 7, st = 6 * g + s;
+        uint32_t v = 0;
+        if (s < 6) {
+            v = 0x7F7F7F7Fu;
+            if (st < 774) {
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int m = fic_map[4 * st + k]; const int sb = m >= 0 ? seg[m] : 0; packed |= vit_sym(sb) << (8 * k); }
+                v = packed;
+            }
+        }
+        dst[w] = v;
+    }
+}
+
+// MSC collect: copy the sub-channel's slice of each of this frame's 4 CIFs into the de-interleaver ring, residue-major:
+// ring[(stream*slots + slot)][cif mod 20][r][j] = softbit (start_cu*64 + r + 16 j) of that CIF
+__global__ void __launch_bounds__(128)
+msc_collect_kernel(MscCollectParams p)
+{
+    extern __shared__ __align__(16) int8_t seg[];
+    const int s = blockIdx.x / 4, c = blockIdx.x % 4, t = threadIdx.x;
+    if (p.active && !p.active[s]) return;
+    const MscSlotState st = p.slots[s * p.n_slots + p.slot];
+    if (!st.enabled) return;
+    const int frag = st.frag;
+    // CIF c of this frame = symbols 4+18c .. 21+18c -> softbits [(3+18c)*3072, +55296)
+    const int8_t* src = p.soft + (int64_t)s * p.soft_stride + (int64_t)(3 + 18 * c) * 3072 + (int64_t)st.start_cu * 64;
+    for (int i = t; i < frag / 4; i += 128) reinterpret_cast<uint32_t*>(seg)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    __syncthreads();
+    const int slice = (int)((st.cif_count + c) % MSC_RING);
+    int8_t* dst = p.ring + ((int64_t)s * MSC_RING + slice) * p.ring_pitch;
+    const int per = frag / 16;
+    for (int o = t; o < frag; o += 128) { const int r = o / per, j = o % per; dst[o] = seg[r + 16 * j]; }
+}
+
+// MSC prep: one CTA per (stream, CIF c).  Gathers the time-de-interleaved fragment into shared memory
+// (out[i] = CIF[n - (16 - map[i & 15])][i], dab-audio.cpp:113-143) and writes the de-punctured symbol row.
+__constant__ int c_deint_delay[16] = {16, 8, 12, 4, 14, 6, 10, 2, 15, 7, 11, 3, 13, 5, 9, 1};   // 16 - map[r]
+__global__ void __launch_bounds__(128)
+msc_prep_kernel(MscPrepParams p)
+{
+    extern __shared__ __align__(16) int8_t frag_s[];
+    const int s = blockIdx.x / 4, c = blockIdx.x % 4, t = threadIdx.x;
+    if (p.active && !p.active[s]) return;
+    const MscSlotState st = p.slots[s * p.n_slots + p.slot];
+    if (!st.enabled) return;
+    const int64_t n = st.cif_count + c;           // index (since selection) of the CIF being completed
+    if (n < 16) return;                           // de-interleaver not yet filled (dab-audio.cpp:146-149)
+    const int frag = st.frag, per = frag / 16;
+    const int8_t* ring = p.ring + (int64_t)s * MSC_RING * p.ring_pitch;
+    for (int o = t; o < frag; o += 128) {
+        const int r = o / per, j = o % per;
+        const int slice = (int)((n - c_deint_delay[r]) % MSC_RING);
+        frag_s[r + 16 * j] = ring[(int64_t)slice * p.ring_pitch + o];
+    }
+    __syncthreads();
+    const int cw = s * 4 + c;
+    uint32_t* dst = p.rows + (int64_t)cw * p.row_words;
+    const int groups = p.row_words / 8, nsteps = p.nsteps;
+    const int16_t* map = p.map;
+    for (int w = t; w < groups * 8; w += 128) {
+        const int g = w >> 3, q = w & 7, stp = 6 * g + q;
+        uint32_t v = 0;
+        if (q < 6) {
+            v = 0x7F7F7F7Fu;
+            if (stp < nsteps) {
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int m = map[4 * stp + k]; const int sb = m >= 0 ? frag_s[m] : 0; packed |= vit_sym(sb) << (8 * k); }
+                v = packed;
+            }
+        }
+        dst[w] = v;
+    }
+    if (t == 0 && p.valid) p.valid[cw] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------ the decoder
+constexpr int VIT_THREADS = 128;
+constexpr int VIT_STAGES = 3;
+constexpr int VIT_ROW_PITCH = 144;      // 128 B of symbols + 16 B pad: 16-byte reads of 8 consecutive rows hit 32 distinct banks
+constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
+
+struct __align__(16) VitSmem {
+    unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];
+    uint64_t full[VIT_STAGES];
+};
+
+__global__ void __launch_bounds__(VIT_THREADS, 4)
+viterbi_kernel(ViterbiParams p)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    VitSmem& sm = *reinterpret_cast<VitSmem*>(smraw);
+    const int t = threadIdx.x;
+    const int cw = blockIdx.x * VIT_THREADS + t;
+    const bool have = cw < p.n_cw;
+    const int groups = p.nsteps / 6;                 // 6 steps per 32-byte group, 4 groups per 128-byte stage
+    const int nstages = (groups + 3) / 4;
+    const unsigned char* row = reinterpret_cast<const unsigned char*>(p.rows + (int64_t)(have ? cw : 0) * p.row_words);
+
+    if (t == 0) { for (int s = 0; s < VIT_STAGES; s++) mbar_init(&sm.full[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    // prologue: fill the ring
+    for (int s = 0; s < VIT_STAGES && s < nstages; s++) {
+        if (t == 0) mbar_expect_tx(&sm.full[s], VIT_THREADS * 128);
+        bulk_g2s(&sm.stage[s][t * VIT_ROW_PITCH], row + (int64_t)s * 128, 128, &sm.full[s]);
+    }
+
+    uint32_t Q[32];
+    vit_init(Q);
+    uint2* dec = p.dec + (int64_t)blockIdx.x * p.nsteps * VIT_THREADS + t;
+
+    for (int s = 0; s < nstages; s++) {
+        const int buf = s % VIT_STAGES;
+        mbar_wait(&sm.full[buf], (s / VIT_STAGES) & 1);
+        vit_normalize(Q);
+        const uint4* my = reinterpret_cast<const uint4*>(&sm.stage[buf][t * VIT_ROW_PITCH]);
+#pragma unroll 1
+        for (int gq = 0; gq < 4; gq++) {
+            const int g = 4 * s + gq;
+            if (g >= groups) break;
+            const uint4 a = my[2 * gq], b = my[2 * gq + 1];
+            const uint32_t w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+            uint32_t d[12];
+            vit_six_steps(Q, w, d);
+            if (have) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) dec[(int64_t)(6 * g + k) * VIT_THREADS] = make_uint2(d[2 * k], d[2 * k + 1]);
+            }
+        }
+        __syncthreads();   // every thread is done with this buffer's phase before it is re-armed
+        if (s + VIT_STAGES < nstages) {
+            if (t == 0) mbar_expect_tx(&sm.full[buf], VIT_THREADS * 128);
+            bulk_g2s(&sm.stage[buf][t * VIT_ROW_PITCH], row + (int64_t)(s + VIT_STAGES) * 128, 128, &sm.full[buf]);
+        }
+    }
+    if (!have) return;
+    if (p.valid && !p.valid[cw]) return;
+    // traceback from state 0, skipping the 6 tail steps (viterbi.cpp:313-339); bit t of the output is MSB-first in byte t/8
+    uint32_t state = 0, acc = 0;
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
+    const uint32_t* prbs = p.prbs_words;
+    for (int tt = p.nbits - 1; tt >= 0; tt--) {
+        const uint2 d = dec[(int64_t)(tt + 6) * VIT_THREADS];
+        const uint32_t word = (state & 32) ? d.y : d.x;
+        const uint32_t k = (word >> (state & 31)) & 1u;
+        state = (state >> 1) | (k << 5);
+        acc |= k << (8 * ((tt >> 3) & 3) + 7 - (tt & 7));
+        if ((tt & 31) == 0) { out[tt >> 5] = prbs ? acc ^ prbs[tt >> 5] : acc; acc = 0; }
+    }
+}
+
+// one thread per frame: CRC of the 12 FIBs (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80)
+__global__ void fic_crc_kernel(const uint8_t* __restrict__ fibs, const int32_t* __restrict__ active, int n_frames, int32_t* __restrict__ mask_out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    if (active && !active[f]) { mask_out[f] = 0; return; }
+    int32_t mask = 0;
+    for (int fib = 0; fib < 12; fib++) {
+        const uint8_t* b = fibs + ((int64_t)f * 12 + fib) * 32;
+        uint32_t reg = 0xFFFF;
+        for (int i = 0; i < 32; i++) {
+            uint32_t byte = b[i];
+            if (i >= 30) byte ^= 0xFF;
+            reg ^= byte << 8;
+#pragma unroll
+            for (int k = 0; k < 8; k++) reg = (reg & 0x8000) ? ((reg << 1) ^ 0x1021) & 0xFFFF : (reg << 1) & 0xFFFF;
+        }
+        if (reg == 0) mask |= 1 << fib;
+    }
+    mask_out[f] = mask;
+}
+
+// packed bytes -> one bit per byte (stage-level API output format of Viterbi::deconvolve)
+__global__ void unpack_bits_kernel(const uint8_t* __restrict__ bytes, int64_t stride, int n_cw, int nbits, uint8_t* __restrict__ bits)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_cw * nbits) return;
+    const int cw = (int)(idx / nbits), b = (int)(idx % nbits);
+    bits[idx] = (bytes[(int64_t)cw * stride + (b >> 3)] >> (7 - (b & 7))) & 1;
+}
+
+// stage-level API helper: punctured softbits [n][frag] -> symbol rows (EEP/UEP de-puncturing only)
+__global__ void msc_expand_kernel(const int8_t* __restrict__ soft, int n, int frag, const int16_t* __restrict__ map, int nsteps, uint32_t* __restrict__ rows, int row_words)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * row_words) return;
+    const int cw = (int)(idx / row_words), w = (int)(idx % row_words), g = w >> 3, q = w & 7, stp = 6 * g + q;
+    uint32_t v = 0;
+    if (q < 6) {
+        v = 0x7F7F7F7Fu;
+        if (stp < nsteps) {
+            uint32_t packed = 0;
+            for (int k = 0; k < 4; k++) { const int m = map[4 * stp + k]; const int sb = m >= 0 ? soft[(int64_t)cw * frag + m] : 0; packed |= vit_sym(sb) << (8 * k); }
+            v = packed;
+        }
+    }
+    rows[idx] = v;
+}
+
+} // namespace
+
+void launch_msc_expand(const int8_t* soft, int n, int frag, const int16_t* map, int nsteps, uint32_t* rows, int row_words, cudaStream_t st)
+{
+    const int64_t total = (int64_t)n * row_words;
+    msc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(soft, n, frag, map, nsteps, rows, row_words);
+}
+
+int vit_row_words(int nsteps) { const int groups = nsteps / 6; return ((groups + 3) / 4) * 4 * 8; }
+
+void launch_sym_rows_from_soft(const int8_t* soft, int n_cw, int nsteps, uint32_t* rows, cudaStream_t st)
+{
+    const int rw = vit_row_words(nsteps);
+    const int64_t total = (int64_t)n_cw * (rw / 8);
+    sym_rows_from_soft_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(soft, n_cw, nsteps, rows, rw);
+}
+
+void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint32_t* rows, cudaStream_t st)
+{
+    fic_prep_kernel<<<n_frames * 4, 128, 0, st>>>(soft, soft_stride, active, tb.fic_map, rows, vit_row_words(774));
+}
+
+void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
+void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st) { msc_prep_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
+
+void launch_viterbi(const ViterbiParams& p, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmem)); attr = true; }
+    const int blocks = (p.n_cw + VIT_THREADS - 1) / VIT_THREADS;
+    viterbi_kernel<<<blocks, VIT_THREADS, sizeof(VitSmem), st>>>(p);
+}
+
+size_t vit_dec_bytes(int n_cw, int nsteps) { return (size_t)((n_cw + VIT_THREADS - 1) / VIT_THREADS) * nsteps * VIT_THREADS * sizeof(uint2); }
+
+void launch_fic_crc(const uint8_t* fibs, const int32_t* active, int n_frames, int32_t* mask_out, cudaStream_t st)
+{
+    fic_crc_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(fibs, active, n_frames, mask_out);
+}
+
+void launch_unpack_bits(const uint8_t* bytes, int64_t stride, int n_cw, int nbits, uint8_t* bits, cudaStream_t st)
+{
+    const int64_t total = (int64_t)n_cw * nbits;
+    unpack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bytes, stride, n_cw, nbits, bits);
+}
+
+} // namespace dabb

@@ -1,0 +1,167 @@
+// viterbi_core.cuh — per-thread K=7 rate-1/4 Viterbi add-compare-select, one codeword per thread, all 64 path
+// metrics in 32 registers as packed signed 16-bit pairs (VIMNMX.S16x2 with two predicate outputs + VIADD.16x2 on
+// sm_100a).
+//
+// Semantics reproduced from the reference (backend/viterbi.cpp): polynomials 0155 0117 0123 0155 (:35-36); branch
+// metric = sum_k (sym_k or 255 - sym_k) (:248-261); new[2i] = min(old[i] + m, old[i+32] + 1020 - m),
+// new[2i+1] = min(old[i] + 1020 - m, old[i+32] + m) with the decision bit (m_a - m_b) > 0, i.e. ties keep the old[i]
+// branch (:263-275); decision bit n of step t belongs to new state n (:276-278); start metrics 63 / 0 (:342-354).
+// The reference's renormalisation (:104-120) subtracts a uniform value and cannot change a decision; here the
+// minimum is subtracted every 24 steps so that metrics stay inside [0, 32767).
+//
+// Register layout.  Layout L_b pairs, in one 32-bit register, the two states that differ in bit b (low half: bit
+// b = 0).  An ACS step maps L_b -> L_{b+1} with plain SIMD (two butterflies per pair of registers, no data movement);
+// L_5 pairs butterfly partners, so that step duplicates halves with PRMT and lands in L_0.  Six consecutive steps
+// (nsteps = nbits + 6 is always a multiple of 6) are unrolled with compile-time register indices.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VIT_HD __host__ __device__ __forceinline__
+#else
+#define VIT_HD inline
+#endif
+
+namespace dabb {
+
+#define VIT_POLY0 0155
+#define VIT_POLY1 0117
+#define VIT_POLY2 0123   /* fourth polynomial == first */
+
+VIT_HD constexpr int vit_parity(unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return (int)(x & 1u); }
+// branch pattern of butterfly i (0..31): bit k = parity((2i) & poly_k), k = 0,1,2 (poly_3 == poly_0)
+VIT_HD constexpr int vit_pat(int i) { return vit_parity((2 * i) & VIT_POLY0) | (vit_parity((2 * i) & VIT_POLY1) << 1) | (vit_parity((2 * i) & VIT_POLY2) << 2); }
+VIT_HD constexpr int vit_remove_bit(int s, int b) { return ((s >> (b + 1)) << b) | (s & ((1 << b) - 1)); }
+VIT_HD constexpr int vit_insert_zero(int j, int b) { return ((j >> b) << (b + 1)) | (j & ((1 << b) - 1)); }
+
+// per-half signed 16-bit minimum; pl/ph = (a_half <= b_half)
+VIT_HD uint32_t vibmin16(uint32_t a, uint32_t b, bool& ph, bool& pl)
+{
+#if defined(__CUDA_ARCH__)
+    return __vibmin_s16x2(a, b, &ph, &pl);
+#else
+    const int16_t al = (int16_t)(a & 0xFFFF), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xFFFF), bh = (int16_t)(b >> 16);
+    pl = al <= bl; ph = ah <= bh;
+    return (uint32_t)(uint16_t)(pl ? al : bl) | ((uint32_t)(uint16_t)(ph ? ah : bh) << 16);
+#endif
+}
+VIT_HD uint32_t dup_lo(uint32_t r)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(r, 0, 0x1010);
+#else
+    return (r & 0xFFFF) | (r << 16);
+#endif
+}
+VIT_HD uint32_t dup_hi(uint32_t r)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(r, 0, 0x3232);
+#else
+    return (r >> 16) | (r & 0xFFFF0000u);
+#endif
+}
+VIT_HD uint32_t vminu16x2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vminu2(a, b);
+#else
+    const uint32_t al = a & 0xFFFF, ah = a >> 16, bl = b & 0xFFFF, bh = b >> 16;
+    return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+
+// branch metrics for the eight patterns from one step's four symbols (bytes s0..s3 of w, each 0..255)
+VIT_HD void vit_metrics(uint32_t w, uint32_t E[8])
+{
+    const uint32_t s0 = w & 0xFF, s1 = (w >> 8) & 0xFF, s2 = (w >> 16) & 0xFF, s3 = w >> 24;
+    const uint32_t A = s0 + s3, B = s1, C = s2;
+    const uint32_t a[2] = {A, 510u - A}, b[2] = {B, 255u - B}, c[2] = {C, 255u - C};
+#pragma unroll
+    for (int p = 0; p < 8; p++) E[p] = a[p & 1] + b[(p >> 1) & 1] + c[(p >> 2) & 1];
+}
+
+// One ACS step from layout L_B to L_{(B+1)%6}.  Q: 32 packed metric registers; dlo/dhi: decision bits of new states
+// 0..31 / 32..63.
+template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], uint32_t& dlo, uint32_t& dhi)
+{
+    uint32_t N[32];
+    dlo = 0; dhi = 0;
+    if constexpr (B < 5) {
+        constexpr int delta = vit_pat(1 << B);   // pattern change when butterfly bit B flips
+        uint32_t MC[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) MC[p] = E[p] | (E[p ^ delta] << 16);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int ilo = vit_insert_zero(j, B);            // butterfly with bit B = 0; its SIMD partner is ilo + (1<<B)
+            const int ra = vit_remove_bit(ilo, B), rb = vit_remove_bit(ilo + 32, B);
+            const int p = vit_pat(ilo);
+            const uint32_t m0 = Q[ra] + MC[p], m1 = Q[rb] + MC[p ^ 7], m2 = Q[ra] + MC[p ^ 7], m3 = Q[rb] + MC[p];
+            bool ph, pl;
+            const int ne = 2 * ilo, nehi = ne + (2 << B);     // new states in the low / high half of the even result
+            N[vit_remove_bit(ne, B + 1)] = vibmin16(m0, m1, ph, pl);
+            if (!pl) { if (ne < 32) dlo |= 1u << ne; else dhi |= 1u << (ne - 32); }
+            if (!ph) { if (nehi < 32) dlo |= 1u << nehi; else dhi |= 1u << (nehi - 32); }
+            N[vit_remove_bit(ne + 1, B + 1)] = vibmin16(m2, m3, ph, pl);
+            if (!pl) { if (ne + 1 < 32) dlo |= 1u << (ne + 1); else dhi |= 1u << (ne + 1 - 32); }
+            if (!ph) { if (nehi + 1 < 32) dlo |= 1u << (nehi + 1); else dhi |= 1u << (nehi + 1 - 32); }
+        }
+    } else {
+        // L_5: register i = (old[i], old[i+32]); result register i = (new[2i], new[2i+1]) = layout L_0
+        uint32_t XC[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) XC[p] = E[p] | (E[p ^ 7] << 16);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const int p = vit_pat(i);
+            const uint32_t x = dup_lo(Q[i]) + XC[p];        // (old[i] + m,        old[i] + 1020 - m)
+            const uint32_t y = dup_hi(Q[i]) + XC[p ^ 7];    // (old[i+32] + 1020-m, old[i+32] + m)
+            bool ph, pl;
+            N[i] = vibmin16(x, y, ph, pl);
+            const int ne = 2 * i;
+            if (!pl) { if (ne < 32) dlo |= 1u << ne; else dhi |= 1u << (ne - 32); }
+            if (!ph) { if (ne + 1 < 32) dlo |= 1u << (ne + 1); else dhi |= 1u << (ne + 1 - 32); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; r++) Q[r] = N[r];
+}
+
+// start metrics in layout L_0: register r = (state 2r, state 2r+1); 63 everywhere, 0 for state 0
+VIT_HD void vit_init(uint32_t (&Q)[32])
+{
+#pragma unroll
+    for (int r = 0; r < 32; r++) Q[r] = 63u | (63u << 16);
+    Q[0] = 0u | (63u << 16);
+}
+
+// subtract the minimum over all 64 states from every state (uniform shift: no decision changes)
+VIT_HD void vit_normalize(uint32_t (&Q)[32])
+{
+    uint32_t m = Q[0];
+#pragma unroll
+    for (int r = 1; r < 32; r++) m = vminu16x2(m, Q[r]);
+    const uint32_t lo = m & 0xFFFF, hi = m >> 16;
+    const uint32_t mn = lo < hi ? lo : hi;
+    const uint32_t sub = mn | (mn << 16);
+#pragma unroll
+    for (int r = 0; r < 32; r++) Q[r] -= sub;
+}
+
+// six steps: words w[0..5] hold the symbols, dec[2*s], dec[2*s+1] receive the decision words
+VIT_HD void vit_six_steps(uint32_t (&Q)[32], const uint32_t w[6], uint32_t dec[12])
+{
+    uint32_t E[8];
+    vit_metrics(w[0], E); vit_acs<0>(Q, E, dec[0], dec[1]);
+    vit_metrics(w[1], E); vit_acs<1>(Q, E, dec[2], dec[3]);
+    vit_metrics(w[2], E); vit_acs<2>(Q, E, dec[4], dec[5]);
+    vit_metrics(w[3], E); vit_acs<3>(Q, E, dec[6], dec[7]);
+    vit_metrics(w[4], E); vit_acs<4>(Q, E, dec[8], dec[9]);
+    vit_metrics(w[5], E); vit_acs<5>(Q, E, dec[10], dec[11]);
+}
+
+// soft bit (int8, 0 = punctured) -> decoder symbol clamp(s + 127, 0, 255)  (viterbi.cpp:232-237)
+VIT_HD uint32_t vit_sym(int s) { int v = s + 127; return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+} // namespace dabb
