@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — DAB transmission frames/s through the full B200 decode chain (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W           # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU path on the host cores
+
+A "step" = one pass of the hot path over one batch: every one of the `--batch` independent ensemble streams of a rank
+decodes its next 96 ms transmission frame (time sync -> 76 FFTs + DQPSK demap -> FIC Viterbi + CRC -> one 96 kbit/s
+EEP-3A DAB+ sub-channel: time de-interleave, Viterbi, energy dispersal, RS(120,110) + Fire code + AU CRC).
+Workload = BASELINE.json configs[3]/[4]: batch = 8192 frames per GPU, streams sharded across ranks with no data-path
+collective (weak scaling); a one-int32 NCCL broadcast of the work descriptor is the only communication.
+
+value    whole-job frames/s with the IQ already resident in HBM (CUDA events on the library's stream, max over ranks)
+e2e      the same through dabb_process() with HOST (pinned) IQ buffers: H2D of every step's samples and D2H of the
+         results inside the timed region
+roofline dominant kernel (ofdm_demod_kernel) timed alone with CUDA events: algorithmic bytes / duration vs the
+         measured HBM copy bandwidth in MEASURED_PEAKS.json
+cpu_baseline  the unmodified reference backend (oracle/_ref, KISS-FFT build) on the host cores, bounded sample
+"""
+import argparse
+import importlib.util
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+TF, TU, TS, TNULL = 196608, 2048, 2552, 2656
+RING_FRAMES = 5
+BUF_LEN = (RING_FRAMES + 1) * TF + 4096
+BITRATE, SUBCH_CU = 96, 72
+# bytes one frame must move through the OFDM kernel: PRS (2048) + 75 symbols x 2552 samples read once, 75 x 3072 softbits written
+OFDM_BYTES_PER_FRAME = (TU + 75 * TS) * 8 + 75 * 3072
+SURVEY_BYTES_PER_FRAME = 1803264   # also counts the null symbol, which this kernel never reads
+ACS_PER_FRAME = (4 * 774 + 4 * 2310) * 64
+
+
+def load_pkg():
+    d = os.path.join(ROOT, "welle.io_b200")
+    if "welle_io_b200" in sys.modules:
+        return sys.modules["welle_io_b200"]
+    spec = importlib.util.spec_from_file_location("welle_io_b200", os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["welle_io_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML, ~2 ms per sample)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # noqa
+            self.err = repr(e)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "error": self.err}
+
+
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    n_frames, seed = args
+    import dabtx
+    from oracle.bind import Ref
+    r = Ref()
+    tx = dabtx.DabTx(seed=seed)
+    iq = tx.frames(n_frames)
+    e = r.e2e(iq, disable_coarse=True, select_at_fib=24, dump_path=f"/tmp/bench_ref_{os.getpid()}.msc")
+    # seconds = wall time from RadioReceiver::restart until the input was exhausted (teardown/drain waits excluded)
+    return e["frames_done"], float(e["seconds"]), int(e["fibs"][:, 0].sum()), len(e["fibs"])
+
+
+def run_reference_cpu(n_procs, frames_per_proc):
+    """the reference's own RadioReceiver (3+ threads per stream) on `n_procs` concurrent streams; frames/s = decoded frames / wall time"""
+    ctx = mp.get_context("fork")
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2); os.dup2(devnull, 2)      # the reference logs to stderr
+    try:
+        t0 = time.time()
+        with ctx.Pool(n_procs) as pool:
+            out = pool.map(_ref_worker, [(frames_per_proc, 0x1000 + i) for i in range(n_procs)])
+        wall = time.time() - t0
+    finally:
+        os.dup2(saved, 2); os.close(devnull)
+    frames = sum(o[0] for o in out)
+    busy = max(o[1] for o in out)
+    return frames / busy, frames, busy, wall, sum(o[2] for o in out), sum(o[3] for o in out)
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.bind import Ref
+    if not Ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libwelle_ref.so missing (built only where /root/reference exists)"}))
+        return
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores // 3, 48))       # one reference receiver runs ~3 busy threads (OFDM, decoder, DabAudio)
+    vals = []
+    for it in range(a.warmup + a.steps):
+        v, frames, busy, wall, ok, tot = run_reference_cpu(n_procs, a.ref_frames)
+        if it >= a.warmup:
+            vals.append((v, busy))
+    v = float(np.mean([x[0] for x in vals]))
+    ms = float(np.mean([x[1] for x in vals]) * 1e3)
+    sample = f"{n_procs} concurrent reference RadioReceiver instances x {a.ref_frames} synthetic frames each (FIC + one 96 kbit/s EEP-3A DAB+ sub-channel), KISS-FFT build"
+    line = {"impl": "reference", "metric": "dab_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int", "data": "synthetic",
+            "config": config_dict(a, None),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(a, groups):
+    return {"workload": f"batch={a.batch} independent Mode-I ensembles per GPU, 1 transmission frame per stream per step: full chain sync+76xFFT+DQPSK -> FIC Viterbi+CRC -> 96 kbit/s EEP-3A DAB+ sub-channel (time de-interleave, Viterbi, RS(120,110)+Fire code) [BASELINE.json configs[3]/[4]]",
+            "batch_frames_per_gpu": a.batch, "subchannel": "96 kbit/s EEP 3-A, 72 CU, DAB+", "snr_db": a.snr, "fft_mode": "exact(KISS-bit-identical)" if a.fft_mode == 0 else "fma",
+            "parallelism": f"streams sharded over {a.gpus} GPU(s), no data-path collective", "l2_policy": "inputs (12.9 GB/step at batch 8192) far exceed the 126 MB L2; no flush needed",
+            "ofdm_groups": groups}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def make_rings(n_distinct):
+    import dabtx
+    rings = []
+    for i in range(n_distinct):
+        _, ring = dabtx.periodic_ring(0xB200 + i, RING_FRAMES)
+        rings.append(ring)
+    return np.stack(rings)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=8192, help="streams (= frames per step) per GPU")
+    ap.add_argument("--e2e-batch", type=int, default=1024)
+    ap.add_argument("--snr", type=float, default=20.0)
+    ap.add_argument("--fft-mode", type=int, default=0)
+    ap.add_argument("--distinct", type=int, default=8)
+    ap.add_argument("--ref-frames", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    if a.warmup < 6:
+        a.warmup = 6      # acquisition + 16-CIF de-interleaver fill + superframe sync must be over before the timed region
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    # ---- CPU baseline first (rank 0, N == 1), before CUDA is initialised in this process (the workers are forked)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            from oracle.bind import Ref
+            if Ref.available():
+                cores = os.cpu_count() or 1
+                n_procs = max(1, min(cores // 3, 48))
+                log(f"cpu baseline: {n_procs} reference receivers x {a.ref_frames} frames")
+                v, frames, busy, wall, ok, tot = run_reference_cpu(n_procs, a.ref_frames)
+                cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
+                       "sample": f"{n_procs} concurrent unmodified reference RadioReceiver instances x {a.ref_frames} synthetic frames (same chain: FIC + one 96 kbit/s DAB+ sub-channel), KISS-FFT build, {busy:.1f} s",
+                       "fib_crc_ok": ok, "fibs": tot}
+                log(f"cpu baseline done: {v:.1f} frames/s")
+        except Exception as e:  # noqa
+            cpu = {"error": repr(e)}
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = load_pkg()
+    S = a.batch
+    # work descriptor: (first stream id of this rank) broadcast from rank 0 — the only collective on the path
+    desc = torch.tensor([S], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.broadcast(desc, 0)
+        S = int(desc.item())
+    hbm_peak, peak_src, sm_max = measured_peaks()
+
+    # ---- synthetic input: `distinct` periodic 5-frame rings, replicated to S stream buffers with per-stream AWGN
+    rings = torch.from_numpy(make_rings(a.distinct).view(np.float32).reshape(a.distinct, RING_FRAMES * TF, 2)).to(dev)
+    sig_pow = float((rings[:, 3000:190000] ** 2).sum(-1).mean())
+    sigma = (sig_pow / (10 ** (a.snr / 10)) / 2) ** 0.5
+    buf = torch.empty((S, BUF_LEN, 2), dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(0x5EED + rank)
+    CH = 256
+    for s0 in range(0, S, CH):
+        n = min(CH, S - s0)
+        idx = (torch.arange(s0, s0 + n, device=dev) + rank * S) % a.distinct
+        blk = rings[idx] + torch.randn((n, RING_FRAMES * TF, 2), device=dev, generator=gen) * sigma
+        buf[s0:s0 + n, :RING_FRAMES * TF] = blk
+        buf[s0:s0 + n, RING_FRAMES * TF:] = blk[:, :BUF_LEN - RING_FRAMES * TF]
+        del blk
+    torch.cuda.synchronize()
+    log(f"input ready: {S} streams x {BUF_LEN} samples")
+
+    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+    ctx.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
+    ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)
+
+    def buf_start_for(call):
+        n = call + 1                      # call k decodes frame k+1 (frame 0 is consumed by the acquisition)
+        return np.full(S, RING_FRAMES * TF * (n // RING_FRAMES), np.int64) if call > 0 else np.zeros(S, np.int64)
+
+    call = 0
+    for _ in range(a.warmup):
+        ctx.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(call), BUF_LEN); call += 1
+    ctx.sync()
+    log("warm-up done")
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.05)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(a.steps):
+        ctx.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(call), BUF_LEN); call += 1
+    e1.record(ext)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    sampler.stop_flag = True
+    ms = float(t.item())
+    value = world * S * a.steps / (ms * 1e-3)
+
+    log(f"timed region done: {ms:.2f} ms for {a.steps} steps")
+    # ---- validity of the timed work: one more step through the synchronous API, every stream must decode
+    out = ctx.process(buf, BUF_LEN, buf_start_for(call), BUF_LEN, msc_stride=3 * BITRATE); call += 1
+    r = out["results"]
+    ok_frames = int((r["status"] == 0).sum()); fib_ok = int(sum(bin(int(m)).count("1") for m in r["fib_crc_mask"]))
+    lf = int(r["n_logical"][:, 0].sum()); rs_unc = int((r["rs_uncorr_mask"][:, 0] != 0).sum()); rs_ev = int(r["n_rs_events"][:, 0].sum())
+    check = {"frames_decoded": ok_frames, "streams": S, "fib_crc_ok": fib_ok, "fibs": 12 * S, "logical_frames": lf, "rs_attempts": rs_ev, "rs_uncorrectable_streams": rs_unc}
+
+    # ---- per-kernel device times over K more steady-state steps (CUDA events on the library's stream after every launch)
+    ctx.profile(True)
+    for _ in range(a.steps):
+        ctx.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(call), BUF_LEN); call += 1
+    ctx.sync()
+    ctx.profile(False)
+    prof = ctx.profile_read()
+    clocks = sampler.summary()
+    f_sm = (clocks["sm_mhz"] or sm_max) * 1e6
+    kern = {k: {"ms_per_step": v["ms"] / a.steps, "launches_per_step": v["n"] / a.steps} for k, v in prof.items()}
+    kms = prof["ofdm_demod_kernel"]["ms"] / prof["ofdm_demod_kernel"]["n"]
+    ach = S * OFDM_BYTES_PER_FRAME / (kms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_ofdm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            per = json.load(open(tp)).get("dram_bytes_per_frame")
+            traffic = per * S if per else None
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "ofdm_demod_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "peak_source": peak_src, "bytes_per_launch": S * OFDM_BYTES_PER_FRAME, "ms_per_launch": kms,
+                "frac_with_survey_bytes": S * SURVEY_BYTES_PER_FRAME / (kms * 1e-3) / 1e9 / hbm_peak,
+                "share_of_step": kms / (sum(v["ms"] for v in prof.values()) / a.steps)}
+    # Viterbi issue-slot figure: 4 int-ops per ACS against 148 SM x 4 schedulers x 32 lanes x f_SM
+    vms = (prof["viterbi_kernel(FIC)"]["ms"] + prof["viterbi_kernel(MSC)"]["ms"]) / a.steps
+    acs_s = S * ACS_PER_FRAME / (vms * 1e-3)
+    peak_ops = 148 * 4 * 32 * f_sm
+    vit = {"kernel": "viterbi_kernel (FIC + MSC launches)", "bound": "issue", "achieved": acs_s * 4 / 1e12, "peak": peak_ops / 1e12, "unit": "Tint-op/s",
+           "frac": acs_s * 4 / peak_ops, "acs_per_s": acs_s, "ms_per_step": vms, "f_sm_mhz": f_sm / 1e6,
+           "note": "4 int-ops per add-compare-select (SURVEY 8d); the kernel packs two states per 32-bit lane-op"}
+
+    log("kernel profile done")
+    # ---- e2e: host (pinned) IQ -> dabb_process -> host results
+    e2e = None
+    if not a.no_e2e:
+        Se = min(a.e2e_batch, S)
+        ctx_e = pkg.Context(n_streams=Se, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+        ctx_e.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
+        host = torch.empty((Se, BUF_LEN, 2), dtype=torch.float32).pin_memory()
+        host.copy_(buf[:Se])
+        WIN = TF + 8192        # samples shipped per stream per step (one frame + sync margin)
+        ce = 0
+
+        def step_e2e(c):
+            n = c + 1
+            if c == 0:
+                return ctx_e.process(host, BUF_LEN, np.zeros(Se, np.int64), 3 * TF, iq_is_host=True, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE), 3 * TF
+            off = (n % RING_FRAMES) * TF
+            base = host.data_ptr() + off * 8
+            return ctx_e.process(base, BUF_LEN, np.full(Se, n * TF, np.int64), min(WIN, BUF_LEN - off), iq_is_host=True, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE), min(WIN, BUF_LEN - off)
+        for _ in range(a.warmup):
+            step_e2e(ce); ce += 1
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); h2d = 0
+        for _ in range(a.steps):
+            o, nsamp = step_e2e(ce); ce += 1; h2d += Se * nsamp * 8
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        d2h = o["results"].nbytes + o["fibs"].nbytes + o["msc"].nbytes + o["sf"].nbytes
+        okf = int((o["results"]["status"] == 0).sum())
+        e2e = {"value": world * Se * a.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h, "batch_frames_per_gpu": Se,
+               "frames_decoded_last_step": okf, "note": "host pinned cf32 -> dabb_process (H2D + all kernels + D2H of results/FIBs/logical frames/superframes); PCIe-bound"}
+        ctx_e.close(); del host
+
+    if rank == 0:
+        line = {"metric": "dab_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int16x2", "data": "synthetic",
+                "config": config_dict(a, None), "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline, "roofline_viterbi": vit,
+                "cpu_baseline": cpu, "check": check, "kernels": kern}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

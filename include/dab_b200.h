@@ -139,6 +139,11 @@ int dabb_sync(dabb_ctx* ctx);
 void* dabb_cuda_stream(dabb_ctx* ctx);              /* cudaStream_t of the context */
 int64_t dabb_kernel_launches(const dabb_ctx* ctx);  /* number of CUDA kernels this context has launched */
 
+/* per-kernel device timing: while enabled, one CUDA event is recorded on the context's stream after every kernel launch;
+ * dabb_profile_read returns {"kernel": {"ms": total, "n": launches}, ...} as JSON text */
+int dabb_profile(dabb_ctx* ctx, int32_t enable);
+int dabb_profile_read(dabb_ctx* ctx, char* json_out, size_t cap);
+
 /* taps (valid after a dabb_process when keep_taps=1): 0 = softbits int8 [n_streams][75*3072],
  * 1 = CIR float [n_streams][2048] (RadioControllerInterface::onNewImpulseResponse) */
 int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes);

@@ -423,12 +423,19 @@ int ref_e2e_run(const float* iq, long nsamples, int disable_coarse, int select_a
 {
     g_last = E2EResult();
     DABParams p(1);
-    GatedMemInput in(iq, (size_t)nsamples, p.T_F);
-    E2EController ri; NullProgramme ph;
+    /* The session is deliberately leaked: tearing the reference receiver down can dead-lock (DabAudio's destructor
+     * clears `running` and notifies without holding the mutex its worker checks `running` under, dab-audio.cpp:87-93 vs
+     * :123-128, so the notification can be lost).  The OFDM thread has already exited by then; the remaining worker
+     * threads idle on their condition variables. */
+    struct Session {
+        GatedMemInput in; E2EController ri; NullProgramme ph; RadioReceiver rx;
+        Session(const float* iq, long n, long tf, RadioReceiverOptions rro) : in(iq, (size_t)n, tf), rx(ri, in, rro) {}
+    };
     RadioReceiverOptions rro; rro.disableCoarseCorrector = disable_coarse != 0; rro.decodeTII = false;
     auto t0 = std::chrono::steady_clock::now();
+    Session* S = new Session(iq, nsamples, p.T_F, rro);
+    GatedMemInput& in = S->in; E2EController& ri = S->ri; NullProgramme& ph = S->ph; RadioReceiver& rx = S->rx;
     {
-        RadioReceiver rx(ri, in, rro);
         ri.rx = &rx; ri.in = &in; ri.ph = &ph; ri.dump = msc_dump_path ? msc_dump_path : ""; ri.select_at_fib = select_at_fib; ri.keep_cir = keep_cir;
         rx.restart(false);
         while (!ri.failed.load() && in.is_ok()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -443,7 +450,6 @@ int ref_e2e_run(const float* iq, long nsamples, int disable_coarse, int select_a
             std::this_thread::sleep_for(std::chrono::milliseconds(1));
         }
         in.stopped = true;
-        rx.stop();
     }
     g_last.fibs = ri.fibs; g_last.rs = ph.rs_events; g_last.corr = ri.corr; g_last.snr = ri.snr; g_last.cirs = ri.cirs;
     g_last.sync_true = ri.sync_true; g_last.sync_false = ri.sync_false; g_last.select_ok = ri.select_ok ? 1 : 0;

@@ -178,7 +178,9 @@ def fig0_2(sid, subch_id, ascty=63):
 class DabTx:
     """One ensemble with one DAB+ sub-channel (EEP) in CUs [start_cu, start_cu + size)."""
 
-    def __init__(self, seed=0xDAB, bitrate=96, profile_a=True, level=3, start_cu=0, subch_id=0, sid=0x1001, amplitude=0.1):
+    def __init__(self, seed=0xDAB, bitrate=96, profile_a=True, level=3, start_cu=0, subch_id=0, sid=0x1001, amplitude=0.1, period_sf=0):
+        self.period_sf = period_sf          # >0: content repeats every period_sf superframes (= 5*period_sf CIFs): an endless periodic stream
+        self._sf_cache, self._fill_cache = {}, {}
         self.rng = np.random.default_rng(seed)
         self.bitrate, self.profile_a, self.level = bitrate, profile_a, level
         self.start_cu, self.size_cu = start_cu, eep_cu(bitrate, profile_a, level)
@@ -216,6 +218,9 @@ class DabTx:
         for i in range(6):
             ln = a[i + 1] - a[i]
             body = self.rng.integers(0, 256, ln - 2, dtype=np.uint8)
+            # first syntactic element = ID_END (111): the reference's AAC decoder (out of scope) rejects the AU cleanly instead of
+            # mis-parsing random bytes (which can make it throw, dabplus_decoder.cpp:460), and no PAD is signalled (:148-149)
+            body[0] |= 0xE0
             c = crc16(body)
             if bad_au is not None and i == bad_au:
                 c ^= 0xFFFF
@@ -227,7 +232,14 @@ class DabTx:
     def _next_logical(self):
         flen = 3 * self.bitrate
         if len(self._sf_queue) < flen:
-            sf = self.superframe(); self.superframes.append(sf)
+            k = len(self.superframes)
+            if self.period_sf:
+                if k % self.period_sf not in self._sf_cache:
+                    self._sf_cache[k % self.period_sf] = self.superframe()
+                sf = self._sf_cache[k % self.period_sf]
+            else:
+                sf = self.superframe()
+            self.superframes.append(sf)
             self._sf_queue = np.concatenate([self._sf_queue, sf])
         fr, self._sf_queue = self._sf_queue[:flen], self._sf_queue[flen:]
         return fr
@@ -254,7 +266,13 @@ class DabTx:
         fic = np.tile(self.ficblk, 4)
         cifs = []
         for _ in range(4):
-            cif = self.rng.integers(0, 2, 864 * 64, dtype=np.uint8)
+            if self.period_sf:
+                key = self.cif_count % (5 * self.period_sf)
+                if key not in self._fill_cache:
+                    self._fill_cache[key] = self.rng.integers(0, 2, 864 * 64, dtype=np.uint8)
+                cif = self._fill_cache[key].copy()
+            else:
+                cif = self.rng.integers(0, 2, 864 * 64, dtype=np.uint8)
             sub = self._next_cif_subch()
             cif[self.start_cu * 64: self.start_cu * 64 + len(sub)] = sub
             cifs.append(cif)
@@ -293,6 +311,15 @@ def add_awgn(iq, snr_db, seed, signal_power=None):
 def freq_shift(iq, hz):
     n = np.arange(len(iq))
     return (iq * np.exp(2j * np.pi * hz * n / 2048000.0)).astype(np.complex64)
+
+
+def periodic_ring(seed, n_frames=5, **kw):
+    """n_frames (multiple of 5) frames of a steady-state stream that repeats seamlessly: frames [n, 2n) of a
+    transmitter whose content has period n frames (time interleaver and superframes wrap consistently)."""
+    assert n_frames % 5 == 0
+    tx = DabTx(seed=seed, period_sf=4 * n_frames // 5, **kw)
+    sig = np.concatenate([tx.modulate(tx.frame_bits()) for _ in range(2 * n_frames)])
+    return tx, sig[n_frames * TF:].astype(np.complex64)
 
 
 def fib_bytes(tx):

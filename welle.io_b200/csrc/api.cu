@@ -65,6 +65,9 @@ struct dabb_ctx {
     dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
     int groups = 1;
     const int32_t** d_info_tab = nullptr;
+    // optional per-kernel timing: one event after every launch, durations = differences of consecutive events
+    bool prof = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_name; size_t prof_used = 0;
+    std::vector<std::pair<std::string, std::pair<double, long>>> prof_acc;
 };
 
 namespace {
@@ -82,12 +85,41 @@ template <typename T> int dalloc(dabb_ctx* ctx, T** p, size_t n, bool zero = tru
     return 0;
 }
 
+void prof_mark(dabb_ctx* ctx, const char* what)
+{
+    if (!ctx->prof) return;
+    if (ctx->prof_used == ctx->prof_ev.size()) {
+        if (ctx->prof_ev.size() >= 16384) return;
+        cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->prof_ev.push_back(e); ctx->prof_name.push_back(what);
+    }
+    ctx->prof_name[ctx->prof_used] = what;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used++], ctx->stream);
+}
+
 int check_launch(dabb_ctx* ctx, const char* what)
 {
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return DABB_E_CUDA; }
+    prof_mark(ctx, what);
     return 0;
+}
+
+void prof_collect(dabb_ctx* ctx)
+{
+    if (ctx->prof_used < 2) { ctx->prof_used = 0; return; }
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 1; i < ctx->prof_used; i++) {
+        const char* nm = ctx->prof_name[i];
+        if (!strcmp(nm, "__step_begin")) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[i - 1], ctx->prof_ev[i]) != cudaSuccess) continue;
+        bool found = false;
+        for (auto& a : ctx->prof_acc) if (a.first == nm) { a.second.first += ms; a.second.second++; found = true; break; }
+        if (!found) ctx->prof_acc.push_back({nm, {ms, 1}});
+    }
+    ctx->prof_used = 0;
 }
 
 void pack_prbs_words(const uint8_t* bits, int nbits, std::vector<uint32_t>& w)
@@ -374,6 +406,7 @@ void dabb_destroy(dabb_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocs) cudaFree(p);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_fibs) cudaFreeHost(ctx->h_fibs);
@@ -386,7 +419,7 @@ void dabb_destroy(dabb_ctx* ctx)
 
 void* dabb_cuda_stream(dabb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t dabb_kernel_launches(const dabb_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); if (ctx->prof) prof_collect(ctx); return 0; }
 
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first, int32_t count, int64_t pos)
 {
@@ -487,6 +520,7 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         iq = ctx->d_iq_stage; stride = io->buf_len;
     }
     CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+    prof_mark(ctx, "__step_begin");
     const int tb = 128, gb = (S + tb - 1) / tb;
     acquire_kernel<<<(S + 31) / 32, 32, 0, ctx->stream>>>(ctx->d_state, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, S);
     if ((rc = check_launch(ctx, "acquire_kernel"))) return rc;
@@ -560,6 +594,33 @@ int dabb_process(dabb_ctx* ctx, const dabb_io* io)
         }
     }
     return DABB_OK;
+}
+
+int dabb_profile(dabb_ctx* ctx, int32_t enable)
+{
+    if (!ctx) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (!enable && ctx->prof) prof_collect(ctx);
+    if (enable && !ctx->prof) { ctx->prof_acc.clear(); ctx->prof_used = 0; }
+    ctx->prof = enable != 0;
+    return 0;
+}
+
+int dabb_profile_read(dabb_ctx* ctx, char* out, size_t cap)
+{
+    if (!ctx || !out || cap < 3) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    std::string j = "{";
+    for (size_t i = 0; i < ctx->prof_acc.size(); i++) {
+        char b[256];
+        snprintf(b, sizeof b, "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", i ? ", " : "", ctx->prof_acc[i].first.c_str(), ctx->prof_acc[i].second.first, ctx->prof_acc[i].second.second);
+        j += b;
+    }
+    j += "}";
+    if (j.size() + 1 > cap) return DABB_E_ARG;
+    memcpy(out, j.c_str(), j.size() + 1);
+    return 0;
 }
 
 int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes)

@@ -58,7 +58,7 @@ class IO(C.Structure):
 
 EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_select_subchannel",
            "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_cuda_stream", "dabb_kernel_launches",
-           "dabb_read_tap", "dabb_ofdm_demod", "dabb_find_index", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
+           "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
            "dabb_rs_superframes", "dabb_dev_alloc", "dabb_dev_free", "dabb_memcpy_h2d", "dabb_memcpy_d2h"]
 
 
@@ -181,6 +181,15 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.dabb_sync(self.h))
+
+    def profile(self, enable):
+        self._ck(self.lib.dabb_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        import json
+        buf = C.create_string_buffer(16384)
+        self._ck(self.lib.dabb_profile_read(self.h, buf, C.c_size_t(16384)))
+        return json.loads(buf.value.decode())
 
     # ---- receiver control
     def reset(self, first=0, count=None, pos=0):
