@@ -42,7 +42,7 @@ std::string g_create_error;
 } // namespace
 
 struct dabb_ctx {
-    int device = 0; cudaStream_t stream = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
+    int device = 0; cudaStream_t stream = nullptr; cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0;
     HostTables* host = nullptr; DevTables dev{};
@@ -346,6 +346,9 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream/event creation failed"; return fail(DABB_E_CUDA); }
     ctx->host = new HostTables();
     build_host_tables(*ctx->host);
     const int S = ctx->S;
@@ -387,6 +390,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         return fail(rc);
     if (ctx->keep_taps && (rc = dalloc(ctx, &ctx->d_cir, (size_t)S * TU))) return fail(rc);
     if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, 774)))) return fail(rc);
+    { void* q = nullptr; if (cudaMalloc(&q, vit_dec_bytes(S * 4, 774)) != cudaSuccess) { ctx->err = "cudaMalloc(FIC decisions)"; return fail(DABB_E_NOMEM); } ctx->allocs.push_back(q); ctx->d_dec_fic = (uint2*)q; }
     ctx->h_slots.assign((size_t)S * ctx->n_slots, MscSlotState{});
     // info arrays of unconfigured slots are never read (finalize skips disabled slots)
     cudaHostAlloc((void**)&ctx->h_results, sizeof(dabb_frame_result) * S, cudaHostAllocDefault);
@@ -405,6 +409,7 @@ void dabb_destroy(dabb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
@@ -412,6 +417,9 @@ void dabb_destroy(dabb_ctx* ctx)
     if (ctx->h_fibs) cudaFreeHost(ctx->h_fibs);
     if (ctx->h_msc) cudaFreeHost(ctx->h_msc);
     if (ctx->h_sf) cudaFreeHost(ctx->h_sf);
+    if (ctx->ev_ofdm) cudaEventDestroy(ctx->ev_ofdm);
+    if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx->host;
     delete ctx;
@@ -484,17 +492,17 @@ int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
     return check_launch(ctx, "set_slot_kernel");
 }
 
-static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc)
+static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc, cudaStream_t st, uint2* dec)
 {
     int rc;
-    launch_fic_prep(ctx->dev, soft, soft_stride, active, n_frames, ctx->d_fic_rows, ctx->stream);
+    launch_fic_prep(ctx->dev, soft, soft_stride, active, n_frames, ctx->d_fic_rows, st);
     if ((rc = check_launch(ctx, "fic_prep_kernel"))) return rc;
     ViterbiParams vp{};
     vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
-    vp.dec = ctx->d_dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
-    launch_viterbi(vp, ctx->stream);
+    vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
+    launch_viterbi(vp, st);
     if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
-    launch_fic_crc(fibs, active, n_frames, crc, ctx->stream);
+    launch_fic_crc(fibs, active, n_frames, crc, st);
     return check_launch(ctx, "fic_crc_kernel");
 }
 
@@ -535,7 +543,16 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     op.r1 = nullptr; op.freqcorr = ctx->d_fc; op.snr = ctx->d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
     launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, ctx->stream);
     if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
-    if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc))) return rc;
+    // FIC chain on the second stream (serial on the main stream while per-kernel profiling is on)
+    const bool overlap = !ctx->prof;
+    if (overlap) {
+        CK(cudaEventRecord(ctx->ev_ofdm, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_ofdm, 0));
+        if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc, ctx->stream2, ctx->d_dec_fic))) return rc;
+        CK(cudaEventRecord(ctx->ev_fic, ctx->stream2));
+    } else {
+        if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc, ctx->stream, ctx->d_dec_fic))) return rc;
+    }
     const int32_t* h_info[DABB_MAX_SUBCH] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < ctx->n_slots; k++) {
         auto& sl = ctx->slot[k];
@@ -560,6 +577,7 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         if ((rc = check_launch(ctx, "superframe_kernel"))) return rc;
     }
     // slot_info pointer table lives in a small device array rewritten each call
+    if (overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fic, 0));
     CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, ctx->stream));
     finalize_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_slots, ctx->n_slots, S, ctx->groups, ctx->d_fc, ctx->d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
     return check_launch(ctx, "finalize_kernel");
@@ -699,7 +717,7 @@ int dabb_fic_decode(dabb_ctx* ctx, const int8_t* soft, int32_t n_frames, uint8_t
     uint32_t* save = ctx->d_fic_rows;
     if (n_frames > ctx->S) { CK(cudaMalloc((void**)&rows, (size_t)n_frames * 4 * vit_row_words(774) * 4)); ctx->d_fic_rows = rows; }
     int rc = ensure_dec(ctx, vit_dec_bytes(n_frames * 4, 774));
-    if (!rc) rc = run_fic(ctx, soft, 9216, nullptr, n_frames, fib_out, crc_mask_out);
+    if (!rc) rc = run_fic(ctx, soft, 9216, nullptr, n_frames, fib_out, crc_mask_out, ctx->stream, ctx->d_dec);
     cudaStreamSynchronize(ctx->stream);
     ctx->d_fic_rows = save;
     if (rows) cudaFree(rows);

@@ -23,18 +23,25 @@ struct __align__(16) OfdmSmem {
     float red[16];
 };
 
-template <bool NCO>
-__device__ __forceinline__ float2 fetch(const float2* __restrict__ src, int64_t idx, const float2* __restrict__ osc, int32_t lp0, int32_t ph)
+// ---- NCO (ofdm-processor.cpp:211-214): sample idx of the frame is multiplied by osc[(lp0 - idx*ph) mod 2 048 000].
+// Per symbol one 64-bit modulo gives the phase of the thread's first sample; the other samples follow by modular
+// subtraction of per-CTA constants (stride 128 and 256 samples).  `mix` is CTA-uniform; lp0 == ph == 0 means the
+// oscillator is (1, 0) for every sample and the multiplication is skipped.
+struct Nco {
+    int32_t lp0, ph, d128, d256;   // d = (stride * ph) mod RATE
+    bool mix;
+};
+__device__ __forceinline__ int32_t mod_rate64(int64_t v) { v %= INPUT_RATE; if (v < 0) v += INPUT_RATE; return (int32_t)v; }
+__device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
 {
-    float2 v = __ldg(src + idx);
-    if (NCO) {
-        // localPhase applied to sample idx of this frame: (lp0 - idx*ph) mod 2 048 000  (ofdm-processor.cpp:211-213)
-        int64_t lp = ((int64_t)lp0 - idx * (int64_t)ph) % INPUT_RATE;
-        if (lp < 0) lp += INPUT_RATE;
-        const float2 o = __ldg(osc + lp);
-        v = cmul_<true>(v, o);   // std::complex product, separately rounded
-    }
-    return v;
+    Nco n; n.lp0 = lp0; n.ph = ph; n.mix = (lp0 != 0) || (ph != 0);
+    n.d128 = n.mix ? mod_rate64(128 * (int64_t)ph) : 0; n.d256 = n.mix ? mod_rate64(256 * (int64_t)ph) : 0;
+    return n;
+}
+__device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
+__device__ __forceinline__ float2 mix_sample(float2 v, const float2* __restrict__ osc, int32_t lp)
+{
+    return cmul_<true>(v, __ldg(osc + lp));   // std::complex product, separately rounded
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red, int t)
@@ -48,43 +55,70 @@ __device__ __forceinline__ float block_sum(float v, float* red, int t)
     return red[0] + red[1] + red[2] + red[3];
 }
 
+// per-thread loop-invariant shared-memory indices of the exchange buffer (see swz() in ofdm_core.cuh)
+struct XIdx {
+    int a[2];     // pass A: swz(8 * rev(n0)) for the two blocks; element e lives at a[h] ^ e
+    int b[4];     // pass B: swz(base) ^ 8a; element (a, b) lives at b[a] + 32 b
+    int kk;
+};
+__device__ __forceinline__ XIdx make_xidx(int t)
+{
+    XIdx x;
+    x.a[0] = swz(8 * rev4x4(t)); x.a[1] = swz(8 * rev4x4(t + 128));
+    x.kk = t & 7;
+    const int sb = swz(128 * (t >> 3) + x.kk);
+#pragma unroll
+    for (int a = 0; a < 4; a++) x.b[a] = sb ^ (8 * a);
+    return x;
+}
+// pass C: position t + 128 c -> (t ^ X(c)) + 128 c with the compile-time constant X(c) = swizzle bits of 128 c
+__device__ __forceinline__ constexpr int xc_of(int c) { return ((c & 1) << 3) | (((c >> 1) & 1) << 2) | ((c >> 2) & 3); }
+
 // FFT of the 2048 samples at src[w0 .. w0+2048) -> v[a+4b] = X[t + 128a + 512b].  Contains two __syncthreads.
-template <bool EXACT, bool INV, bool NCO>
-__device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ src, int64_t w0, float2 v[16], OfdmSmem& sm, int t,
-                                                    const float2* __restrict__ osc, int32_t lp0, int32_t ph)
+template <bool EXACT, bool INV>
+__device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ src, int64_t w0, float2 v[16], OfdmSmem& sm, int t, const XIdx& xi,
+                                                    const float2* __restrict__ osc, const Nco& nco)
 {
     // pass A: two blocks n0 = t, t+128; loads are lane-consecutive for each c
     float2 x[16];
+    const float2* p = src + w0 + t;
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) x[8 * h + c] = fetch<NCO>(src, w0 + t + 128 * h + 256 * c, osc, lp0, ph);
+        for (int c = 0; c < 8; c++) x[8 * h + c] = __ldg(p + 128 * h + 256 * c);
+    if (nco.mix) {
+        int32_t lp = mod_rate64((int64_t)nco.lp0 - (w0 + t) * (int64_t)nco.ph);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            x[c] = mix_sample(x[c], osc, lp);
+            x[8 + c] = mix_sample(x[8 + c], osc, sub_mod(lp, nco.d128));
+            lp = sub_mod(lp, nco.d256);
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         float2 y[8];
         passA_block<EXACT, INV>(x + 8 * h, y, sm.tw);
-        const int q = rev4x4(t + 128 * h);
 #pragma unroll
-        for (int e = 0; e < 8; e++) sm.xbuf[swz(8 * q + e)] = y[e];
+        for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
     }
     __syncthreads();
     // pass B
     {
-        const int kk = t & 7, base = 128 * (t >> 3) + kk;
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[swz(base + 8 * a + 32 * b)];
-        passB<EXACT, INV>(v, kk, sm.tw);
+            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[xi.b[a] + 32 * b];
+        passB<EXACT, INV>(v, xi.kk, sm.tw);
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int a = 0; a < 4; a++) sm.xbuf[swz(base + 8 * a + 32 * b)] = v[a + 4 * b];
+            for (int a = 0; a < 4; a++) sm.xbuf[xi.b[a] + 32 * b] = v[a + 4 * b];
     }
     __syncthreads();
     // pass C
 #pragma unroll
-    for (int c = 0; c < 16; c++) v[c] = sm.xbuf[swz(t + 128 * c)];
+    for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
     passC<EXACT, INV>(v, t, sm.tw);
 }
 
@@ -102,8 +136,9 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
 
     const float2* src = p.iq + (int64_t)f * p.stride + p.prs_start[f];
     // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
-    const int32_t lpP = (NCO && p.nco) ? p.nco[4 * f] : 0, phP = (NCO && p.nco) ? p.nco[4 * f + 1] : 0;
-    const int32_t lpS = (NCO && p.nco) ? p.nco[4 * f + 2] : 0, phS = (NCO && p.nco) ? p.nco[4 * f + 3] : 0;
+    const Nco ncoP = make_nco((NCO && p.nco) ? p.nco[4 * f] : 0, (NCO && p.nco) ? p.nco[4 * f + 1] : 0);
+    const Nco ncoS = make_nco((NCO && p.nco) ? p.nco[4 * f + 2] : 0, (NCO && p.nco) ? p.nco[4 * f + 3] : 0);
+    const XIdx xi = make_xidx(t);
 
     // loop-invariant: logical carrier index of each owned bin (-1 = unused)
     int inv[NSLOT];
@@ -120,20 +155,26 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         // first) at 2048 + (l-1)*2552 and its FFT window at +504 (ofdm-decoder.cpp:178-180)
         const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
         const int64_t w0 = (l == 0) ? 0 : s0 + TG;
-        const int32_t lp0 = l == 0 ? lpP : lpS, ph = l == 0 ? phP : phS;
+        const Nco& nco = l == 0 ? ncoP : ncoS;
         float2 v[16];
-        fft2048_from_global<EXACT, false, NCO>(src, w0, v, sm, t, tb.osc, lp0, ph);
+        fft2048_from_global<EXACT, false>(src, w0, v, sm, t, xi, tb.osc, nco);
 
         if (l >= l_first) {
             // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
             // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = 2048 + t + 128 r).
+            {
+                int32_t lpa = 0, lpb = 0;
+                if (nco.mix) { lpb = mod_rate64((int64_t)nco.lp0 - (s0 + t) * (int64_t)nco.ph); lpa = mod_rate64((int64_t)nco.lp0 - (s0 + TU + t) * (int64_t)nco.ph); }
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int i = t + 128 * r;
-                if (i < TG) {
-                    const float2 a = fetch<NCO>(src, s0 + TU + i, tb.osc, lp0, ph), b = fetch<NCO>(src, s0 + i, tb.osc, lp0, ph);
-                    fc.x += a.x * b.x + a.y * b.y;
-                    fc.y += a.y * b.x - a.x * b.y;
+                for (int r = 0; r < 4; r++) {
+                    const int i = t + 128 * r;
+                    if (i < TG) {
+                        float2 a = __ldg(src + s0 + TU + i), b = __ldg(src + s0 + i);
+                        if (nco.mix) { a = mix_sample(a, tb.osc, lpa); b = mix_sample(b, tb.osc, lpb); }
+                        fc.x += a.x * b.x + a.y * b.y;
+                        fc.y += a.y * b.x - a.x * b.y;
+                    }
+                    if (nco.mix) { lpa = sub_mod(lpa, nco.d128); lpb = sub_mod(lpb, nco.d128); }
                 }
             }
             // demap owned bins against the previous symbol, scatter softbits into logical order
@@ -212,9 +253,10 @@ find_index_kernel(DevTables tb, SyncParams p)
     for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_fwd[i];
     __syncthreads();
     const float2* src = p.iq + (int64_t)f * p.stride + p.win_start[f];
-    const int32_t lp0 = (NCO && p.nco) ? p.nco[2 * f] : 0, ph = (NCO && p.nco) ? p.nco[2 * f + 1] : 0;
+    const Nco nco = make_nco((NCO && p.nco) ? p.nco[2 * f] : 0, (NCO && p.nco) ? p.nco[2 * f + 1] : 0);
+    const XIdx xi = make_xidx(t);
     float2 v[16];
-    fft2048_from_global<EXACT, false, NCO>(src, 0, v, sm.o, t, tb.osc, lp0, ph);
+    fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb.osc, nco);
     // res = X * conj(ref), staged to global-order in a second buffer: reuse cir/pk as a float2[2048] scratch
     float2* scratch = reinterpret_cast<float2*>(sm.cir);   // cir+pk are contiguous: 2*2048 floats
 #pragma unroll
@@ -239,24 +281,22 @@ find_index_kernel(DevTables tb, SyncParams p)
         for (int h = 0; h < 2; h++) {
             float2 y[8];
             passA_block<EXACT, true>(x + 8 * h, y, sm.o.tw);
-            const int q = rev4x4(t + 128 * h);
 #pragma unroll
-            for (int e = 0; e < 8; e++) sm.o.xbuf[swz(8 * q + e)] = y[e];
+            for (int e = 0; e < 8; e++) sm.o.xbuf[xi.a[h] ^ e] = y[e];
         }
         __syncthreads();
-        const int kk = t & 7, base = 128 * (t >> 3) + kk;
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.o.xbuf[swz(base + 8 * a + 32 * b)];
-        passB<EXACT, true>(v, kk, sm.o.tw);
+            for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.o.xbuf[xi.b[a] + 32 * b];
+        passB<EXACT, true>(v, xi.kk, sm.o.tw);
 #pragma unroll
         for (int b = 0; b < 4; b++)
 #pragma unroll
-            for (int a = 0; a < 4; a++) sm.o.xbuf[swz(base + 8 * a + 32 * b)] = v[a + 4 * b];
+            for (int a = 0; a < 4; a++) sm.o.xbuf[xi.b[a] + 32 * b] = v[a + 4 * b];
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 16; c++) v[c] = sm.o.xbuf[swz(t + 128 * c)];
+        for (int c = 0; c < 16; c++) v[c] = sm.o.xbuf[(t ^ xc_of(c)) + 128 * c];
         passC<EXACT, true>(v, t, sm.o.tw);
     }
     // scale by 1/2048 (fft.cpp:146-158) and take the magnitude the way glibc's hypotf does (double sqrt, narrowed)
@@ -306,8 +346,8 @@ find_index_kernel(DevTables tb, SyncParams p)
 
 template <typename K> static void set_smem(K k, size_t bytes)
 {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); done = true; }
+    // every template instantiation is its own function: set the attribute per launch (it is a cheap host-side call)
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)

@@ -230,13 +230,21 @@ viterbi_kernel(ViterbiParams p)
     uint32_t state = 0, acc = 0;
     uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
     const uint32_t* prbs = p.prbs_words;
-    for (int tt = p.nbits - 1; tt >= 0; tt--) {
-        const uint2 d = dec[(int64_t)(tt + 6) * VIT_THREADS];
-        const uint32_t word = (state & 32) ? d.y : d.x;
-        const uint32_t k = (word >> (state & 31)) & 1u;
-        state = (state >> 1) | (k << 5);
-        acc |= k << (8 * ((tt >> 3) & 3) + 7 - (tt & 7));
-        if ((tt & 31) == 0) { out[tt >> 5] = prbs ? acc ^ prbs[tt >> 5] : acc; acc = 0; }
+    // the decision words are read back in blocks of 16 independent loads (their addresses do not depend on the path),
+    // so the serial state recursion runs from registers; nbits is a multiple of 32
+    for (int tb = p.nbits - 16; tb >= 0; tb -= 16) {
+        uint2 d[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = dec[(int64_t)(tb + k + 6) * VIT_THREADS];
+#pragma unroll
+        for (int k = 15; k >= 0; k--) {
+            const int tt = tb + k;
+            const uint32_t word = (state & 32) ? d[k].y : d[k].x;
+            const uint32_t bit = (word >> (state & 31)) & 1u;
+            state = (state >> 1) | (bit << 5);
+            acc |= bit << (8 * ((tt >> 3) & 3) + 7 - (tt & 7));
+        }
+        if ((tb & 31) == 0) { out[tb >> 5] = prbs ? acc ^ prbs[tb >> 5] : acc; acc = 0; }
     }
 }
 

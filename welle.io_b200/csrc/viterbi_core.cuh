@@ -86,7 +86,15 @@ VIT_HD void vit_metrics(uint32_t w, uint32_t E[8])
 template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], uint32_t& dlo, uint32_t& dhi)
 {
     uint32_t N[32];
-    dlo = 0; dhi = 0;
+    // decision bits are OR-ed into four partial words per half (short dependency chains, no branches)
+    uint32_t pl_[4] = {0, 0, 0, 0}, ph_[4] = {0, 0, 0, 0};
+#if defined(__CUDA_ARCH__)
+    // forced predication: `@!p or.b32 acc, acc, bit` (the compiler otherwise turns some of these into divergent branches)
+#define VIT_OR_IF_NOT(acc, pred_le, bitconst) asm("{\n.reg .pred q;\nsetp.eq.u32 q, %1, 0;\n@q or.b32 %0, %0, %2;\n}" : "+r"(acc) : "r"((uint32_t)(pred_le)), "r"((uint32_t)(bitconst)))
+#else
+#define VIT_OR_IF_NOT(acc, pred_le, bitconst) do { if (!(pred_le)) (acc) |= (bitconst); } while (0)
+#endif
+#define VIT_SETBIT(pred_le, n) do { if ((n) < 32) VIT_OR_IF_NOT(pl_[((n) >> 3) & 3], pred_le, 1u << ((n) & 31)); else VIT_OR_IF_NOT(ph_[((n) >> 3) & 3], pred_le, 1u << ((n) & 31)); } while (0)
     if constexpr (B < 5) {
         constexpr int delta = vit_pat(1 << B);   // pattern change when butterfly bit B flips
         uint32_t MC[8];
@@ -101,11 +109,9 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], 
             bool ph, pl;
             const int ne = 2 * ilo, nehi = ne + (2 << B);     // new states in the low / high half of the even result
             N[vit_remove_bit(ne, B + 1)] = vibmin16(m0, m1, ph, pl);
-            if (!pl) { if (ne < 32) dlo |= 1u << ne; else dhi |= 1u << (ne - 32); }
-            if (!ph) { if (nehi < 32) dlo |= 1u << nehi; else dhi |= 1u << (nehi - 32); }
+            VIT_SETBIT(pl, ne); VIT_SETBIT(ph, nehi);
             N[vit_remove_bit(ne + 1, B + 1)] = vibmin16(m2, m3, ph, pl);
-            if (!pl) { if (ne + 1 < 32) dlo |= 1u << (ne + 1); else dhi |= 1u << (ne + 1 - 32); }
-            if (!ph) { if (nehi + 1 < 32) dlo |= 1u << (nehi + 1); else dhi |= 1u << (nehi + 1 - 32); }
+            VIT_SETBIT(pl, ne + 1); VIT_SETBIT(ph, nehi + 1);
         }
     } else {
         // L_5: register i = (old[i], old[i+32]); result register i = (new[2i], new[2i+1]) = layout L_0
@@ -120,10 +126,13 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], 
             bool ph, pl;
             N[i] = vibmin16(x, y, ph, pl);
             const int ne = 2 * i;
-            if (!pl) { if (ne < 32) dlo |= 1u << ne; else dhi |= 1u << (ne - 32); }
-            if (!ph) { if (ne + 1 < 32) dlo |= 1u << (ne + 1); else dhi |= 1u << (ne + 1 - 32); }
+            VIT_SETBIT(pl, ne); VIT_SETBIT(ph, ne + 1);
         }
     }
+#undef VIT_SETBIT
+#undef VIT_OR_IF_NOT
+    dlo = (pl_[0] | pl_[1]) | (pl_[2] | pl_[3]);
+    dhi = (ph_[0] | ph_[1]) | (ph_[2] | ph_[3]);
 #pragma unroll
     for (int r = 0; r < 32; r++) Q[r] = N[r];
 }
