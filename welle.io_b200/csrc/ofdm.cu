@@ -122,75 +122,176 @@ __device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ s
     passC<EXACT, INV>(v, t, sm.tw);
 }
 
-template <bool EXACT, bool NCO>
+// ---- TMA / mbarrier helpers (SASS: UBLKCP, SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra WAIT_LOOP;\nDONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
+constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real, then two 128-byte dummy areas for unused bins
+struct __align__(16) DemodSmem {
+    float2 inbuf[IN_CAP];            // 20 KB: one symbol, guard interval first, filled by one cp.async.bulk (TMA)
+    float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
+    float2 tw[TwLayout::C5];         // 4 KB: twiddles of all stages but the last (those come through L1 with __ldg)
+    int8_t sbuf[3072 + 1664];
+    float red[16];
+    uint64_t full;
+};
+
+// one symbol's samples, already in shared memory at in[0..], -> spectrum in registers (same pass structure as
+// fft2048_from_global); idx0 = frame-relative index of in[0] for the NCO phase
+template <bool EXACT>
+__device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
+                                                  const float2* __restrict__ tw_c5, const float2* __restrict__ osc, const Nco& nco)
+{
+    float2 x[16];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[8 * h + c] = in[t + 128 * h + 256 * c];
+    if (nco.mix) {
+        int32_t lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            x[c] = mix_sample(x[c], osc, lp);
+            x[8 + c] = mix_sample(x[8 + c], osc, sub_mod(lp, nco.d128));
+            lp = sub_mod(lp, nco.d256);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        float2 y[8];
+        passA_block<EXACT, false>(x + 8 * h, y, sm.tw);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
+    }
+}
+template <bool EXACT>
+__device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int t, const XIdx& xi, const float2* __restrict__ tw_c5)
+{
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[xi.b[a] + 32 * b];
+    passB<EXACT, false>(v, xi.kk, sm.tw);
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) sm.xbuf[xi.b[a] + 32 * b] = v[a + 4 * b];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
+    // pass C with the m=512 twiddles read through the read-only path (12 KB, L1 resident, lane-consecutive)
+    {
+        const float2 w1 = sm.tw[TwLayout::C4 + t], w2 = sm.tw[TwLayout::C4 + 128 + t], w3 = sm.tw[TwLayout::C4 + 256 + t];
+#pragma unroll
+        for (int b = 0; b < 4; b++) bfly4<EXACT, false>(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3], w1, w2, w3);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int k5 = t + 128 * a;
+            bfly4<EXACT, false>(v[a], v[a + 4], v[a + 8], v[a + 12], __ldg(tw_c5 + k5), __ldg(tw_c5 + 512 + k5), __ldg(tw_c5 + 1024 + k5));
+        }
+    }
+}
+
+template <bool EXACT, bool TAP>
 __global__ void __launch_bounds__(OFDM_THREADS, 4)
 ofdm_demod_kernel(DevTables tb, OfdmParams p)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    OfdmSmem& sm = *reinterpret_cast<OfdmSmem*>(smraw);
+    DemodSmem& sm = *reinterpret_cast<DemodSmem*>(smraw);
     const int t = threadIdx.x;
     const int f = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
     if (p.active && !p.active[f]) return;
 
-    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.tw[i] = tb.tw_fwd[i];
-
     const float2* src = p.iq + (int64_t)f * p.stride + p.prs_start[f];
-    // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
-    const Nco ncoP = make_nco((NCO && p.nco) ? p.nco[4 * f] : 0, (NCO && p.nco) ? p.nco[4 * f + 1] : 0);
-    const Nco ncoS = make_nco((NCO && p.nco) ? p.nco[4 * f + 2] : 0, (NCO && p.nco) ? p.nco[4 * f + 3] : 0);
-    const XIdx xi = make_xidx(t);
+    const int l_first = 1 + g * p.sym_per_cta, l_last = l_first + p.sym_per_cta;   // data symbols [l_first, l_last)
 
-    // loop-invariant: logical carrier index of each owned bin (-1 = unused)
-    int inv[NSLOT];
+    // sample range of symbol l relative to the first useful PRS sample: the PRS is [0,2048); symbol l >= 1 (guard first)
+    // starts at 2048 + (l-1)*2552, its FFT window 504 samples later (ofdm-decoder.cpp:178-180)
+    auto issue = [&](int l) {
+        const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
+        const int count = (l == 0) ? TU : TS;
+        const float2* g0 = src + s0;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(g0) >> 3) & 1);     // cp.async.bulk needs 16-byte aligned addresses
+        const uint32_t bytes = (uint32_t)(((count + shift + 1) & ~1) * 8);
+        mbar_expect_tx(&sm.full, bytes);
+        bulk_g2s(sm.inbuf, g0 - shift, bytes, &sm.full);
+    };
+    if (t == 0) { mbar_init(&sm.full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (t == 0) issue(l_first - 1);
+
+    for (int i = t; i < TwLayout::C5; i += OFDM_THREADS) sm.tw[i] = tb.tw_fwd[i];
+    const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
+    // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
+    const Nco ncoP = make_nco(p.nco ? p.nco[4 * f] : 0, p.nco ? p.nco[4 * f + 1] : 0);
+    const Nco ncoS = make_nco(p.nco ? p.nco[4 * f + 2] : 0, p.nco ? p.nco[4 * f + 3] : 0);
+    const XIdx xi = make_xidx(t);
+    // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
+    int sidx[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; s++) inv[s] = tb.invperm[t + 128 * slot_c(s)];
+    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + (t & 63); }
     __syncthreads();
 
-    const int l_first = 1 + g * p.sym_per_cta, l_last = l_first + p.sym_per_cta;   // data symbols [l_first, l_last)
     float2 prev[NSLOT];
     float2 fc = make_float2(0.f, 0.f);
+    uint32_t parity = 0;
 
     for (int l = l_first - 1; l < l_last; l++) {
-        // sample offsets relative to the first useful PRS sample: PRS occupies [0,2048); symbol l>=1 starts (guard
-        // first) at 2048 + (l-1)*2552 and its FFT window at +504 (ofdm-decoder.cpp:178-180)
         const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
-        const int64_t w0 = (l == 0) ? 0 : s0 + TG;
+        const int goff = (l == 0) ? 0 : TG;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src + s0) >> 3) & 1);
         const Nco& nco = l == 0 ? ncoP : ncoS;
+        mbar_wait(&sm.full, parity); parity ^= 1;
+        const float2* in = sm.inbuf + shift;
         float2 v[16];
-        fft2048_from_global<EXACT, false>(src, w0, v, sm, t, xi, tb.osc, nco);
-
+        fft2048_from_smem<EXACT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb.osc, nco);
         if (l >= l_first) {
             // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
-            // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = 2048 + t + 128 r).
-            {
-                int32_t lpa = 0, lpb = 0;
-                if (nco.mix) { lpb = mod_rate64((int64_t)nco.lp0 - (s0 + t) * (int64_t)nco.ph); lpa = mod_rate64((int64_t)nco.lp0 - (s0 + TU + t) * (int64_t)nco.ph); }
+            // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = t + 128 r).
+            int32_t lpa = 0, lpb = 0;
+            if (nco.mix) { lpb = mod_rate64((int64_t)nco.lp0 - (s0 + t) * (int64_t)nco.ph); lpa = mod_rate64((int64_t)nco.lp0 - (s0 + TU + t) * (int64_t)nco.ph); }
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int i = t + 128 * r;
-                    if (i < TG) {
-                        float2 a = __ldg(src + s0 + TU + i), b = __ldg(src + s0 + i);
-                        if (nco.mix) { a = mix_sample(a, tb.osc, lpa); b = mix_sample(b, tb.osc, lpb); }
-                        fc.x += a.x * b.x + a.y * b.y;
-                        fc.y += a.y * b.x - a.x * b.y;
-                    }
-                    if (nco.mix) { lpa = sub_mod(lpa, nco.d128); lpb = sub_mod(lpb, nco.d128); }
+            for (int r = 0; r < 4; r++) {
+                const int i = t + 128 * r;
+                if (i < TG) {
+                    float2 a = in[TU + i], b = in[i];
+                    if (nco.mix) { a = mix_sample(a, tb.osc, lpa); b = mix_sample(b, tb.osc, lpb); }
+                    fc.x += a.x * b.x + a.y * b.y;
+                    fc.y += a.y * b.x - a.x * b.y;
                 }
+                if (nco.mix) { lpa = sub_mod(lpa, nco.d128); lpb = sub_mod(lpb, nco.d128); }
             }
-            // demap owned bins against the previous symbol, scatter softbits into logical order
+        }
+        __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
+        if (t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(l + 1);
+        }
+        fft2048_finish<EXACT>(v, sm, t, xi, tw_c5);   // contains barrier (2)
+
+        if (l >= l_first) {
+            // demap owned bins against the previous symbol, scatter softbits into logical order (branch free)
 #pragma unroll
             for (int s = 0; s < NSLOT; s++) {
                 const float2 X = v[slot_c(s)];
-                if (inv[s] >= 0) {
-                    int8_t sre, sim; float2 r1;
-                    demap_one<EXACT>(X, prev[s], sre, sim, r1);
-                    sm.sbuf[inv[s]] = sre;
-                    sm.sbuf[KC + inv[s]] = sim;
-                    if (p.r1) p.r1[((int64_t)f * 75 + (l - 1)) * KC + inv[s]] = r1;
-                }
+                int8_t sre, sim; float2 r1;
+                demap_one<EXACT>(X, prev[s], sre, sim, r1);
+                sm.sbuf[sidx[s]] = sre;
+                sm.sbuf[KC + sidx[s]] = sim;
+                if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
                 prev[s] = X;
             }
-            __syncthreads();
+            __syncthreads();                   // (3)
             // 3072 B -> global, 16 B per store
             {
                 uint4* dst = reinterpret_cast<uint4*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
@@ -353,11 +454,11 @@ template <typename K> static void set_smem(K k, size_t bytes)
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)
 {
     const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
-    const size_t sm = sizeof(OfdmSmem);
-    const bool nco = p.nco != nullptr;
-#define LAUNCH(E, N) do { set_smem(ofdm_demod_kernel<E, N>, sm); ofdm_demod_kernel<E, N><<<grid, block, sm, st>>>(tb, p); } while (0)
-    if (fft_mode == 0) { if (nco) LAUNCH(true, true); else LAUNCH(true, false); }
-    else { if (nco) LAUNCH(false, true); else LAUNCH(false, false); }
+    const size_t sm = sizeof(DemodSmem);
+    const bool tap = p.r1 != nullptr;
+#define LAUNCH(E, T) do { set_smem(ofdm_demod_kernel<E, T>, sm); ofdm_demod_kernel<E, T><<<grid, block, sm, st>>>(tb, p); } while (0)
+    if (fft_mode == 0) { if (tap) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (tap) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
 }
 
