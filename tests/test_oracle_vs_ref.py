@@ -1,0 +1,160 @@
+"""Pins the C oracle (oracle/dab_oracle.c) against the UNMODIFIED reference compiled from /root/reference
+(oracle/_ref/libwelle_ref.so, KISS-FFT build).  Integer stages and - because the oracle keeps the reference's float
+operation order - the float stages too must be bit-identical.  Skipped where the reference build is not available."""
+import numpy as np
+import pytest
+
+import dabtx
+
+TU, TS, TF, TNULL = 2048, 2552, 196608, 2656
+
+
+@pytest.fixture(scope="module")
+def sig():
+    tx = dabtx.DabTx(seed=0xDAB)
+    return tx, tx.frames(14)
+
+
+def test_tables(oracle, ref):
+    assert np.array_equal(oracle.perm_table(), ref.perm_table())
+    assert np.array_equal(dabtx.perm_table(), ref.perm_table())
+    assert np.array_equal(oracle.prs_table().view(np.uint32), ref.prs_table().view(np.uint32))
+    assert np.abs(dabtx.prs_spectrum() - ref.prs_table()).max() < 1e-6
+    assert np.array_equal(oracle.pcodes(), ref.pcodes()) and np.array_equal(dabtx.pcodes(), ref.pcodes())
+    # KATs printed by the reference's classes
+    assert list(ref.perm_table()[:12]) == [-513, -14, 329, 692, -733, 13, 680, 273, -36, 43, 85, -432] and ref.perm_table()[1535] == 197
+    assert "".join(map(str, oracle.prbs(32))) == "00000111101111100010111001100100"
+
+
+def test_fft_bit_exact(oracle, ref):
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        x = (rng.standard_normal(2048) + 1j * rng.standard_normal(2048)).astype(np.complex64)
+        assert np.array_equal(oracle.fft(x).view(np.uint32), ref.fft(x).view(np.uint32))
+        assert np.array_equal(oracle.ifft_scaled(x).view(np.uint32), ref.fft(x, True).view(np.uint32))
+
+
+def test_find_index_and_demod(oracle, ref, sig):
+    tx, iq = sig
+    base = 3 * TF + TNULL
+    for off in (199, 100, 350, -3000):
+        v = iq[base - off: base - off + TU]
+        i1, c1 = oracle.find_index(v); i2, c2 = ref.find_index(v)
+        assert i1 == i2 and np.array_equal(c1.view(np.uint32), c2.view(np.uint32))
+    st = base + 305
+    prs, syms = iq[st: st + TU], iq[st + TU: st + TU + 75 * TS]
+    s1, r1 = oracle.demod_frame(prs, syms, True); s2, r2 = ref.demod_frame(prs, syms, True)
+    assert np.array_equal(s1, s2) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+    fb1, ok1 = oracle.fic_decode(s1[:3].reshape(-1)); fb2, ok2 = ref.fic_decode(s2[:3].reshape(-1))
+    assert np.array_equal(fb1, fb2) and np.array_equal(ok1, ok2) and ok1.all()
+    assert np.array_equal(np.packbits(fb1[0]), dabtx.fib_bytes(tx))
+
+
+def test_viterbi(oracle, ref):
+    rng = np.random.default_rng(5)
+    for nb in (768, 2304, 192, 24 * 64):
+        soft = rng.integers(-128, 128, (nb + 6) * 4).astype(np.int8)
+        assert np.array_equal(oracle.viterbi(soft, nb), ref.viterbi(soft, nb))
+        bits = rng.integers(0, 2, nb).astype(np.uint8)
+        enc = oracle.conv_encode(bits)
+        assert np.array_equal(enc, dabtx.conv_encode(bits))
+        s = np.clip((enc.astype(np.float32) * 2 - 1) * 40 + rng.standard_normal(enc.size) * 45, -127, 127).astype(np.int8)
+        d1, d2 = oracle.viterbi(s, nb), ref.viterbi(s, nb)
+        assert np.array_equal(d1, d2)
+
+
+@pytest.mark.parametrize("cfg", [(96, 1, 3), (64, 1, 1), (8, 1, 2), (32, 1, 2), (128, 1, 4), (32, 0, 1), (64, 0, 2), (96, 0, 3), (128, 0, 4)])
+def test_eep(oracle, ref, cfg):
+    br, pa, lv = cfg
+    rng = np.random.default_rng(br * 10 + lv)
+    p = oracle.prot_eep(br, pa, lv)
+    assert p.in_bits == dabtx.eep_cu(br, bool(pa), lv) * 64
+    soft = rng.integers(-127, 128, p.in_bits).astype(np.int8)
+    assert np.array_equal(oracle.msc_deconvolve(p, soft, True), ref.eep_deconvolve(br, pa, lv, soft, True))
+
+
+@pytest.mark.parametrize("cfg", [(32, 5), (48, 3), (128, 1), (192, 2), (384, 1), (80, 1), (64, 4), (56, 2), (320, 4)])
+def test_uep(oracle, ref, cfg):
+    br, lv = cfg
+    rng = np.random.default_rng(br * 10 + lv)
+    p = oracle.prot_uep(br, lv)
+    soft = rng.integers(-127, 128, p.in_bits).astype(np.int8)
+    assert np.array_equal(oracle.msc_deconvolve(p, soft, True), ref.uep_deconvolve(br, lv, soft, True))
+
+
+def test_rs_and_crc(oracle, ref):
+    rng = np.random.default_rng(7)
+    d = np.arange(110, dtype=np.uint8)
+    assert " ".join("%02X" % x for x in oracle.rs_encode(d)) == "A2 8A 69 0C EA 30 BD D4 A3 5C"      # reference KAT
+    assert np.array_equal(oracle.rs_encode(d), ref.rs_encode(d)) and np.array_equal(dabtx.rs_parity(d), ref.rs_encode(d))
+    for trial in range(1500):
+        data = rng.integers(0, 256, 110).astype(np.uint8)
+        cw = np.concatenate([data, oracle.rs_encode(data)])
+        ne = int(rng.integers(0, 9)); pos = rng.choice(120, ne, replace=False)
+        e = cw.copy(); e[pos] ^= rng.integers(1, 256, ne).astype(np.uint8)
+        if trial % 10 == 0:
+            e = rng.integers(0, 256, 120).astype(np.uint8)
+        a = oracle.rs_decode_codeword(e); b = ref.rs_decode_codeword(e)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+        if a[0] > 0:
+            assert np.array_equal(a[2][:a[0]], b[2][:b[0]])
+    assert oracle.crc_fire(np.arange(9, dtype=np.uint8)) == ref.crc_fire(np.arange(9, dtype=np.uint8)) == 0x3F9E
+    k = np.frombuffer(b"123456789", np.uint8)
+    assert oracle.crc_ccitt(k) == ref.crc_ccitt(k) == 0xD64E
+    z = np.zeros(256, np.uint8)
+    assert oracle.check_crc_bits(z) == ref.check_crc_bits(z) == 0
+
+
+def test_superframe_filter(oracle, ref):
+    rng = np.random.default_rng(8)
+    tx = dabtx.DabTx(seed=3)
+    stream = np.concatenate([tx.superframe() for _ in range(6)])
+    bad = stream.copy(); idx = rng.choice(len(bad), 300, replace=False); bad[idx] ^= rng.integers(1, 256, 300).astype(np.uint8)
+    for s in (stream, bad):
+        fr = np.concatenate([rng.integers(0, 256, (2, 288)).astype(np.uint8), s.reshape(-1, 288)])
+        ev, outs = oracle.superframe_filter(fr); fec, auerr, good = ref.superframe_filter(fr)
+        assert np.array_equal(np.array([[e["uncorr"], e["corr"]] for e in ev]), fec)
+        assert auerr == sum(e["num_aus"] - bin(e["au_ok"]).count("1") for e in ev if e["sync"])
+        a = oracle.rs_decode_superframe(s[:1440]); b = ref.rs_decode_superframe(s[:1440])
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
+def test_dabaudio_chain(oracle, ref, tmp_path):
+    """time de-interleaver + EEP + Viterbi + dispersal + byte pack through the reference's DabAudio thread"""
+    rng = np.random.default_rng(11)
+    p = oracle.prot_eep(96, 1, 3)
+    cifs = rng.integers(-127, 128, (24, 72 * 64)).astype(np.int8)
+    data, rs = ref.dabaudio_chain(cifs, 96, True, 3, dabplus=True, dump_path=str(tmp_path / "chain.msc"))
+    de = oracle.deinterleave(cifs)
+    mine = np.concatenate([oracle.pack_bits(oracle.msc_deconvolve(p, d, True)) for d in de])
+    n = min(len(mine), len(data))
+    assert n >= 7 * 288 and np.array_equal(mine[:n], data[:n])
+
+
+def test_closed_loop_receiver(oracle, ref, sig, tmp_path):
+    """oracle.rx_run == reference RadioReceiver (flow-controlled input) on the same stream: FIBs, logical frames, RS events"""
+    tx, iq = sig
+    e = ref.e2e(iq, disable_coarse=True, select_at_fib=24, dump_path=str(tmp_path / "e2e.msc"))
+    p = oracle.prot_eep(96, 1, 3)
+    m = oracle.rx_run(iq, prot=p, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    assert e["select_ok"] == 1 and len(e["fibs"]) >= 12 * 11
+    assert np.array_equal(m["fibs"][:len(e["fibs"])], e["fibs"]) and e["fibs"][:, 0].all()
+    n = min(len(m["msc"]), len(e["msc"]))
+    assert n >= 288 * 20 and np.array_equal(m["msc"][:n], e["msc"][:n])
+    k = min(len(m["rs"]), len(e["rs"]))
+    assert k >= 3 and np.array_equal(m["rs"][:k], e["rs"][:k])
+    lf = np.concatenate(tx.logical)
+    assert np.array_equal(e["msc"], lf[8 * 288: 8 * 288 + len(e["msc"])])      # first logical frame = CIF of selection + 16
+    assert all(i["start_index"] == 504 for i in m["info"][1:]) and all(i["fine"] == 0 for i in m["info"])
+
+
+def test_closed_loop_with_noise(oracle, ref, tmp_path):
+    tx = dabtx.DabTx(seed=0x77)
+    s = tx.frames(16)
+    iq = dabtx.add_awgn(s, 9.0, seed=5, signal_power=float(np.mean(np.abs(s[3000:190000]) ** 2)))
+    e = ref.e2e(iq, disable_coarse=True, select_at_fib=24, dump_path=str(tmp_path / "n.msc"))
+    p = oracle.prot_eep(96, 1, 3)
+    m = oracle.rx_run(iq, prot=p, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    assert np.array_equal(m["fibs"][:len(e["fibs"])], e["fibs"])
+    n = min(len(m["msc"]), len(e["msc"]))
+    assert n > 0 and np.array_equal(m["msc"][:n], e["msc"][:n])

@@ -6,3 +6,4 @@ The directory name contains a dot, so import it by path (see tests/conftest.py::
 from .dabb200 import (Context, DabbError, DevBuf, build, load_library, LIB_PATH, EXPORTS, RESULT_DTYPE,  # noqa: F401
                       FFT_EXACT, FFT_FMA, FRAME_DECODED, FRAME_NEED_SAMPLES, FRAME_NO_SYNC, FRAME_ACQUIRING,
                       L, K, TU, TS, TG, TNULL, TF, SOFT_PER_FRAME, MAX_SUBCH)
+from . import sharding  # noqa: F401
