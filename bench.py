@@ -215,10 +215,8 @@ def main():
     pkg = load_pkg()
     S = a.batch
     # work descriptor: (first stream id of this rank) broadcast from rank 0 — the only collective on the path
-    desc = torch.tensor([S], dtype=torch.int32, device=dev)
     if world > 1:
-        dist.broadcast(desc, 0)
-        S = int(desc.item())
+        S = pkg.sharding.broadcast_descriptor([S], dev)[0]
     hbm_peak, peak_src, sm_max = measured_peaks()
 
     # ---- synthetic input: `distinct` periodic 5-frame rings, replicated to S stream buffers with per-stream AWGN
