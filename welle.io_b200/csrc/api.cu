@@ -20,7 +20,7 @@ struct StreamState {
     int64_t pos;            // logical sample index of the next sample to read
     int32_t coarse, fine;   // Hz; fine has int16 semantics
     int32_t local_phase;    // localPhase after the last sample read
-    int32_t fic_ratio;      // 0..10
+    int32_t pad0;
     int32_t acquired;       // 0: null search needed, 1: tracking
     int32_t started;        // 0: sLevel warm-up (T_F/2 samples) not done yet
     float slevel;
@@ -35,6 +35,10 @@ struct StepScratch {        // per stream, rewritten every step
     int32_t nco_frame[4];
     int32_t active;         // this stream decodes a frame in this step
     int32_t status;
+    // receiver state after this frame, filled by advance_kernel for the result record
+    int32_t r_start_index, r_fine, r_coarse;
+    float r_fx, r_fy, r_slevel;
+    int64_t r_next_pos;
 };
 
 std::string g_create_error;
@@ -42,7 +46,9 @@ std::string g_create_error;
 } // namespace
 
 struct dabb_ctx {
-    int device = 0; cudaStream_t stream = nullptr; cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
+    int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
+    int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0;
     HostTables* host = nullptr; DevTables dev{};
@@ -243,38 +249,54 @@ __global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_
     nco_frame[4 * s] = lp_prs0; nco_frame[4 * s + 1] = p1; nco_frame[4 * s + 2] = lp_sym0; nco_frame[4 * s + 3] = p2;
 }
 
-__global__ void finalize_kernel(StreamState* st, const StepScratch* scr, MscSlotState* slots, int n_slots, int S, int groups,
-                                const float2* fc_part, const int32_t* snr, const int32_t* crc, const int32_t* const* slot_info,
-                                dabb_frame_result* res)
+// lane A, right after the OFDM kernel: the part of OFDMProcessor::run that feeds the next frame's synchronisation
+// (fine corrector update :450-451, consumed samples, NCO phase, corrector wrap :478-486)
+__global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int groups, const float2* fc_part)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const StepScratch c = scr[s];
+    StepScratch c = scr[s];
     StreamState z = st[s];
-    dabb_frame_result r;
-    memset(&r, 0, sizeof r);
-    r.status = c.status;
+    c.r_start_index = z.start_index; c.r_fx = 0.f; c.r_fy = 0.f;
     if (c.active) {
-        // FreqCorr: partial sums in group order
-        float fx = 0.f, fy = 0.f;
+        float fx = 0.f, fy = 0.f;      // FreqCorr: partial sums in group order
         for (int g = 0; g < groups; g++) { fx += fc_part[(int64_t)s * groups + g].x; fy += fc_part[(int64_t)s * groups + g].y; }
         const int idx = z.start_index;
         const int32_t p1 = c.nco_frame[1], p2 = c.nco_frame[3];
-        // FIC success counter, one saturating update per FIB in order (fic-handler.cpp:214-229)
-        const int mask = crc[s];
-        for (int f = 0; f < 12; f++) { if ((mask >> f) & 1) { if (z.fic_ratio < 10) z.fic_ratio++; } else if (z.fic_ratio > 0) z.fic_ratio--; }
         // fineCorrector += 0.1 * arg(FreqCorr) / M_PI * (carrierDiff / 2), int16 store (ofdm-processor.cpp:450-451)
         const double upd = 0.1 * (double)(float)atan2((double)fy, (double)fx) / 3.14159265358979323846 * 500;
         z.fine = (int32_t)(int16_t)((double)z.fine + upd);
         const int32_t p3 = z.coarse + z.fine;
-        int64_t lp = (int64_t)z.local_phase - (int64_t)(TU + idx) * p1 - (int64_t)75 * TS * p2 - (int64_t)TNULL * p3;
+        const int64_t lp = (int64_t)z.local_phase - (int64_t)(TU + idx) * p1 - (int64_t)75 * TS * p2 - (int64_t)TNULL * p3;
         z.local_phase = mod_rate(lp);
         z.pos += (int64_t)TU + idx + 75 * (int64_t)TS + TNULL;
         if (z.fine > 500) { z.coarse += 1000; z.fine -= 1000; }
         else if (z.fine < -500) { z.coarse -= 1000; z.fine += 1000; }
         z.nframes++;
-        r.start_index = idx; r.snr_raw = snr[s]; r.fib_crc_mask = mask;
-        r.freq_corr_re = fx; r.freq_corr_im = fy;
+        c.r_fx = fx; c.r_fy = fy;
+        st[s] = z;
+    }
+    c.r_fine = z.fine; c.r_coarse = z.coarse; c.r_next_pos = z.pos; c.r_slevel = z.slevel;
+    scr[s] = c;
+}
+
+// lane B, after FIC / MSC / RS of the frame: decoder-side state and the result record
+__global__ void finalize_kernel(const StepScratch* scr, MscSlotState* slots, int n_slots, int S, int32_t* fic_ratio,
+                                const int32_t* snr, const int32_t* crc, const int32_t* const* slot_info, dabb_frame_result* res)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const StepScratch c = scr[s];
+    dabb_frame_result r;
+    memset(&r, 0, sizeof r);
+    r.status = c.status;
+    int ratio = fic_ratio[s];
+    if (c.active) {
+        // FIC success counter, one saturating update per FIB in order (fic-handler.cpp:214-229)
+        const int mask = crc[s];
+        for (int f = 0; f < 12; f++) { if ((mask >> f) & 1) { if (ratio < 10) ratio++; } else if (ratio > 0) ratio--; }
+        fic_ratio[s] = ratio;
+        r.snr_raw = snr[s]; r.fib_crc_mask = mask;
         for (int k = 0; k < n_slots; k++) {
             MscSlotState& m = slots[s * n_slots + k];
             if (!m.enabled) continue;
@@ -284,20 +306,18 @@ __global__ void finalize_kernel(StreamState* st, const StepScratch* scr, MscSlot
             for (int e = 0; e < 4; e++) r.rs_corr[k][e] = inf[3 + e];
             r.sf_ready[k] = inf[7]; r.sf_au_count[k] = inf[8]; r.sf_au_crc_mask[k] = inf[9];
         }
-        st[s] = z;
-    } else {
-        r.start_index = z.start_index;
     }
-    r.fine_corr = z.fine; r.coarse_corr = z.coarse; r.fic_ratio = z.fic_ratio; r.next_pos = z.pos; r.slevel = z.slevel;
+    r.start_index = c.r_start_index; r.freq_corr_re = c.r_fx; r.freq_corr_im = c.r_fy;
+    r.fine_corr = c.r_fine; r.coarse_corr = c.r_coarse; r.fic_ratio = ratio; r.next_pos = c.r_next_pos; r.slevel = c.r_slevel;
     res[s] = r;
 }
 
-__global__ void reset_kernel(StreamState* st, MscSlotState* slots, int n_slots, int first, int count, int64_t pos)
+__global__ void reset_kernel(StreamState* st, MscSlotState* slots, int n_slots, int first, int count, int64_t pos, int32_t* fic_ratio)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     StreamState z{}; z.pos = pos; z.start_index = -1;
-    st[first + i] = z;
+    st[first + i] = z; fic_ratio[first + i] = 0;
     for (int k = 0; k < n_slots; k++) { MscSlotState& m = slots[(first + i) * n_slots + k]; m.cif_count = 0; m.sf_frame_count = 0; }
 }
 
@@ -306,6 +326,13 @@ __global__ void set_slot_kernel(MscSlotState* slots, int n_slots, int slot, int 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     slots[(first + i) * n_slots + slot] = v;
+}
+
+void sync_all(dabb_ctx* ctx)
+{
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->streamB) cudaStreamSynchronize(ctx->streamB);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
 }
 
 int ensure_dec(dabb_ctx* ctx, size_t bytes)
@@ -346,6 +373,9 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    // lane B (FIC/MSC/RS of frame n) runs on its own stream so that it overlaps lane A (time sync + OFDM of frame n+1)
+    if (cudaStreamCreateWithFlags(&ctx->streamB, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream/event creation failed"; return fail(DABB_E_CUDA); }
@@ -380,11 +410,11 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
     }
     ctx->ring_pitch = ctx->max_cu * 64;
-    if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
-        (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, S)) || (rc = dalloc(ctx, &ctx->d_prs, S)) ||
-        (rc = dalloc(ctx, &ctx->d_nco_sync, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_nco_frame, 4 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_active, S)) ||
-        (rc = dalloc(ctx, &ctx->d_index, S)) || (rc = dalloc(ctx, &ctx->d_snr, S)) || (rc = dalloc(ctx, &ctx->d_fc, (size_t)S * ctx->groups)) ||
-        (rc = dalloc(ctx, &ctx->d_soft, (size_t)S * DABB_SOFT_PER_FRAME, false)) || (rc = dalloc(ctx, &ctx->d_fic_rows, (size_t)S * 4 * vit_row_words(774), false)) ||
+    if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fic_ratio, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
+        (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_prs, 2 * (size_t)S)) ||
+        (rc = dalloc(ctx, &ctx->d_nco_sync, 4 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_nco_frame, 8 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_active, 2 * (size_t)S)) ||
+        (rc = dalloc(ctx, &ctx->d_index, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_snr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fc, 2 * (size_t)S * ctx->groups)) ||
+        (rc = dalloc(ctx, &ctx->d_soft, 2 * (size_t)S * DABB_SOFT_PER_FRAME, false)) || (rc = dalloc(ctx, &ctx->d_fic_rows, (size_t)S * 4 * vit_row_words(774), false)) ||
         (rc = dalloc(ctx, &ctx->d_fibs, (size_t)S * 12 * 32)) || (rc = dalloc(ctx, &ctx->d_crc, S)) || (rc = dalloc(ctx, &ctx->d_results, S)) ||
         (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)))
         return fail(rc);
@@ -396,7 +426,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     cudaHostAlloc((void**)&ctx->h_results, sizeof(dabb_frame_result) * S, cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_fibs, (size_t)S * 12 * 32, cudaHostAllocDefault);
     {
-        reset_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, 0, S, 0);
+        reset_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, 0, S, 0, ctx->d_fic_ratio);
         ctx->launches++;
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = std::string("init failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(DABB_E_CUDA); }
@@ -408,8 +438,7 @@ void dabb_destroy(dabb_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    sync_all(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
@@ -419,6 +448,8 @@ void dabb_destroy(dabb_ctx* ctx)
     if (ctx->h_sf) cudaFreeHost(ctx->h_sf);
     if (ctx->ev_ofdm) cudaEventDestroy(ctx->ev_ofdm);
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
+    for (int i = 0; i < 2; i++) { if (ctx->evA[i]) cudaEventDestroy(ctx->evA[i]); if (ctx->evB[i]) cudaEventDestroy(ctx->evB[i]); }
+    if (ctx->streamB) cudaStreamDestroy(ctx->streamB);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx->host;
@@ -427,22 +458,24 @@ void dabb_destroy(dabb_ctx* ctx)
 
 void* dabb_cuda_stream(dabb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t dabb_kernel_launches(const dabb_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); if (ctx->prof) prof_collect(ctx); return 0; }
+int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->streamB)); CK(cudaStreamSynchronize(ctx->stream2)); if (ctx->prof) prof_collect(ctx); return 0; }
 
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first, int32_t count, int64_t pos)
 {
     if (!ctx || first < 0 || count < 0 || first + count > ctx->S) return DABB_E_ARG;
     if (!count) return 0;
     cudaSetDevice(ctx->device);
-    reset_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, first, count, pos);
+    sync_all(ctx);
+    reset_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, ctx->d_slots, ctx->n_slots, first, count, pos, ctx->d_fic_ratio);
     for (int i = first; i < first + count; i++) for (int k = 0; k < ctx->n_slots; k++) { ctx->h_slots[(size_t)i * ctx->n_slots + k].cif_count = 0; ctx->h_slots[(size_t)i * ctx->n_slots + k].sf_frame_count = 0; }
-    return check_launch(ctx, "reset_kernel");
+    { int rc_ = check_launch(ctx, "reset_kernel"); cudaStreamSynchronize(ctx->stream); ctx->evB_valid[0] = ctx->evB_valid[1] = false; return rc_; }
 }
 
 int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t slot, const dabb_subchannel* sc)
 {
     if (!ctx || !sc || first < 0 || count < 1 || first + count > ctx->S || slot < 0 || slot >= ctx->n_slots) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     ProtProfile prof;
     if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
     if (sc->length_cu < 1 || sc->length_cu > ctx->max_cu || sc->start_cu < 0 || sc->start_cu + sc->length_cu > 864) { ctx->err = "sub-channel does not fit (raise dabb_config.max_subch_cu)"; return DABB_E_ARG; }
@@ -479,17 +512,18 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
     MscSlotState v{}; v.enabled = 1; v.start_cu = sc->start_cu; v.frag = sc->length_cu * 64; v.bitrate = sc->bitrate; v.dabplus = sc->dabplus; v.cif_count = 0; v.sf_frame_count = 0;
     set_slot_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_slots, ctx->n_slots, slot, first, count, v);
     for (int i = first; i < first + count; i++) ctx->h_slots[(size_t)i * ctx->n_slots + slot] = v;
-    return check_launch(ctx, "set_slot_kernel");
+    { int rc_ = check_launch(ctx, "set_slot_kernel"); cudaStreamSynchronize(ctx->stream); return rc_; }
 }
 
 int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t slot)
 {
     if (!ctx || first < 0 || count < 1 || first + count > ctx->S || slot < 0 || slot >= ctx->n_slots) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     MscSlotState v{};
     set_slot_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_slots, ctx->n_slots, slot, first, count, v);
     for (int i = first; i < first + count; i++) ctx->h_slots[(size_t)i * ctx->n_slots + slot] = v;
-    return check_launch(ctx, "set_slot_kernel");
+    { int rc_ = check_launch(ctx, "set_slot_kernel"); cudaStreamSynchronize(ctx->stream); return rc_; }
 }
 
 static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc, cudaStream_t st, uint2* dec)
@@ -512,11 +546,26 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     cudaSetDevice(ctx->device);
     const int S = ctx->S;
     int rc;
+    // Two lanes: A = acquisition, time sync, OFDM demod and the sync-state update of frame n; B = FIC, MSC, RS and the
+    // result record of frame n.  Lane A of frame n+1 only needs lane A of frame n, so B(n) overlaps A(n+1); the per-frame
+    // scratch and the softbits are double buffered by frame parity.  With per-kernel profiling on everything runs
+    // serially on the main stream.
+    const int par = (int)(ctx->step & 1);
+    const bool serial = ctx->prof;
+    cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB, F = serial ? ctx->stream : ctx->stream2;
+    StepScratch* scr = ctx->d_scr + (size_t)par * S;
+    int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
+    int32_t* d_nco_sync = ctx->d_nco_sync + (size_t)par * 2 * S; int32_t* d_nco_frame = ctx->d_nco_frame + (size_t)par * 4 * S;
+    int32_t* d_active = ctx->d_active + (size_t)par * S; int32_t* d_index = ctx->d_index + (size_t)par * S; int32_t* d_snr = ctx->d_snr + (size_t)par * S;
+    float2* d_fc = ctx->d_fc + (size_t)par * S * ctx->groups;
+    int8_t* d_soft = ctx->d_soft + (size_t)par * S * DABB_SOFT_PER_FRAME;
+
     const float2* iq = reinterpret_cast<const float2*>(io->iq);
     int64_t stride = io->stride_samples;
     if (io->iq_is_host) {
         const size_t need = (size_t)S * io->buf_len;
         if (need > ctx->iq_stage_samples) {
+            sync_all(ctx);
             if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
             ctx->d_iq_stage = nullptr; ctx->iq_stage_samples = 0;
             cudaError_t e = cudaMalloc((void**)&ctx->d_iq_stage, need * sizeof(float2));
@@ -524,63 +573,65 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
             ctx->iq_stage_samples = need;
         }
         CK(cudaMemcpy2DAsync(ctx->d_iq_stage, (size_t)io->buf_len * sizeof(float2), io->iq, (size_t)stride * sizeof(float2), (size_t)io->buf_len * sizeof(float2), S,
-                             cudaMemcpyHostToDevice, ctx->stream));
+                             cudaMemcpyHostToDevice, A));
         iq = ctx->d_iq_stage; stride = io->buf_len;
     }
-    CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, ctx->stream));
+    // the buffers of this parity were last used by lane B two frames ago
+    if (!serial && ctx->evB_valid[par]) CK(cudaStreamWaitEvent(A, ctx->evB[par], 0));
+    CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, A));
     prof_mark(ctx, "__step_begin");
     const int tb = 128, gb = (S + tb - 1) / tb;
-    acquire_kernel<<<(S + 31) / 32, 32, 0, ctx->stream>>>(ctx->d_state, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, S);
+    // ---------------- lane A
+    acquire_kernel<<<(S + 31) / 32, 32, 0, A>>>(ctx->d_state, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, S);
     if ((rc = check_launch(ctx, "acquire_kernel"))) return rc;
-    plan_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_buf_start, io->buf_len, S, ctx->d_win, ctx->d_nco_sync, ctx->d_active);
+    plan_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, ctx->d_buf_start, io->buf_len, S, d_win, d_nco_sync, d_active);
     if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
-    SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = ctx->d_win; sp.nco = ctx->d_nco_sync; sp.active = ctx->d_active; sp.index_out = ctx->d_index; sp.cir_out = ctx->d_cir; sp.n = S;
-    launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
+    SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = d_win; sp.nco = d_nco_sync; sp.active = d_active; sp.index_out = d_index; sp.cir_out = ctx->d_cir; sp.n = S;
+    launch_find_index(ctx->dev, sp, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
-    post_sync_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_index, S, ctx->d_prs, ctx->d_nco_frame, ctx->d_active);
+    post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
-    OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = ctx->d_prs; op.nco = ctx->d_nco_frame; op.active = ctx->d_active; op.soft = ctx->d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
-    op.r1 = nullptr; op.freqcorr = ctx->d_fc; op.snr = ctx->d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
-    launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, ctx->stream);
+    OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
+    op.r1 = nullptr; op.freqcorr = d_fc; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
-    // FIC chain on the second stream (serial on the main stream while per-kernel profiling is on)
-    const bool overlap = !ctx->prof;
-    if (overlap) {
-        CK(cudaEventRecord(ctx->ev_ofdm, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_ofdm, 0));
-        if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc, ctx->stream2, ctx->d_dec_fic))) return rc;
-        CK(cudaEventRecord(ctx->ev_fic, ctx->stream2));
-    } else {
-        if ((rc = run_fic(ctx, ctx->d_soft, DABB_SOFT_PER_FRAME, ctx->d_active, S, ctx->d_fibs, ctx->d_crc, ctx->stream, ctx->d_dec_fic))) return rc;
-    }
+    advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->groups, d_fc);
+    if ((rc = check_launch(ctx, "advance_kernel"))) return rc;
+    if (!serial) { CK(cudaEventRecord(ctx->evA[par], A)); CK(cudaStreamWaitEvent(B, ctx->evA[par], 0)); }
+    // ---------------- lane B: FIC chain forked onto its own stream, MSC chain per slot, then the result record
+    if (!serial) { CK(cudaEventRecord(ctx->ev_ofdm, B)); CK(cudaStreamWaitEvent(F, ctx->ev_ofdm, 0)); }
+    if ((rc = run_fic(ctx, d_soft, DABB_SOFT_PER_FRAME, d_active, S, ctx->d_fibs, ctx->d_crc, F, ctx->d_dec_fic))) return rc;
+    if (!serial) CK(cudaEventRecord(ctx->ev_fic, F));
     const int32_t* h_info[DABB_MAX_SUBCH] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < ctx->n_slots; k++) {
         auto& sl = ctx->slot[k];
         h_info[k] = sl.d_info;
         if (!sl.configured) continue;
         const int flen_pad = (sl.flen + 15) & ~15;
-        CK(cudaMemsetAsync(sl.d_valid, 0, sizeof(int32_t) * S * 4, ctx->stream));
-        MscCollectParams cp{}; cp.soft = ctx->d_soft; cp.soft_stride = DABB_SOFT_PER_FRAME; cp.active = ctx->d_active; cp.slots = ctx->d_slots; cp.n_slots = ctx->n_slots; cp.slot = k; cp.ring = sl.d_ring; cp.ring_pitch = ctx->ring_pitch;
-        launch_msc_collect(cp, S, ctx->stream);
+        CK(cudaMemsetAsync(sl.d_valid, 0, sizeof(int32_t) * S * 4, B));
+        MscCollectParams cp{}; cp.soft = d_soft; cp.soft_stride = DABB_SOFT_PER_FRAME; cp.active = d_active; cp.slots = ctx->d_slots; cp.n_slots = ctx->n_slots; cp.slot = k; cp.ring = sl.d_ring; cp.ring_pitch = ctx->ring_pitch;
+        launch_msc_collect(cp, S, B);
         if ((rc = check_launch(ctx, "msc_collect_kernel"))) return rc;
-        MscPrepParams pp{}; pp.active = ctx->d_active; pp.slots = ctx->d_slots; pp.n_slots = ctx->n_slots; pp.slot = k; pp.ring = sl.d_ring; pp.ring_pitch = ctx->ring_pitch; pp.map = sl.d_map; pp.nsteps = sl.nsteps;
+        MscPrepParams pp{}; pp.active = d_active; pp.slots = ctx->d_slots; pp.n_slots = ctx->n_slots; pp.slot = k; pp.ring = sl.d_ring; pp.ring_pitch = ctx->ring_pitch; pp.map = sl.d_map; pp.nsteps = sl.nsteps;
         pp.rows = sl.d_rows; pp.row_words = sl.row_words; pp.valid = sl.d_valid;
-        launch_msc_prep(pp, S, ctx->stream);
+        launch_msc_prep(pp, S, B);
         if ((rc = check_launch(ctx, "msc_prep_kernel"))) return rc;
         ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = ctx->d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
-        launch_viterbi(vp, ctx->stream);
+        launch_viterbi(vp, B);
         if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
-        SuperframeParams fp{}; fp.active = ctx->d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;
+        SuperframeParams fp{}; fp.active = d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;
         fp.valid = sl.d_valid; fp.window = sl.d_window; fp.window_pitch = 5 * flen_pad; fp.sf_out = sl.d_sf; fp.sf_pitch = 5 * flen_pad; fp.info = sl.d_info; fp.gf_exp = ctx->dev.gf_exp; fp.gf_log = ctx->dev.gf_log;
-        launch_superframe(fp, ctx->stream);
+        launch_superframe(fp, B);
         if ((rc = check_launch(ctx, "superframe_kernel"))) return rc;
     }
-    // slot_info pointer table lives in a small device array rewritten each call
-    if (overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fic, 0));
-    CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, ctx->stream));
-    finalize_kernel<<<gb, tb, 0, ctx->stream>>>(ctx->d_state, ctx->d_scr, ctx->d_slots, ctx->n_slots, S, ctx->groups, ctx->d_fc, ctx->d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
-    return check_launch(ctx, "finalize_kernel");
+    if (!serial) CK(cudaStreamWaitEvent(B, ctx->ev_fic, 0));
+    CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, B));
+    finalize_kernel<<<gb, tb, 0, B>>>(scr, ctx->d_slots, ctx->n_slots, S, ctx->d_fic_ratio, d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
+    if ((rc = check_launch(ctx, "finalize_kernel"))) return rc;
+    if (!serial) { CK(cudaEventRecord(ctx->evB[par], B)); ctx->evB_valid[par] = true; }
+    ctx->last_parity = par; ctx->step++;
+    return DABB_OK;
 }
 
 int dabb_process(dabb_ctx* ctx, const dabb_io* io)
@@ -588,8 +639,10 @@ int dabb_process(dabb_ctx* ctx, const dabb_io* io)
     int rc = dabb_process_async(ctx, io);
     if (rc) return rc;
     const int S = ctx->S;
-    if (io->results) CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(dabb_frame_result) * S, cudaMemcpyDeviceToHost, ctx->stream));
-    if (io->fibs) CK(cudaMemcpyAsync(ctx->h_fibs, ctx->d_fibs, (size_t)S * 12 * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStream_t B = ctx->prof ? ctx->stream : ctx->streamB;
+    if (io->results) CK(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(dabb_frame_result) * S, cudaMemcpyDeviceToHost, B));
+    if (io->fibs) CK(cudaMemcpyAsync(ctx->h_fibs, ctx->d_fibs, (size_t)S * 12 * 32, cudaMemcpyDeviceToHost, B));
+    CK(cudaStreamSynchronize(B));
     CK(cudaStreamSynchronize(ctx->stream));
     if (io->results) memcpy(io->results, ctx->h_results, sizeof(dabb_frame_result) * S);
     if (io->fibs) memcpy(io->fibs, ctx->h_fibs, (size_t)S * 12 * 32);
@@ -645,8 +698,8 @@ int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes)
 {
     if (!ctx || !host_out) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (what == 0) { const size_t n = (size_t)ctx->S * DABB_SOFT_PER_FRAME; CK(cudaMemcpy(host_out, ctx->d_soft, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
+    sync_all(ctx);
+    if (what == 0) { const size_t n = (size_t)ctx->S * DABB_SOFT_PER_FRAME; CK(cudaMemcpy(host_out, ctx->d_soft + (size_t)ctx->last_parity * n, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     if (what == 1 && ctx->d_cir) { const size_t n = (size_t)ctx->S * TU * 4; CK(cudaMemcpy(host_out, ctx->d_cir, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     ctx->err = "tap not available (keep_taps = 0?)";
     return DABB_E_STATE;
@@ -657,6 +710,7 @@ int dabb_ofdm_demod(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_
 {
     if (!ctx || !iq || !prs_start || !soft || n < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     OfdmParams op{}; op.iq = reinterpret_cast<const float2*>(iq); op.stride = stride; op.prs_start = prs_start; op.active = nullptr; op.soft = soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = reinterpret_cast<float2*>(r1); op.freqcorr = reinterpret_cast<float2*>(fc); op.snr = nullptr; op.n_frames = n;
     op.groups = (fc || n >= 1024) ? 1 : (n >= 64 ? 5 : 25); op.sym_per_cta = 75 / op.groups;
@@ -680,6 +734,7 @@ int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_
 {
     if (!ctx || !iq || !win_start || !index_out || n < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
     return check_launch(ctx, "find_index_kernel");
@@ -689,6 +744,7 @@ int dabb_viterbi(dabb_ctx* ctx, const int8_t* soft, int32_t n_cw, int32_t nbits,
 {
     if (!ctx || !soft || !bits_out || n_cw < 1 || nbits < 32 || (nbits % 32) || ((nbits + 6) % 6)) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     const int nsteps = nbits + 6, rw = vit_row_words(nsteps), ob = nbits / 8;
     uint32_t* rows = nullptr; uint8_t* bytes = nullptr;
     CK(cudaMalloc((void**)&rows, (size_t)n_cw * rw * 4));
@@ -713,6 +769,7 @@ int dabb_fic_decode(dabb_ctx* ctx, const int8_t* soft, int32_t n_frames, uint8_t
 {
     if (!ctx || !soft || !fib_out || !crc_mask_out || n_frames < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     uint32_t* rows = nullptr;
     uint32_t* save = ctx->d_fic_rows;
     if (n_frames > ctx->S) { CK(cudaMalloc((void**)&rows, (size_t)n_frames * 4 * vit_row_words(774) * 4)); ctx->d_fic_rows = rows; }
@@ -728,6 +785,7 @@ int dabb_msc_decode(dabb_ctx* ctx, const dabb_subchannel* sc, const int8_t* soft
 {
     if (!ctx || !sc || !soft || !bytes_out || n < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     ProtProfile prof;
     if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
     const int frag = sc->length_cu * 64, nbits = 24 * prof.bitrate, nsteps = nbits + 6, rw = vit_row_words(nsteps), flen = 3 * prof.bitrate;
@@ -762,6 +820,7 @@ int dabb_rs_superframes(dabb_ctx* ctx, uint8_t* sf, int32_t n, int32_t sf_len, i
 {
     if (!ctx || !sf || !info || n < 1 || sf_len < 120 || (sf_len % 120)) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
+    sync_all(ctx);
     launch_rs_superframes(sf, n, sf_len, info, ctx->dev.gf_exp, ctx->dev.gf_log, ctx->stream);
     return check_launch(ctx, "rs_superframes_kernel");
 }

@@ -303,6 +303,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
             // reference symbol only (the PRS when l == 0): keep its spectrum, estimate SNR from the PRS
 #pragma unroll
             for (int s = 0; s < NSLOT; s++) prev[s] = v[slot_c(s)];
+            __syncthreads();                   // (3') every thread is done reading xbuf before the next symbol's pass A overwrites it
             if (l == 0 && p.snr) {
                 // OfdmDecoder::get_snr method 1 (ofdm-decoder.cpp:246-265): noise bins 1094..1259 and 788..887,
                 // signal bins 1664..2047 and 0..383
