@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--coresident", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)
@@ -236,7 +237,7 @@ def main():
     torch.cuda.synchronize()
     log(f"input ready: {S} streams x {BUF_LEN} samples")
 
-    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU, coresident=a.coresident)
     ctx.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
     ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)
 
@@ -306,10 +307,10 @@ def main():
                 "frac_with_survey_bytes": S * SURVEY_BYTES_PER_FRAME / (kms * 1e-3) / 1e9 / hbm_peak,
                 "share_of_step": kms / (sum(v["ms"] for v in prof.values()) / a.steps)}
     # Viterbi issue-slot figure: 4 int-ops per ACS against 148 SM x 4 schedulers x 32 lanes x f_SM
-    vms = (prof["viterbi_kernel(FIC)"]["ms"] + prof["viterbi_kernel(MSC)"]["ms"]) / a.steps
+    vms = sum(v_["ms"] for k_, v_ in prof.items() if k_.startswith("viterbi_kernel")) / a.steps
     acs_s = S * ACS_PER_FRAME / (vms * 1e-3)
     peak_ops = 148 * 4 * 32 * f_sm
-    vit = {"kernel": "viterbi_kernel (FIC + MSC launches)", "bound": "issue", "achieved": acs_s * 4 / 1e12, "peak": peak_ops / 1e12, "unit": "Tint-op/s",
+    vit = {"kernel": "viterbi_batch_kernel (FIC + MSC codewords in one launch)", "bound": "issue", "achieved": acs_s * 4 / 1e12, "peak": peak_ops / 1e12, "unit": "Tint-op/s",
            "frac": acs_s * 4 / peak_ops, "acs_per_s": acs_s, "ms_per_step": vms, "f_sm_mhz": f_sm / 1e6,
            "note": "4 int-ops per add-compare-select (SURVEY 8d); the kernel packs two states per 32-bit lane-op"}
 
@@ -351,6 +352,37 @@ def main():
         e2e = {"value": world * Se * a.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h, "batch_frames_per_gpu": Se,
                "frames_decoded_last_step": okf, "note": "host pinned cf32 -> dabb_process (H2D + all kernels + D2H of results/FIBs/logical frames/superframes); PCIe-bound"}
         ctx_e.close(); del host
+        # the same with the RAW-file u8 format (2 bytes per sample over PCIe instead of 8), converted on the device
+        try:
+            ctx_u = pkg.Context(n_streams=Se, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+            ctx_u.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
+            hu = torch.empty((Se, BUF_LEN, 2), dtype=torch.uint8).pin_memory()
+            hu.copy_((buf[:Se] * 256.0 + 128.0).round().clamp(0, 255).to(torch.uint8))
+            cu = 0
+
+            def step_u8(c):
+                n = c + 1
+                if c == 0:
+                    return ctx_u.process(hu, BUF_LEN, np.zeros(Se, np.int64), 3 * TF, iq_is_host=True, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=pkg.IQ_U8), 3 * TF
+                off = (n % RING_FRAMES) * TF
+                return ctx_u.process(hu.data_ptr() + off * 2, BUF_LEN, np.full(Se, n * TF, np.int64), min(WIN, BUF_LEN - off), iq_is_host=True, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=pkg.IQ_U8), min(WIN, BUF_LEN - off)
+            for _ in range(a.warmup):
+                step_u8(cu); cu += 1
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); h2du = 0
+            for _ in range(a.steps):
+                ou, nsamp = step_u8(cu); cu += 1; h2du += Se * nsamp * 2
+            torch.cuda.synchronize()
+            dtu = time.perf_counter() - t0
+            tu = torch.tensor([dtu], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+            e2e["u8_input"] = {"value": world * Se * a.steps / float(tu.item()), "unit": "frames/s", "h2d_bytes_per_step": h2du // a.steps,
+                               "frames_decoded_last_step": int((ou["results"]["status"] == 0).sum()), "fib_crc_ok_last_step": int(sum(bin(int(m)).count("1") for m in ou["results"]["fib_crc_mask"])),
+                               "note": "RAW u8 IQ (CRAWFile .u8.iq format) shipped as bytes and converted on the device; SURVEY 8(f) rank 2"}
+            ctx_u.close(); del hu
+        except Exception as e:  # noqa
+            e2e["u8_input"] = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": "dab_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,

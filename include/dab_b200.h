@@ -113,7 +113,7 @@ typedef struct {
 enum { DABB_FRAME_DECODED = 0, DABB_FRAME_NEED_SAMPLES = 1, DABB_FRAME_NO_SYNC = 2, DABB_FRAME_ACQUIRING = 3 };
 
 /* One decode step for all streams.
- *   iq            interleaved cf32 (re,im), stream s at iq + s*stride_samples complex samples
+ *   iq            interleaved (re,im) samples in `iq_format` (default cf32), stream s at iq + s*stride_samples complex samples
  *   iq_is_host    0: device pointer; 1: host pointer (pinned or pageable) -> copied H2D inside the call
  *   buf_start[s]  logical sample index of the first sample in stream s's buffer (host array, n_streams entries)
  *   buf_len       complex samples available per stream buffer
@@ -131,7 +131,11 @@ enum { DABB_FRAME_DECODED = 0, DABB_FRAME_NEED_SAMPLES = 1, DABB_FRAME_NO_SYNC =
 typedef struct {
     const float* iq; int32_t iq_is_host; int64_t stride_samples; const int64_t* buf_start; int64_t buf_len;
     dabb_frame_result* results; uint8_t* fibs; uint8_t* msc; int32_t msc_stride; uint8_t* sf; int32_t sf_stride;
+    int32_t iq_format;   /* DABB_IQ_*: raw sample format of `iq` (strides and lengths stay in complex samples); converted on the
+                            device exactly like CRAWFile::convertSamples (input/raw_file.cpp:324-366) */
+    int32_t reserved;
 } dabb_io;
+enum { DABB_IQ_CF32 = 0, DABB_IQ_U8 = 1, DABB_IQ_S8 = 2, DABB_IQ_S16LE = 3, DABB_IQ_S16BE = 4 };
 int dabb_process(dabb_ctx* ctx, const dabb_io* io);
 /* asynchronous form for benchmarking with device-resident inputs: enqueue only, no host copies */
 int dabb_process_async(dabb_ctx* ctx, const dabb_io* io);

@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 TF = 196608
 
 
-def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0):
+def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0, disable_coarse=True):
     S = len(sigs)
     n = max(len(s) for s in sigs)
     buf = np.zeros((S, n), np.complex64)
     for i, s in enumerate(sigs):
         buf[i, :len(s)] = s
-    ctx = pkg.Context(n_streams=S, keep_taps=True, n_subch_slots=n_slots, fft_mode=fft_mode)
+    ctx = pkg.Context(n_streams=S, keep_taps=True, n_subch_slots=n_slots, fft_mode=fft_mode, disable_coarse=disable_coarse)
     d = ctx.dev(buf)
     res = [dict(info=[], fibs=[], crc=[], msc=[], rs=[], soft=[], sf=[]) for _ in range(S)]
     selected = False
@@ -93,3 +93,53 @@ def test_closed_loop_matches_oracle(oracle):
     sf_bytes = [s for s, _, _ in res[0]["sf"]]
     txsf = [bytes(s) for s in tx0.superframes]
     assert all(bytes(s) in txsf for s in sf_bytes)
+
+
+def test_coarse_corrector_matches_oracle(oracle):
+    """RadioReceiverOptions::disableCoarseCorrector = false: processPRS (PatternOfZeros) runs while the FIC success counter is
+    low.  A clean stream must stay at coarse 0; a stream shifted by +2 carriers must be pulled back exactly like the oracle."""
+    pkg = load_pkg()
+    prot = oracle.prot_eep(96, 1, 3)
+    tx0 = dabtx.DabTx(seed=0xC0A); s0 = tx0.frames(14)
+    tx1 = dabtx.DabTx(seed=0xC0B); s1 = dabtx.freq_shift(tx1.frames(14), 2000.0)
+    sigs = [s0, s1]
+    res = run_gpu(pkg, sigs, disable_coarse=False)
+    for i, sig in enumerate(sigs):
+        orc = oracle.rx_run(sig, prot=prot, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=False)
+        n = min(len(res[i]["info"]), orc["frames"])
+        assert n >= 8
+        assert [x[2] for x in res[i]["info"][:n]] == [x["coarse"] for x in orc["info"][:n]], (i, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
+        assert all(abs(a[1] - b["fine"]) <= 1 for a, b in zip(res[i]["info"][:n], orc["info"][:n]))
+        crc_o = [int(sum(int(o) << k for k, o in enumerate(orc["fibs"][12 * f: 12 * f + 12, 0]))) for f in range(n)]
+        assert res[i]["crc"][:n] == crc_o
+    assert all(c == 0 for _, _, c in res[0]["info"])
+    assert res[1]["info"][-1][2] != 0 and res[1]["crc"][-1] == 0xFFF
+
+
+def test_raw_sample_formats(oracle):
+    """u8 / s16 RAW-file sample formats converted on the device (CRAWFile::convertSamples semantics) through the host-buffer
+    path of dabb_process: FIBs must equal the oracle fed with the CPU-converted float samples."""
+    pkg = load_pkg()
+    tx = dabtx.DabTx(seed=0xF0F)
+    sig = tx.frames(9)
+    inter = np.stack([sig.real, sig.imag], axis=-1)
+    u8 = np.clip(np.round(inter * 2.0 * 128.0 + 128.0), 0, 255).astype(np.uint8)
+    f_u8 = ((u8.astype(np.float32) - 128.0) / 128.0).view(np.complex64).reshape(-1)
+    s16 = np.clip(np.round(inter * 20000.0), -32768, 32767).astype(np.int16)
+    f_s16 = s16.astype(np.float32).view(np.complex64).reshape(-1)
+    s16_bytes = s16.astype(">i2").view(np.uint8).reshape(len(sig), 4)       # the reference's "s16le" reader takes the first byte as the high byte
+    for fmt, raw, ref_sig in ((pkg.IQ_U8, u8, f_u8), (pkg.IQ_S16LE, s16_bytes, f_s16)):
+        ctx = pkg.Context(n_streams=1)
+        raw = np.ascontiguousarray(raw)
+        fibs, crcs = [], []
+        for step in range(9):
+            out = ctx.process(raw, len(sig), np.zeros(1, np.int64), len(sig), iq_is_host=True, iq_format=fmt)
+            r = out["results"]
+            if r["status"][0] == pkg.FRAME_DECODED and r["next_pos"][0] <= len(sig):
+                fibs.append(out["fibs"][0].copy()); crcs.append(int(r["fib_crc_mask"][0]))
+        ctx.close()
+        o = oracle.rx_run(ref_sig, disable_coarse=True)
+        n = min(len(fibs), o["frames"])
+        assert n >= 6
+        for f in range(n):
+            assert np.array_equal(fibs[f], o["fibs"][12 * f:12 * f + 12, 1:]) and crcs[f] == 0xFFF, (fmt, f)

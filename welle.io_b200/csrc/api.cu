@@ -47,7 +47,7 @@ std::string g_create_error;
 
 struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
-    int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr;
+    int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0;
@@ -62,11 +62,11 @@ struct dabb_ctx {
     struct Slot {
         bool configured = false; ProtProfile prof{}; int nsteps = 0, nbits = 0, row_words = 0, flen = 0;
         int16_t* d_map = nullptr; uint32_t* d_prbs_words = nullptr; uint32_t* d_rows = nullptr; int32_t* d_valid = nullptr;
-        uint8_t* d_logical = nullptr; int8_t* d_ring = nullptr; uint8_t* d_window = nullptr; uint8_t* d_sf = nullptr; int32_t* d_info = nullptr;
+        uint8_t* d_logical = nullptr; uint2* d_dec = nullptr; int8_t* d_ring = nullptr; uint8_t* d_window = nullptr; uint8_t* d_sf = nullptr; int32_t* d_info = nullptr;
     } slot[DABB_MAX_SUBCH];
     uint32_t* d_fic_prbs_words = nullptr;
     std::vector<MscSlotState> h_slots;
-    float2* d_iq_stage = nullptr; size_t iq_stage_samples = 0;
+    float2* d_iq_stage = nullptr; size_t iq_stage_samples = 0; uint8_t* d_raw_stage = nullptr; size_t raw_stage_bytes = 0;
     // pinned host staging for results
     dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
     int groups = 1;
@@ -219,7 +219,7 @@ __global__ void plan_kernel(StreamState* st, StepScratch* scr, const int64_t* bu
     win[s] = c.win_start; nco_sync[2 * s] = c.nco_sync[0]; nco_sync[2 * s + 1] = c.nco_sync[1]; active[s] = c.active;
 }
 
-__global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_t* index, int S, int64_t* prs, int32_t* nco_frame, int32_t* active)
+__global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_t* index, const int32_t* coarse_corr, int S, int64_t* prs, int32_t* nco_frame, int32_t* active)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -239,7 +239,12 @@ __global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_
     c.prs_start = c.win_start + idx;
     // phase applied to PRS sample 0 (the (idx+1)-th sample read in this frame)
     const int32_t lp_prs0 = mod_rate((int64_t)z.local_phase - (int64_t)(idx + 1) * p1);
-    const int32_t p2 = p1;   // coarse corrector update would go here (ofdm-processor.cpp:397-409)
+    // coarse corrector (ofdm-processor.cpp:397-409): find_index_kernel evaluated processPRS where the FIC ratio asked for it
+    if (coarse_corr) {
+        const int corr = coarse_corr[s];
+        if (corr != 0 && corr != 100) { z.coarse += corr * 1000; if (abs(z.coarse) > 35000) z.coarse = 0; }
+    }
+    const int32_t p2 = z.coarse + z.fine;
     // phase applied to the first data-symbol sample = lp after 2048+idx samples, minus p2; expressed at index 2048
     const int32_t lp_after_prs = mod_rate((int64_t)z.local_phase - (int64_t)(TU + idx) * p1);
     const int32_t lp_sym0 = mod_rate((int64_t)lp_after_prs - p2 + (int64_t)TU * p2);   // so that lp(i) = lp_sym0 - i*p2 for i >= 2048
@@ -335,6 +340,26 @@ void sync_all(dabb_ctx* ctx)
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
 }
 
+// raw file formats -> cf32, value for value like CRAWFile::convertSamples (input/raw_file.cpp:336-363): u8 (b-128)/128,
+// s8 b/128, "s16le"/"s16be" unscaled with the byte order the reference applies to each name
+__global__ void convert_iq_kernel(const uint8_t* __restrict__ raw, int64_t raw_stride_samples, int fmt, float2* __restrict__ out, int64_t out_stride, int64_t len, int S)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= len || s >= S) return;
+    float re, im;
+    if (fmt == DABB_IQ_U8) { const uchar2 b = reinterpret_cast<const uchar2*>(raw)[(int64_t)s * raw_stride_samples + i]; re = (float)((int)b.x - 128) / 128.0f; im = (float)((int)b.y - 128) / 128.0f; }
+    else if (fmt == DABB_IQ_S8) { const char2 b = reinterpret_cast<const char2*>(raw)[(int64_t)s * raw_stride_samples + i]; re = (float)b.x / 128.0f; im = (float)b.y / 128.0f; }
+    else {
+        const uchar4 b = reinterpret_cast<const uchar4*>(raw)[(int64_t)s * raw_stride_samples + i];
+        int16_t I, Q;
+        if (fmt == DABB_IQ_S16LE) { I = (int16_t)((b.x << 8) | b.y); Q = (int16_t)((b.z << 8) | b.w); }
+        else { I = (int16_t)((b.y << 8) | b.x); Q = (int16_t)((b.w << 8) | b.z); }
+        re = (float)I; im = (float)Q;
+    }
+    out[(int64_t)s * out_stride + i] = make_float2(re, im);
+}
+
 int ensure_dec(dabb_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->dec_bytes) return 0;
@@ -374,10 +399,15 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
     // lane B (FIC/MSC/RS of frame n) runs on its own stream so that it overlaps lane A (time sync + OFDM of frame n+1)
-    if (cudaStreamCreateWithFlags(&ctx->streamB, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    {
+        int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lane B gets the higher priority: its CTAs take the SM resources lane A leaves free
+        if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+        ctx->ofdm_smem_floor = cfg->reserved[0] == 2 ? 50 * 1024 : 0;   // experimental co-residency cap (measured slower: off by default)
+    }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
-    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); } }
+    if ( cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream/event creation failed"; return fail(DABB_E_CUDA); }
     ctx->host = new HostTables();
     build_host_tables(*ctx->host);
@@ -410,7 +440,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
     }
     ctx->ring_pitch = ctx->max_cu * 64;
-    if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fic_ratio, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
+    if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fic_ratio, S)) || (rc = dalloc(ctx, &ctx->d_coarse, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
         (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_prs, 2 * (size_t)S)) ||
         (rc = dalloc(ctx, &ctx->d_nco_sync, 4 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_nco_frame, 8 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_active, 2 * (size_t)S)) ||
         (rc = dalloc(ctx, &ctx->d_index, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_snr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fc, 2 * (size_t)S * ctx->groups)) ||
@@ -442,6 +472,7 @@ void dabb_destroy(dabb_ctx* ctx)
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
+    if (ctx->d_raw_stage) cudaFree(ctx->d_raw_stage);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_fibs) cudaFreeHost(ctx->h_fibs);
     if (ctx->h_msc) cudaFreeHost(ctx->h_msc);
@@ -505,7 +536,7 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
         CK(cudaMemcpyAsync(sl.d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(sl.d_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, sl.nsteps)))) return rc;
+        { void* q = nullptr; if (cudaMalloc(&q, vit_dec_bytes(S * 4, sl.nsteps)) != cudaSuccess) { ctx->err = "cudaMalloc(slot decisions)"; return DABB_E_NOMEM; } ctx->allocs.push_back(q); sl.d_dec = (uint2*)q; }
         sl.configured = true;
         if (sl.flen > ctx->flen_max) ctx->flen_max = sl.flen;
     }
@@ -526,6 +557,14 @@ int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
     { int rc_ = check_launch(ctx, "set_slot_kernel"); cudaStreamSynchronize(ctx->stream); return rc_; }
 }
 
+static ViterbiParams fic_viterbi_params(dabb_ctx* ctx, int n_frames, uint8_t* fibs, uint2* dec)
+{
+    ViterbiParams vp{};
+    vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
+    vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
+    return vp;
+}
+
 static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc, cudaStream_t st, uint2* dec)
 {
     int rc;
@@ -534,7 +573,7 @@ static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const
     ViterbiParams vp{};
     vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
     vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
-    launch_viterbi(vp, st);
+    launch_viterbi(vp, st, ctx->vit_stages_now);
     if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
     launch_fic_crc(fibs, active, n_frames, crc, st);
     return check_launch(ctx, "fic_crc_kernel");
@@ -552,7 +591,8 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     // serially on the main stream.
     const int par = (int)(ctx->step & 1);
     const bool serial = ctx->prof;
-    cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB, F = serial ? ctx->stream : ctx->stream2;
+    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 1;
+    cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
     StepScratch* scr = ctx->d_scr + (size_t)par * S;
     int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
     int32_t* d_nco_sync = ctx->d_nco_sync + (size_t)par * 2 * S; int32_t* d_nco_frame = ctx->d_nco_frame + (size_t)par * 4 * S;
@@ -562,7 +602,9 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
 
     const float2* iq = reinterpret_cast<const float2*>(io->iq);
     int64_t stride = io->stride_samples;
-    if (io->iq_is_host) {
+    const int fmt = io->iq_format;
+    if (fmt < 0 || fmt > DABB_IQ_S16BE) { ctx->err = "unknown iq_format"; return DABB_E_ARG; }
+    if (io->iq_is_host || fmt != DABB_IQ_CF32) {
         const size_t need = (size_t)S * io->buf_len;
         if (need > ctx->iq_stage_samples) {
             sync_all(ctx);
@@ -572,8 +614,29 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
             if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(iq staging): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
             ctx->iq_stage_samples = need;
         }
-        CK(cudaMemcpy2DAsync(ctx->d_iq_stage, (size_t)io->buf_len * sizeof(float2), io->iq, (size_t)stride * sizeof(float2), (size_t)io->buf_len * sizeof(float2), S,
-                             cudaMemcpyHostToDevice, A));
+        if (fmt == DABB_IQ_CF32) {
+            CK(cudaMemcpy2DAsync(ctx->d_iq_stage, (size_t)io->buf_len * sizeof(float2), io->iq, (size_t)stride * sizeof(float2), (size_t)io->buf_len * sizeof(float2), S,
+                                 cudaMemcpyHostToDevice, A));
+        } else {
+            const size_t bps = (fmt == DABB_IQ_U8 || fmt == DABB_IQ_S8) ? 2 : 4;
+            const uint8_t* raw = reinterpret_cast<const uint8_t*>(io->iq);
+            int64_t raw_stride = stride;
+            if (io->iq_is_host) {
+                if (need * bps > ctx->raw_stage_bytes) {
+                    sync_all(ctx);
+                    if (ctx->d_raw_stage) cudaFree(ctx->d_raw_stage);
+                    ctx->d_raw_stage = nullptr; ctx->raw_stage_bytes = 0;
+                    cudaError_t e = cudaMalloc((void**)&ctx->d_raw_stage, need * bps);
+                    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(raw staging): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+                    ctx->raw_stage_bytes = need * bps;
+                }
+                CK(cudaMemcpy2DAsync(ctx->d_raw_stage, (size_t)io->buf_len * bps, io->iq, (size_t)stride * bps, (size_t)io->buf_len * bps, S, cudaMemcpyHostToDevice, A));
+                raw = ctx->d_raw_stage; raw_stride = io->buf_len;
+            }
+            const dim3 grid((unsigned)((io->buf_len + 255) / 256), (unsigned)S);
+            convert_iq_kernel<<<grid, 256, 0, A>>>(raw, raw_stride, fmt, ctx->d_iq_stage, io->buf_len, io->buf_len, S);
+            if ((rc = check_launch(ctx, "convert_iq_kernel"))) return rc;
+        }
         iq = ctx->d_iq_stage; stride = io->buf_len;
     }
     // the buffers of this parity were last used by lane B two frames ago
@@ -587,21 +650,26 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     plan_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, ctx->d_buf_start, io->buf_len, S, d_win, d_nco_sync, d_active);
     if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
     SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = d_win; sp.nco = d_nco_sync; sp.active = d_active; sp.index_out = d_index; sp.cir_out = ctx->d_cir; sp.n = S;
+    sp.fic_ratio = ctx->d_fic_ratio; sp.coarse_out = ctx->disable_coarse ? nullptr : ctx->d_coarse;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
-    post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, S, d_prs, d_nco_frame, d_active);
+    post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, ctx->disable_coarse ? nullptr : ctx->d_coarse, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = nullptr; op.freqcorr = d_fc; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
+    op.smem_floor = serial ? 0 : ctx->ofdm_smem_floor;
     launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
     advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->groups, d_fc);
     if ((rc = check_launch(ctx, "advance_kernel"))) return rc;
     if (!serial) { CK(cudaEventRecord(ctx->evA[par], A)); CK(cudaStreamWaitEvent(B, ctx->evA[par], 0)); }
-    // ---------------- lane B: FIC chain forked onto its own stream, MSC chain per slot, then the result record
-    if (!serial) { CK(cudaEventRecord(ctx->ev_ofdm, B)); CK(cudaStreamWaitEvent(F, ctx->ev_ofdm, 0)); }
-    if ((rc = run_fic(ctx, d_soft, DABB_SOFT_PER_FRAME, d_active, S, ctx->d_fibs, ctx->d_crc, F, ctx->d_dec_fic))) return rc;
-    if (!serial) CK(cudaEventRecord(ctx->ev_fic, F));
+    // ---------------- lane B: de-puncturing for FIC and every selected slot, ONE Viterbi launch over all codeword sets,
+    // then CRC / RS and the result record
+    launch_fic_prep(ctx->dev, d_soft, DABB_SOFT_PER_FRAME, d_active, S, ctx->d_fic_rows, B);
+    if ((rc = check_launch(ctx, "fic_prep_kernel"))) return rc;
+    ViterbiBatch vb{}; vb.n = 0;
+    vb.p[vb.n++] = fic_viterbi_params(ctx, S, ctx->d_fibs, ctx->d_dec_fic);
     const int32_t* h_info[DABB_MAX_SUBCH] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < ctx->n_slots; k++) {
         auto& sl = ctx->slot[k];
@@ -616,16 +684,23 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         pp.rows = sl.d_rows; pp.row_words = sl.row_words; pp.valid = sl.d_valid;
         launch_msc_prep(pp, S, B);
         if ((rc = check_launch(ctx, "msc_prep_kernel"))) return rc;
-        ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = ctx->d_dec;
+        ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
-        launch_viterbi(vp, B);
-        if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
+        vb.p[vb.n++] = vp;
+    }
+    launch_viterbi_batch(vb, B, 3);
+    if ((rc = check_launch(ctx, "viterbi_kernel(FIC+MSC)"))) return rc;
+    launch_fic_crc(ctx->d_fibs, d_active, S, ctx->d_crc, B);
+    if ((rc = check_launch(ctx, "fic_crc_kernel"))) return rc;
+    for (int k = 0; k < ctx->n_slots; k++) {
+        auto& sl = ctx->slot[k];
+        if (!sl.configured) continue;
+        const int flen_pad = (sl.flen + 15) & ~15;
         SuperframeParams fp{}; fp.active = d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;
         fp.valid = sl.d_valid; fp.window = sl.d_window; fp.window_pitch = 5 * flen_pad; fp.sf_out = sl.d_sf; fp.sf_pitch = 5 * flen_pad; fp.info = sl.d_info; fp.gf_exp = ctx->dev.gf_exp; fp.gf_log = ctx->dev.gf_log;
         launch_superframe(fp, B);
         if ((rc = check_launch(ctx, "superframe_kernel"))) return rc;
     }
-    if (!serial) CK(cudaStreamWaitEvent(B, ctx->ev_fic, 0));
     CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, B));
     finalize_kernel<<<gb, tb, 0, B>>>(scr, ctx->d_slots, ctx->n_slots, S, ctx->d_fic_ratio, d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
     if ((rc = check_launch(ctx, "finalize_kernel"))) return rc;
@@ -735,7 +810,7 @@ int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_
     if (!ctx || !iq || !win_start || !index_out || n < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
-    SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n;
+    SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n; sp.fic_ratio = nullptr; sp.coarse_out = nullptr;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
     return check_launch(ctx, "find_index_kernel");
 }

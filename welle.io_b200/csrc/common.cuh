@@ -31,6 +31,7 @@ struct OfdmParams {
     float2* freqcorr;                            // optional [n][groups] partial CP correlation sums
     int32_t* snr;                                // optional [n] get_snr value of the PRS
     int n_frames; int groups; int sym_per_cta;   // groups * sym_per_cta == 75
+    int smem_floor;                              // request at least this much dynamic shared memory (caps CTAs/SM so that other kernels fit beside it)
 };
 
 struct SyncParams {
@@ -39,6 +40,9 @@ struct SyncParams {
     const int32_t* nco;                          // [n][2] or nullptr
     const int32_t* active;
     int32_t* index_out; float* cir_out; int n;
+    // coarse frequency corrector (OFDMProcessor::processPRS, PatternOfZeros): evaluated for streams whose FIC success
+    // counter is below 5 (ofdm-processor.cpp:397); result = carrier offset, or 0 when not evaluated
+    const int32_t* fic_ratio; int32_t* coarse_out;
 };
 
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);

@@ -135,13 +135,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef DEMOD_CTAS_PER_SM
+#define DEMOD_CTAS_PER_SM 5
+#endif
 constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
-constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real, then two 128-byte dummy areas for unused bins
+constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real; unused bins write into a 64-byte dummy area behind it
+constexpr int SB_IM = 1536;      // imaginary-part softbits sit 1536 bytes after the real ones; for the dummy area too
 struct __align__(16) DemodSmem {
     float2 inbuf[IN_CAP];            // 20 KB: one symbol, guard interval first, filled by one cp.async.bulk (TMA)
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
-    float2 tw[TwLayout::C5];         // 4 KB: twiddles of all stages but the last (those come through L1 with __ldg)
-    int8_t sbuf[3072 + 1664];
+    float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
+    int8_t sbuf[3072 + 64 + 1536 + 64];
     float red[16];
     uint64_t full;
 };
@@ -191,7 +195,8 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
     // pass C with the m=512 twiddles read through the read-only path (12 KB, L1 resident, lane-consecutive)
     {
-        const float2 w1 = sm.tw[TwLayout::C4 + t], w2 = sm.tw[TwLayout::C4 + 128 + t], w3 = sm.tw[TwLayout::C4 + 256 + t];
+        const float2* tw_c4 = tw_c5 - 384;
+        const float2 w1 = __ldg(tw_c4 + t), w2 = __ldg(tw_c4 + 128 + t), w3 = __ldg(tw_c4 + 256 + t);
 #pragma unroll
         for (int b = 0; b < 4; b++) bfly4<EXACT, false>(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3], w1, w2, w3);
 #pragma unroll
@@ -203,7 +208,7 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
 }
 
 template <bool EXACT, bool TAP>
-__global__ void __launch_bounds__(OFDM_THREADS, 4)
+__global__ void __launch_bounds__(OFDM_THREADS, DEMOD_CTAS_PER_SM)
 ofdm_demod_kernel(DevTables tb, OfdmParams p)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -230,7 +235,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     __syncthreads();
     if (t == 0) issue(l_first - 1);
 
-    for (int i = t; i < TwLayout::C5; i += OFDM_THREADS) sm.tw[i] = tb.tw_fwd[i];
+    if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
     const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
     // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
     const Nco ncoP = make_nco(p.nco ? p.nco[4 * f] : 0, p.nco ? p.nco[4 * f + 1] : 0);
@@ -287,7 +292,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
                 sm.sbuf[sidx[s]] = sre;
-                sm.sbuf[KC + sidx[s]] = sim;
+                sm.sbuf[SB_IM + sidx[s]] = sim;
                 if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
                 prev[s] = X;
             }
@@ -438,9 +443,47 @@ find_index_kernel(DevTables tb, SyncParams p)
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
     if ((t & 31) == 0) sm.wmin[t >> 5] = best;
     __syncthreads();
+    best = min(min(sm.wmin[0], sm.wmin[1]), min(sm.wmin[2], sm.wmin[3]));
+    if (t == 0) p.index_out[f] = best == (1 << 30) ? -1 : best;
+    if (!p.coarse_out) return;
+    if (t == 0) p.coarse_out[f] = 0;
+    if (best == (1 << 30) || p.fic_ratio[f] * 10 >= 50) return;      // CTA-uniform
+    // ---- coarse AFC: FFT of the aligned PRS (window start + index), then the "pattern of zeros" search over +-36 carriers
+    // (ofdm-processor.cpp:537-545,582-613).  Needs bins 2012..2047 and 0..58 in natural order: staged in sm.cir (as float2).
+    __syncthreads();
+    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_fwd[i];
+    __syncthreads();
+    // the PRS useful part starts `best` samples into the window; its samples continue the NCO phase sequence
+    Nco nco2 = nco;
+    if (nco.mix) nco2.lp0 = nco.lp0;       // fetch indices are relative to the window start, so the same lp0/ph apply with w0 = best
+    fft2048_from_global<EXACT, false>(src, best, v, sm.o, t, xi, tb.osc, nco2);
+    float2* spec = reinterpret_cast<float2*>(sm.cir);     // 128 entries: [0..35] = bins 2012..2047, [36..94] = bins 0..58
+    if (t < 59) spec[36 + t] = v[0];
+    if (t >= 92) spec[t - 92] = v[15];
+    __syncthreads();
+    float mysum = 1e30f;
+    if (t < 72) {
+        // candidate i = Tu - 36 + t; fft_buffer[(i + k) % Tu] = spec[t + k]
+        auto ap = [&](int a, int b) -> float {       // arg(X[a] * conj(X[b]))
+            const float2 A = spec[a], B = spec[b];
+            const float c = B.x, d = -B.y;
+            const float re = __fsub_rn(__fmul_rn(A.x, c), __fmul_rn(A.y, d)), im = __fadd_rn(__fmul_rn(A.x, d), __fmul_rn(A.y, c));
+            return atan2f(im, re);
+        };
+        const double PI = 3.14159265358979323846;
+        const float a1 = (float)fabs(fabs((double)ap(t + 1, t + 2) / PI) - 1);
+        const float a2 = (float)fabs(fabs((double)ap(t + 2, t + 3) / PI) - 1);
+        const float a3 = fabsf(ap(t + 3, t + 4)), a4 = fabsf(ap(t + 4, t + 5)), a5 = fabsf(ap(t + 5, t + 6));
+        const float b1 = (float)fabs(fabs((double)ap(t + 17, t + 19) / PI) - 1);
+        const float b2 = fabsf(ap(t + 19, t + 20)), b3 = fabsf(ap(t + 20, t + 21)), b4 = fabsf(ap(t + 21, t + 22));
+        mysum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4), a5), b1), b2), b3), b4);
+    }
+    sm.pk[t] = mysum;
+    __syncthreads();
     if (t == 0) {
-        best = min(min(sm.wmin[0], sm.wmin[1]), min(sm.wmin[2], sm.wmin[3]));
-        p.index_out[f] = best == (1 << 30) ? -1 : best;
+        float mmin = 1000.f; int index = 100;      // sequential first-minimum like the CPU loop
+        for (int i = 0; i < 72; i++) if (sm.pk[i] < mmin) { mmin = sm.pk[i]; index = TU - 36 + i; }
+        p.coarse_out[f] = index - TU;
     }
 }
 
@@ -455,7 +498,7 @@ template <typename K> static void set_smem(K k, size_t bytes)
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)
 {
     const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
-    const size_t sm = sizeof(DemodSmem);
+    const size_t sm = sizeof(DemodSmem) > (size_t)p.smem_floor ? sizeof(DemodSmem) : (size_t)p.smem_floor;
     const bool tap = p.r1 != nullptr;
 #define LAUNCH(E, T) do { set_smem(ofdm_demod_kernel<E, T>, sm); ofdm_demod_kernel<E, T><<<grid, block, sm, st>>>(tb, p); } while (0)
     if (fft_mode == 0) { if (tap) LAUNCH(true, true); else LAUNCH(true, false); }

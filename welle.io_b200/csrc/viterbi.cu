@@ -28,6 +28,14 @@ __device__ __forceinline__ uint32_t sym4(uint32_t w)   // four int8 softbits -> 
     return __vsubus4(w ^ 0x80808080u, 0x01010101u);
 }
 
+// one trellis step: four map entries (index into the punctured softbits or -1 = punctured -> softbit 0) -> four symbols
+__device__ __forceinline__ uint32_t gather_sym4(const int8_t* seg, uint2 m)
+{
+    const int i0 = (int16_t)(m.x & 0xFFFF), i1 = (int16_t)(m.x >> 16), i2 = (int16_t)(m.y & 0xFFFF), i3 = (int16_t)(m.y >> 16);
+    const uint32_t b0 = i0 >= 0 ? (uint8_t)seg[i0] : 0u, b1 = i1 >= 0 ? (uint8_t)seg[i1] : 0u, b2 = i2 >= 0 ? (uint8_t)seg[i2] : 0u, b3 = i3 >= 0 ? (uint8_t)seg[i3] : 0u;
+    return sym4(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -85,17 +93,13 @@ fic_prep_kernel(const int8_t* __restrict__ soft, int64_t soft_stride, const int3
     __syncthreads();
     uint32_t* dst = rows + (int64_t)cw * row_words;
     const int groups = row_words / 8;
+    const uint2* map2 = reinterpret_cast<const uint2*>(fic_map);     // four int16 indices per trellis step
     for (int w = t; w < groups * 8; w += 128) {
         const int g = w >> 3, s = w & 7, st = 6 * g + s;
         uint32_t v = 0;
         if (s < 6) {
             v = 0x7F7F7F7Fu;
-            if (st < 774) {
-                uint32_t packed = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) { const int m = fic_map[4 * st + k]; const int sb = m >= 0 ? seg[m] : 0; packed |= vit_sym(sb) << (8 * k); }
-                v = packed;
-            }
+            if (st < 774) v = gather_sym4(seg, map2[st]);
         }
         dst[w] = v;
     }
@@ -146,18 +150,13 @@ msc_prep_kernel(MscPrepParams p)
     const int cw = s * 4 + c;
     uint32_t* dst = p.rows + (int64_t)cw * p.row_words;
     const int groups = p.row_words / 8, nsteps = p.nsteps;
-    const int16_t* map = p.map;
+    const uint2* map2 = reinterpret_cast<const uint2*>(p.map);
     for (int w = t; w < groups * 8; w += 128) {
         const int g = w >> 3, q = w & 7, stp = 6 * g + q;
         uint32_t v = 0;
         if (q < 6) {
             v = 0x7F7F7F7Fu;
-            if (stp < nsteps) {
-                uint32_t packed = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) { const int m = map[4 * stp + k]; const int sb = m >= 0 ? frag_s[m] : 0; packed |= vit_sym(sb) << (8 * k); }
-                v = packed;
-            }
+            if (stp < nsteps) v = gather_sym4(frag_s, map2[stp]);
         }
         dst[w] = v;
     }
@@ -166,22 +165,24 @@ msc_prep_kernel(MscPrepParams p)
 
 // ------------------------------------------------------------------------------------------------ the decoder
 constexpr int VIT_THREADS = 128;
-constexpr int VIT_STAGES = 3;
+constexpr int VIT_STAGES_MAX = 3;
 constexpr int VIT_ROW_PITCH = 144;      // 128 B of symbols + 16 B pad: 16-byte reads of 8 consecutive rows hit 32 distinct banks
 constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
 
-struct __align__(16) VitSmem {
+template <int VIT_STAGES> struct __align__(16) VitSmemT {
     unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];
     uint64_t full[VIT_STAGES];
 };
 
-__global__ void __launch_bounds__(VIT_THREADS, 4)
-viterbi_kernel(ViterbiParams p)
+// VIT_STAGES = 3: stand-alone launches (deep prefetch).  VIT_STAGES = 1: 18 KB of shared memory so that one CTA fits into
+// what four OFDM CTAs leave free on an SM (the copy latency is then hidden by the co-resident OFDM warps).
+template <int VIT_STAGES>
+__device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int block)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    VitSmem& sm = *reinterpret_cast<VitSmem*>(smraw);
+    VitSmemT<VIT_STAGES>& sm = *reinterpret_cast<VitSmemT<VIT_STAGES>*>(smraw);
     const int t = threadIdx.x;
-    const int cw = blockIdx.x * VIT_THREADS + t;
+    const int cw = block * VIT_THREADS + t;
     const bool have = cw < p.n_cw;
     const int groups = p.nsteps / 6;                 // 6 steps per 32-byte group, 4 groups per 128-byte stage
     const int nstages = (groups + 3) / 4;
@@ -198,7 +199,7 @@ viterbi_kernel(ViterbiParams p)
 
     uint32_t Q[32];
     vit_init(Q);
-    uint2* dec = p.dec + (int64_t)blockIdx.x * p.nsteps * VIT_THREADS + t;
+    uint2* dec = p.dec + (int64_t)block * p.nsteps * VIT_THREADS + t;
 
     for (int s = 0; s < nstages; s++) {
         const int buf = s % VIT_STAGES;
@@ -246,6 +247,20 @@ viterbi_kernel(ViterbiParams p)
         }
         if ((tb & 31) == 0) { out[tb >> 5] = prbs ? acc ^ prbs[tb >> 5] : acc; acc = 0; }
     }
+}
+
+template <int VIT_STAGES>
+__global__ void __launch_bounds__(VIT_THREADS, 4)
+viterbi_kernel(ViterbiParams p) { viterbi_cta<VIT_STAGES>(p, blockIdx.x); }
+
+// several independent codeword sets (FIC + one per selected sub-channel slot) in one launch, so that their CTAs share the SMs
+template <int VIT_STAGES>
+__global__ void __launch_bounds__(VIT_THREADS, 4)
+viterbi_batch_kernel(ViterbiBatch b)
+{
+    int k = 0;
+    while (k + 1 < b.n && (int)blockIdx.x >= b.cta_end[k]) k++;
+    viterbi_cta<VIT_STAGES>(b.p[k], (int)blockIdx.x - (k ? b.cta_end[k - 1] : 0));
 }
 
 // one thread per frame: CRC of the 12 FIBs (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80)
@@ -322,12 +337,28 @@ void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_strid
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
 void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st) { msc_prep_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
 
-void launch_viterbi(const ViterbiParams& p, cudaStream_t st)
+void launch_viterbi(const ViterbiParams& p, cudaStream_t st, int stages)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmem)); attr = true; }
     const int blocks = (p.n_cw + VIT_THREADS - 1) / VIT_THREADS;
-    viterbi_kernel<<<blocks, VIT_THREADS, sizeof(VitSmem), st>>>(p);
+    if (stages == 1) {
+        viterbi_kernel<1><<<blocks, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(p);
+    } else {
+        cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemT<3>));
+        viterbi_kernel<3><<<blocks, VIT_THREADS, sizeof(VitSmemT<3>), st>>>(p);
+    }
+}
+
+void launch_viterbi_batch(ViterbiBatch& b, cudaStream_t st, int stages)
+{
+    int total = 0;
+    for (int k = 0; k < b.n; k++) { total += (b.p[k].n_cw + VIT_THREADS - 1) / VIT_THREADS; b.cta_end[k] = total; }
+    if (!total) return;
+    if (stages == 1) {
+        viterbi_batch_kernel<1><<<total, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(b);
+    } else {
+        cudaFuncSetAttribute(viterbi_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemT<3>));
+        viterbi_batch_kernel<3><<<total, VIT_THREADS, sizeof(VitSmemT<3>), st>>>(b);
+    }
 }
 
 size_t vit_dec_bytes(int n_cw, int nsteps) { return (size_t)((n_cw + VIT_THREADS - 1) / VIT_THREADS) * nsteps * VIT_THREADS * sizeof(uint2); }

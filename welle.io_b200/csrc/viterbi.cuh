@@ -41,6 +41,9 @@ struct ViterbiParams {
     const int32_t* valid;             // optional per-codeword flag
 };
 
+struct ViterbiBatch { int n; ViterbiParams p[5]; int cta_end[5]; };
+void launch_viterbi_batch(ViterbiBatch& b, cudaStream_t st, int stages = 3);
+
 int vit_row_words(int nsteps);
 size_t vit_dec_bytes(int n_cw, int nsteps);
 void launch_sym_rows_from_soft(const int8_t* soft, int n_cw, int nsteps, uint32_t* rows, cudaStream_t st);
@@ -48,7 +51,7 @@ void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_strid
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st);
 void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st);
 void launch_msc_expand(const int8_t* soft, int n, int frag, const int16_t* map, int nsteps, uint32_t* rows, int row_words, cudaStream_t st);
-void launch_viterbi(const ViterbiParams& p, cudaStream_t st);
+void launch_viterbi(const ViterbiParams& p, cudaStream_t st, int stages = 3);
 void launch_fic_crc(const uint8_t* fibs, const int32_t* active, int n_frames, int32_t* mask_out, cudaStream_t st);
 void launch_unpack_bits(const uint8_t* bytes, int64_t stride, int n_cw, int nbits, uint8_t* bits, cudaStream_t st);
 

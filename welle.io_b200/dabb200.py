@@ -15,6 +15,7 @@ L, K, TU, TS, TG, TNULL, TF = 76, 1536, 2048, 2552, 504, 2656, 196608
 SOFT_PER_FRAME = 75 * 3072
 MAX_SUBCH = 4
 FFT_EXACT, FFT_FMA = 0, 1
+IQ_CF32, IQ_U8, IQ_S8, IQ_S16LE, IQ_S16BE = 0, 1, 2, 3, 4
 FRAME_DECODED, FRAME_NEED_SAMPLES, FRAME_NO_SYNC, FRAME_ACQUIRING = 0, 1, 2, 3
 
 
@@ -53,7 +54,8 @@ assert RESULT_DTYPE.itemsize == C.sizeof(FrameResult), (RESULT_DTYPE.itemsize, C
 
 class IO(C.Structure):
     _fields_ = [("iq", C.c_void_p), ("iq_is_host", C.c_int32), ("stride_samples", C.c_int64), ("buf_start", C.c_void_p), ("buf_len", C.c_int64),
-                ("results", C.c_void_p), ("fibs", C.c_void_p), ("msc", C.c_void_p), ("msc_stride", C.c_int32), ("sf", C.c_void_p), ("sf_stride", C.c_int32)]
+                ("results", C.c_void_p), ("fibs", C.c_void_p), ("msc", C.c_void_p), ("msc_stride", C.c_int32), ("sf", C.c_void_p), ("sf_stride", C.c_int32),
+                ("iq_format", C.c_int32), ("reserved", C.c_int32)]
 
 
 EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_select_subchannel",
@@ -137,13 +139,14 @@ class DevBuf:
 
 class Context:
     def __init__(self, n_streams=1, device=0, fft_mode=FFT_EXACT, disable_coarse=True, keep_taps=False, n_subch_slots=1,
-                 max_subch_cu=0, ofdm_groups=0):
+                 max_subch_cu=0, ofdm_groups=0, coresident=False):
         self.lib = load_library()
         cfg = Config()
         cfg.abi_version = self.lib.dabb_abi_version()
         cfg.device, cfg.n_streams, cfg.transmission_mode = device, n_streams, 1
         cfg.fft_mode, cfg.disable_coarse, cfg.keep_taps = fft_mode, int(disable_coarse), int(keep_taps)
         cfg.n_subch_slots, cfg.max_subch_cu, cfg.ofdm_groups = n_subch_slots, max_subch_cu, ofdm_groups
+        cfg.reserved[0] = 2 if coresident else 0      # 2: cap the OFDM kernel at 4 CTAs/SM so that lane-B CTAs fit beside it (experimental)
         h = C.c_void_p()
         rc = self.lib.dabb_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -203,13 +206,14 @@ class Context:
     def remove_subchannel(self, slot=0, first=0, count=None):
         self._ck(self.lib.dabb_remove_subchannel(self.h, first, self.n_streams if count is None else count, slot))
 
-    def process(self, iq, stride, buf_start, buf_len, iq_is_host=False, msc_stride=0, sf_stride=0, want=("results", "fibs")):
+    def process(self, iq, stride, buf_start, buf_len, iq_is_host=False, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0):
         S = self.n_streams
         bs = np.ascontiguousarray(buf_start, np.int64)
         assert bs.size == S
         io = IO()
         io.iq = _addr(iq)
         io.iq_is_host, io.stride_samples, io.buf_len = int(iq_is_host), stride, buf_len
+        io.iq_format = iq_format
         io.buf_start = bs.ctypes.data
         out = {}
         if "results" in want:
