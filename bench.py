@@ -318,7 +318,7 @@ def main():
     # ---- e2e: host (pinned) IQ -> dabb_process -> host results
     e2e = None
     if not a.no_e2e:
-        Se = min(a.e2e_batch, S)
+        Se = min(a.e2e_batch if world == 1 else min(a.e2e_batch, 512), S)     # pinned host footprint per rank: Se x 9.5 MB
         ctx_e = pkg.Context(n_streams=Se, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
         ctx_e.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
         host = torch.empty((Se, BUF_LEN, 2), dtype=torch.float32).pin_memory()

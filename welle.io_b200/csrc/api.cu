@@ -664,12 +664,12 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->groups, d_fc);
     if ((rc = check_launch(ctx, "advance_kernel"))) return rc;
     if (!serial) { CK(cudaEventRecord(ctx->evA[par], A)); CK(cudaStreamWaitEvent(B, ctx->evA[par], 0)); }
-    // ---------------- lane B: de-puncturing for FIC and every selected slot, ONE Viterbi launch over all codeword sets,
-    // then CRC / RS and the result record
-    launch_fic_prep(ctx->dev, d_soft, DABB_SOFT_PER_FRAME, d_active, S, ctx->d_fic_rows, B);
-    if ((rc = check_launch(ctx, "fic_prep_kernel"))) return rc;
-    ViterbiBatch vb{}; vb.n = 0;
-    vb.p[vb.n++] = fic_viterbi_params(ctx, S, ctx->d_fibs, ctx->d_dec_fic);
+    // ---------------- lane B: FIC chain forked onto its own stream, MSC chain per slot (longest first), then the result record.
+    // (One fused Viterbi launch over FIC + MSC codewords was measured slower: 1.44 ms vs 0.34 + 1.02 ms.)
+    cudaStream_t F = serial ? ctx->stream : ctx->stream2;
+    if (!serial) { CK(cudaEventRecord(ctx->ev_ofdm, B)); CK(cudaStreamWaitEvent(F, ctx->ev_ofdm, 0)); }
+    if ((rc = run_fic(ctx, d_soft, DABB_SOFT_PER_FRAME, d_active, S, ctx->d_fibs, ctx->d_crc, F, ctx->d_dec_fic))) return rc;
+    if (!serial) CK(cudaEventRecord(ctx->ev_fic, F));
     const int32_t* h_info[DABB_MAX_SUBCH] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < ctx->n_slots; k++) {
         auto& sl = ctx->slot[k];
@@ -686,21 +686,14 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         if ((rc = check_launch(ctx, "msc_prep_kernel"))) return rc;
         ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
-        vb.p[vb.n++] = vp;
-    }
-    launch_viterbi_batch(vb, B, 3);
-    if ((rc = check_launch(ctx, "viterbi_kernel(FIC+MSC)"))) return rc;
-    launch_fic_crc(ctx->d_fibs, d_active, S, ctx->d_crc, B);
-    if ((rc = check_launch(ctx, "fic_crc_kernel"))) return rc;
-    for (int k = 0; k < ctx->n_slots; k++) {
-        auto& sl = ctx->slot[k];
-        if (!sl.configured) continue;
-        const int flen_pad = (sl.flen + 15) & ~15;
+        launch_viterbi(vp, B, ctx->vit_stages_now);
+        if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
         SuperframeParams fp{}; fp.active = d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;
         fp.valid = sl.d_valid; fp.window = sl.d_window; fp.window_pitch = 5 * flen_pad; fp.sf_out = sl.d_sf; fp.sf_pitch = 5 * flen_pad; fp.info = sl.d_info; fp.gf_exp = ctx->dev.gf_exp; fp.gf_log = ctx->dev.gf_log;
         launch_superframe(fp, B);
         if ((rc = check_launch(ctx, "superframe_kernel"))) return rc;
     }
+    if (!serial) CK(cudaStreamWaitEvent(B, ctx->ev_fic, 0));
     CK(cudaMemcpyAsync((void*)ctx->d_info_tab, h_info, sizeof(void*) * DABB_MAX_SUBCH, cudaMemcpyHostToDevice, B));
     finalize_kernel<<<gb, tb, 0, B>>>(scr, ctx->d_slots, ctx->n_slots, S, ctx->d_fic_ratio, d_snr, ctx->d_crc, ctx->d_info_tab, ctx->d_results);
     if ((rc = check_launch(ctx, "finalize_kernel"))) return rc;

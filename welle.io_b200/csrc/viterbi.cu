@@ -213,7 +213,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
             const uint4 a = my[2 * gq], b = my[2 * gq + 1];
             const uint32_t w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
             uint32_t d[12];
-            vit_six_steps(Q, w, d);
+            vit_six_steps(Q, w, d, p.one);
             if (have) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) dec[(int64_t)(6 * g + k) * VIT_THREADS] = make_uint2(d[2 * k], d[2 * k + 1]);
@@ -337,8 +337,9 @@ void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_strid
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
 void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st) { msc_prep_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
 
-void launch_viterbi(const ViterbiParams& p, cudaStream_t st, int stages)
+void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
 {
+    ViterbiParams p = p_in; p.one = 1u;
     const int blocks = (p.n_cw + VIT_THREADS - 1) / VIT_THREADS;
     if (stages == 1) {
         viterbi_kernel<1><<<blocks, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(p);
@@ -351,7 +352,7 @@ void launch_viterbi(const ViterbiParams& p, cudaStream_t st, int stages)
 void launch_viterbi_batch(ViterbiBatch& b, cudaStream_t st, int stages)
 {
     int total = 0;
-    for (int k = 0; k < b.n; k++) { total += (b.p[k].n_cw + VIT_THREADS - 1) / VIT_THREADS; b.cta_end[k] = total; }
+    for (int k = 0; k < b.n; k++) { total += (b.p[k].n_cw + VIT_THREADS - 1) / VIT_THREADS; b.cta_end[k] = total; b.p[k].one = 1u; }
     if (!total) return;
     if (stages == 1) {
         viterbi_batch_kernel<1><<<total, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(b);

@@ -39,6 +39,7 @@ struct ViterbiParams {
     uint8_t* out; int64_t out_stride; // packed bytes, multiple of 4
     const uint32_t* prbs_words;       // energy-dispersal sequence packed like the output (or nullptr)
     const int32_t* valid;             // optional per-codeword flag
+    uint32_t one;                     // = 1 (set by the launcher; keeps a multiply-add opaque to the assembler, see viterbi_core.cuh)
 };
 
 struct ViterbiBatch { int n; ViterbiParams p[5]; int cta_end[5]; };

@@ -83,14 +83,18 @@ VIT_HD void vit_metrics(uint32_t w, uint32_t E[8])
 
 // One ACS step from layout L_B to L_{(B+1)%6}.  Q: 32 packed metric registers; dlo/dhi: decision bits of new states
 // 0..31 / 32..63.
-template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], uint32_t& dlo, uint32_t& dhi)
+template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], uint32_t& dlo, uint32_t& dhi, const uint32_t one)
 {
+    (void)one;
     uint32_t N[32];
     // decision bits are OR-ed into four partial words per half (short dependency chains, no branches)
     uint32_t pl_[4] = {0, 0, 0, 0}, ph_[4] = {0, 0, 0, 0};
 #if defined(__CUDA_ARCH__)
-    // forced predication: `@!p or.b32 acc, acc, bit` (the compiler otherwise turns some of these into divergent branches)
-#define VIT_OR_IF_NOT(acc, pred_le, bitconst) asm("{\n.reg .pred q;\nsetp.eq.u32 q, %1, 0;\n@q or.b32 %0, %0, %2;\n}" : "+r"(acc) : "r"((uint32_t)(pred_le)), "r"((uint32_t)(bitconst)))
+    // forced predication (the compiler otherwise turns some of these into divergent branches).  The bit is ADDED with a
+    // predicated multiply-add (`@!p mad.lo acc = bit * 1 + acc`; every bit is set at most once, so add == or): that is an
+    // IMAD on the FMA pipe, which balances the ALU pipe where the packed min/add instructions already run at half rate.
+    // `one` is the value 1 passed through a kernel parameter so that the assembler cannot fold the multiply away.
+#define VIT_OR_IF_NOT(acc, pred_le, bitconst) asm("{\n.reg .pred q;\nsetp.eq.u32 q, %1, 0;\n@q mad.lo.u32 %0, %2, %3, %0;\n}" : "+r"(acc) : "r"((uint32_t)(pred_le)), "r"((uint32_t)(bitconst)), "r"(one))
 #else
 #define VIT_OR_IF_NOT(acc, pred_le, bitconst) do { if (!(pred_le)) (acc) |= (bitconst); } while (0)
 #endif
@@ -159,15 +163,15 @@ VIT_HD void vit_normalize(uint32_t (&Q)[32])
 }
 
 // six steps: words w[0..5] hold the symbols, dec[2*s], dec[2*s+1] receive the decision words
-VIT_HD void vit_six_steps(uint32_t (&Q)[32], const uint32_t w[6], uint32_t dec[12])
+VIT_HD void vit_six_steps(uint32_t (&Q)[32], const uint32_t w[6], uint32_t dec[12], const uint32_t one = 1u)
 {
     uint32_t E[8];
-    vit_metrics(w[0], E); vit_acs<0>(Q, E, dec[0], dec[1]);
-    vit_metrics(w[1], E); vit_acs<1>(Q, E, dec[2], dec[3]);
-    vit_metrics(w[2], E); vit_acs<2>(Q, E, dec[4], dec[5]);
-    vit_metrics(w[3], E); vit_acs<3>(Q, E, dec[6], dec[7]);
-    vit_metrics(w[4], E); vit_acs<4>(Q, E, dec[8], dec[9]);
-    vit_metrics(w[5], E); vit_acs<5>(Q, E, dec[10], dec[11]);
+    vit_metrics(w[0], E); vit_acs<0>(Q, E, dec[0], dec[1], one);
+    vit_metrics(w[1], E); vit_acs<1>(Q, E, dec[2], dec[3], one);
+    vit_metrics(w[2], E); vit_acs<2>(Q, E, dec[4], dec[5], one);
+    vit_metrics(w[3], E); vit_acs<3>(Q, E, dec[6], dec[7], one);
+    vit_metrics(w[4], E); vit_acs<4>(Q, E, dec[8], dec[9], one);
+    vit_metrics(w[5], E); vit_acs<5>(Q, E, dec[10], dec[11], one);
 }
 
 // soft bit (int8, 0 = punctured) -> decoder symbol clamp(s + 127, 0, 255)  (viterbi.cpp:232-237)
