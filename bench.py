@@ -314,6 +314,31 @@ def main():
            "frac": acs_s * 4 / peak_ops, "acs_per_s": acs_s, "ms_per_step": vms, "f_sm_mhz": f_sm / 1e6,
            "note": "4 int-ops per add-compare-select (SURVEY 8d); the kernel packs two states per 32-bit lane-op"}
 
+    # the same OFDM kernel in DABB_FFT_FMA arithmetic (contracted multiply-adds: <= 1e-6 relative on the spectra, softbits within
+    # 1 LSB; integer outputs unchanged in the tests) timed alone through the stage-level entry point, for comparison
+    fma = None
+    try:
+        Cc = pkg.dabb200.C
+        ctx_f = pkg.Context(n_streams=1, device=local, fft_mode=pkg.FFT_FMA)
+        softf = torch.empty((S, 75 * 3072), dtype=torch.int8, device=dev)
+        prsf = torch.full((S,), TNULL + 305 + TF, dtype=torch.int64, device=dev)
+        extf = torch.cuda.ExternalStream(ctx_f.cuda_stream(), device=dev)
+        dur = []
+        for i in range(5):
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            prsf.fill_(TNULL + 305 + TF * (1 + i % 4)); torch.cuda.synchronize()
+            k0.record(extf)
+            ctx_f._ck(ctx_f.lib.dabb_ofdm_demod(ctx_f.h, Cc.c_void_p(buf.data_ptr()), Cc.c_int64(BUF_LEN), Cc.c_void_p(prsf.data_ptr()), S, None, Cc.c_void_p(softf.data_ptr()), None, None))
+            k1.record(extf); torch.cuda.synchronize()
+            if i >= 2:
+                dur.append(k0.elapsed_time(k1))
+        fms = float(np.mean(dur))
+        fma = {"ms_per_launch": fms, "achieved": S * OFDM_BYTES_PER_FRAME / (fms * 1e-3) / 1e9, "frac": S * OFDM_BYTES_PER_FRAME / (fms * 1e-3) / 1e9 / hbm_peak,
+               "note": "ofdm_demod_kernel<FMA> alone (stage API, sync'd launches); the default and every other number in this line use the bit-exact arithmetic"}
+        ctx_f.close(); del softf, prsf
+    except Exception as e:  # noqa
+        fma = {"error": repr(e)}
+    roofline["fma_mode"] = fma
     log("kernel profile done")
     # ---- e2e: host (pinned) IQ -> dabb_process -> host results
     e2e = None

@@ -139,13 +139,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 #define DEMOD_CTAS_PER_SM 5
 #endif
 constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
-constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real; unused bins write into a 64-byte dummy area behind it
+constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real; every thread's one unused bin writes to its own dummy byte behind it
 constexpr int SB_IM = 1536;      // imaginary-part softbits sit 1536 bytes after the real ones; for the dummy area too
 struct __align__(16) DemodSmem {
     float2 inbuf[IN_CAP];            // 20 KB: one symbol, guard interval first, filled by one cp.async.bulk (TMA)
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
-    int8_t sbuf[3072 + 64 + 1536 + 64];
+    int8_t sbuf[3072 + 128 + 1536];   // re [0,1536) | im [1536,3072) | dummy re [3072,3200) | (gap) | dummy im [4608,4736)
     float red[16];
     uint64_t full;
 };
@@ -244,7 +244,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
     int sidx[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + (t & 63); }
+    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
     __syncthreads();
 
     float2 prev[NSLOT];
