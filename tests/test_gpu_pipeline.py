@@ -143,3 +143,49 @@ def test_raw_sample_formats(oracle):
         assert n >= 6
         for f in range(n):
             assert np.array_equal(fibs[f], o["fibs"][12 * f:12 * f + 12, 1:]) and crcs[f] == 0xFFF, (fmt, f)
+
+
+def test_two_subchannel_slots_and_remove(oracle):
+    """two sub-channels decoded at once (slot 0: the DAB+ EEP-3A service; slot 1: a 64 kbit/s UEP-3 DAB/MP2 sub-channel placed on
+    the random-filled capacity units 200..247), then slot 1 removed.  Slot 1's logical frames must equal the oracle's
+    time-de-interleaver + UEP Viterbi + dispersal applied to the softbits the GPU itself produced."""
+    pkg = load_pkg()
+    tx = dabtx.DabTx(seed=0x2222)
+    sig = tx.frames(12)
+    ctx = pkg.Context(n_streams=1, keep_taps=True, n_subch_slots=2)
+    d = ctx.dev(sig.reshape(1, -1))
+    n = len(sig)
+    prot = oracle.prot_uep(64, 3)
+    cu1, start1 = 48, 200
+    cifs, got1, got0 = [], [], []
+    selected = removed = False
+    for step in range(12):
+        out = ctx.process(d, n, np.zeros(1, np.int64), n, msc_stride=288)
+        r = out["results"]
+        if r["status"][0] != pkg.FRAME_DECODED or r["next_pos"][0] > n:
+            continue
+        if selected and not removed:
+            soft = ctx.read_tap(0)[0]
+            for c in range(4):
+                cifs.append(soft[3 + 18 * c: 21 + 18 * c].reshape(-1)[start1 * 64:(start1 + cu1) * 64].copy())
+            for c in range(4 - int(r["n_logical"][0][1]), 4):
+                got1.append(out["msc"][0, 1, c, :192].copy())
+        if selected:
+            for c in range(4 - int(r["n_logical"][0][0]), 4):
+                got0.append(out["msc"][0, 0, c, :288].copy())
+            assert int(r["n_rs_events"][0][1]) == 0          # DAB (MP2) sub-channel: no superframe / RS handling
+        if not selected:
+            ctx.select_subchannel(0, 72, 96, eep_profile_a=True, eep_level=3, dabplus=True, slot=0)
+            ctx.select_subchannel(start1, cu1, 64, short_form=True, uep_level=3, dabplus=False, slot=1)
+            selected = True
+        elif len(cifs) >= 28 and not removed:
+            ctx.remove_subchannel(slot=1); removed = True
+    ctx.close()
+    de = oracle.deinterleave(np.stack(cifs))
+    exp = [oracle.pack_bits(oracle.msc_deconvolve(prot, x[:prot.in_bits], True)) for x in de]
+    assert len(got1) == len(exp) >= 8
+    for a, b in zip(got1, exp):
+        assert np.array_equal(a, b)
+    lf = np.concatenate(tx.logical); g0 = np.concatenate(got0)
+    hits = [k for k in range(40) if np.array_equal(g0[:288], lf[k * 288:(k + 1) * 288])]
+    assert hits and np.array_equal(g0, lf[hits[0] * 288: hits[0] * 288 + len(g0)])

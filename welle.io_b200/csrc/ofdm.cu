@@ -139,13 +139,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 #define DEMOD_CTAS_PER_SM 5
 #endif
 constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
-constexpr int SB_DUMMY = 3072;   // softbit staging: [0,3072) real; every thread's one unused bin writes to its own dummy byte behind it
-constexpr int SB_IM = 1536;      // imaginary-part softbits sit 1536 bytes after the real ones; for the dummy area too
+constexpr int SB_DUMMY = 1536;   // softbit staging as (re, im) byte pairs indexed by logical carrier: [0,1536) real entries, then one private
+                                 // dummy entry per thread for its unused bin
 struct __align__(16) DemodSmem {
     float2 inbuf[IN_CAP];            // 20 KB: one symbol, guard interval first, filled by one cp.async.bulk (TMA)
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
-    int8_t sbuf[3072 + 128 + 1536];   // re [0,1536) | im [1536,3072) | dummy re [3072,3200) | (gap) | dummy im [4608,4736)
+    uint16_t sbuf[1536 + 128];        // (re | im << 8) per logical carrier: one 16-bit scatter store per carrier
     float red[16];
     uint64_t full;
 };
@@ -291,18 +291,23 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 const float2 X = v[slot_c(s)];
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
-                sm.sbuf[sidx[s]] = sre;
-                sm.sbuf[SB_IM + sidx[s]] = sim;
+                sm.sbuf[sidx[s]] = (uint16_t)((uint8_t)sre | ((uint16_t)(uint8_t)sim << 8));
                 if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
                 prev[s] = X;
             }
             __syncthreads();                   // (3)
-            // 3072 B -> global, 16 B per store
-            {
+            // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits) and store 16 B per thread and half
+            if (t < 96) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(sm.sbuf) + 2 * t;     // 16 pairs
+                const uint4 a = s4[0], b = s4[1];
+                uint4 re, im;
+                re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
+                re.y = __byte_perm(a.z, a.w, 0x6420); im.y = __byte_perm(a.z, a.w, 0x7531);
+                re.z = __byte_perm(b.x, b.y, 0x6420); im.z = __byte_perm(b.x, b.y, 0x7531);
+                re.w = __byte_perm(b.z, b.w, 0x6420); im.w = __byte_perm(b.z, b.w, 0x7531);
                 uint4* dst = reinterpret_cast<uint4*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
-                const uint4* s4 = reinterpret_cast<const uint4*>(sm.sbuf);
-                dst[t] = s4[t];
-                if (t < 64) dst[128 + t] = s4[128 + t];
+                dst[t] = re;
+                dst[96 + t] = im;
             }
         } else {
             // reference symbol only (the PRS when l == 0): keep its spectrum, estimate SNR from the PRS
