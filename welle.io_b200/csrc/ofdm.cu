@@ -11,6 +11,7 @@
 // 75*3072 out.  One 128-thread CTA walks `sym_per_cta` consecutive symbols of one frame and keeps
 // the previous symbol's spectrum in registers (differential demodulation needs only that).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace dabb {
 
@@ -152,7 +153,9 @@ struct __align__(16) DemodSmem {
 
 // one symbol's samples, already in shared memory at in[0..], -> spectrum in registers (same pass structure as
 // fft2048_from_global); idx0 = frame-relative index of in[0] for the NCO phase
-template <bool EXACT>
+template <bool DIRECT> __device__ __forceinline__ float2 ld_in(const float2* in, int i) { return DIRECT ? __ldg(in + i) : in[i]; }
+
+template <bool EXACT, bool DIRECT>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
                                                   const float2* __restrict__ tw_c5, const float2* __restrict__ osc, const Nco& nco)
 {
@@ -160,7 +163,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int c = 0; c < 8; c++) x[8 * h + c] = in[t + 128 * h + 256 * c];
+        for (int c = 0; c < 8; c++) x[8 * h + c] = ld_in<DIRECT>(in, t + 128 * h + 256 * c);
     if (nco.mix) {
         int32_t lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
 #pragma unroll
@@ -207,7 +210,7 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     }
 }
 
-template <bool EXACT, bool TAP>
+template <bool EXACT, bool TAP, bool DIRECT>
 __global__ void __launch_bounds__(OFDM_THREADS, DEMOD_CTAS_PER_SM)
 ofdm_demod_kernel(DevTables tb, OfdmParams p)
 {
@@ -233,7 +236,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     };
     if (t == 0) { mbar_init(&sm.full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    if (t == 0) issue(l_first - 1);
+    if (!DIRECT && t == 0) issue(l_first - 1);
 
     if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
     const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
@@ -256,10 +259,10 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         const int goff = (l == 0) ? 0 : TG;
         const int shift = (int)((reinterpret_cast<uintptr_t>(src + s0) >> 3) & 1);
         const Nco& nco = l == 0 ? ncoP : ncoS;
-        mbar_wait(&sm.full, parity); parity ^= 1;
-        const float2* in = sm.inbuf + shift;
+        if (!DIRECT) { mbar_wait(&sm.full, parity); parity ^= 1; }
+        const float2* in = DIRECT ? (src + s0) : (sm.inbuf + shift);
         float2 v[16];
-        fft2048_from_smem<EXACT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb.osc, nco);
+        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb.osc, nco);
         if (l >= l_first) {
             // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
             // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = t + 128 r).
@@ -269,7 +272,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
             for (int r = 0; r < 4; r++) {
                 const int i = t + 128 * r;
                 if (i < TG) {
-                    float2 a = in[TU + i], b = in[i];
+                    float2 a = ld_in<DIRECT>(in, TU + i), b = ld_in<DIRECT>(in, i);
                     if (nco.mix) { a = mix_sample(a, tb.osc, lpa); b = mix_sample(b, tb.osc, lpb); }
                     fc.x += a.x * b.x + a.y * b.y;
                     fc.y += a.y * b.x - a.x * b.y;
@@ -278,7 +281,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
             }
         }
         __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
-        if (t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
+        if (!DIRECT && t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(l + 1);
         }
@@ -505,9 +508,10 @@ void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, c
     const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
     const size_t sm = sizeof(DemodSmem) > (size_t)p.smem_floor ? sizeof(DemodSmem) : (size_t)p.smem_floor;
     const bool tap = p.r1 != nullptr;
-#define LAUNCH(E, T) do { set_smem(ofdm_demod_kernel<E, T>, sm); ofdm_demod_kernel<E, T><<<grid, block, sm, st>>>(tb, p); } while (0)
-    if (fft_mode == 0) { if (tap) LAUNCH(true, true); else LAUNCH(true, false); }
-    else { if (tap) LAUNCH(false, true); else LAUNCH(false, false); }
+#define LAUNCH(E, T, D) do { set_smem(ofdm_demod_kernel<E, T, D>, sm); ofdm_demod_kernel<E, T, D><<<grid, block, sm, st>>>(tb, p); } while (0)
+    static const bool direct = getenv("DABB_OFDM_DIRECT") != nullptr;    // experiment: global -> register loads instead of TMA staging
+    if (fft_mode == 0) { if (tap) LAUNCH(true, true, false); else if (direct) LAUNCH(true, false, true); else LAUNCH(true, false, false); }
+    else { if (tap) LAUNCH(false, true, false); else LAUNCH(false, false, false); }
 #undef LAUNCH
 }
 
