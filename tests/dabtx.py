@@ -204,10 +204,13 @@ class DabTx:
         self.cif_count = 0
 
     # ---- DAB+ superframe
-    def superframe(self, bad_au=None):
+    def superframe(self, bad_au=None, au_starts=None):
+        """one DAB+ superframe (dac_rate=1, sbr=0: 6 AUs); au_starts = the five explicit AU start addresses (else even)"""
         S = self.S; n_data = 110 * S
         sf = np.zeros(120 * S, np.uint8)
         au = [11] + [11 + (n_data - 11) * i // 6 for i in range(1, 6)] + [n_data]
+        if au_starts is not None:
+            au = [11] + [int(x) for x in au_starts] + [n_data]
         sf[2] = 0x40
         a = au
         sf[3] = a[1] >> 4; sf[4] = ((a[1] & 0xF) << 4) | (a[2] >> 8); sf[5] = a[2] & 0xFF
@@ -217,10 +220,13 @@ class DabTx:
         sf[0], sf[1] = fc >> 8, fc & 0xFF
         for i in range(6):
             ln = a[i + 1] - a[i]
-            body = self.rng.integers(0, 256, ln - 2, dtype=np.uint8)
+            body = self.rng.integers(0, 256, max(ln - 2, 0), dtype=np.uint8)
+            if ln < 2:
+                continue
             # first syntactic element = ID_END (111): the reference's AAC decoder (out of scope) rejects the AU cleanly instead of
             # mis-parsing random bytes (which can make it throw, dabplus_decoder.cpp:460), and no PAD is signalled (:148-149)
-            body[0] |= 0xE0
+            if len(body):
+                body[0] |= 0xE0
             c = crc16(body)
             if bad_au is not None and i == bad_au:
                 c ^= 0xFFFF

@@ -171,3 +171,35 @@ def test_rs_superframes(ctx, oracle):
         assert info[i, 2] == ev[0]["sync"]
         if ev[0]["sync"]:
             assert (info[i, 3] & 0xFF) == ev[0]["au_ok"] and (info[i, 3] >> 8) == ev[0]["num_aus"]
+
+
+@pytest.mark.parametrize("bitrate", [32, 96, 192])
+def test_rs_superframes_au_layouts(ctx, oracle, bitrate):
+    """AU CRCs over odd layouts (AUs of 2, 3, 4, 17, 18, 33 bytes, AUs that are not multiples of the CRC chunk) and with single
+    corrupted AUs; compared with the oracle's SuperframeFilter restatement (dabplus_decoder.cpp:122-131,171-215)"""
+    rng = np.random.default_rng(bitrate)
+    tx = dabtx.DabTx(seed=11, bitrate=bitrate)
+    n_data = 110 * bitrate // 8
+    sfs = []
+    small = [2, 3, 4, 17, 18, 33, 16, 32, 19]
+    for i in range(48):
+        if i % 3 == 0:
+            lens = [small[(i + k) % len(small)] for k in range(5)]
+        else:
+            room = n_data - 11 - 12
+            cuts = np.sort(rng.choice(np.arange(1, room // 2), 5, replace=False)) * 2 + (i & 1)
+            lens = np.diff(np.concatenate([[0], cuts])).tolist()
+            lens = [max(2, int(x)) for x in lens]
+        starts = 11 + np.cumsum(lens)
+        if starts[-1] >= n_data - 1:
+            continue
+        sf = tx.superframe(bad_au=(i % 6 if i % 4 == 0 else None), au_starts=starts)
+        sfs.append(sf)
+    assert len(sfs) > 20
+    sfs = np.stack(sfs)
+    out, info = ctx.rs_superframes(sfs)
+    for i in range(len(sfs)):
+        ev, _ = oracle.superframe_filter(sfs[i].reshape(5, -1))
+        assert info[i, 2] == ev[0]["sync"] == 1, i
+        assert (info[i, 3] & 0xFF) == ev[0]["au_ok"] and (info[i, 3] >> 8) == ev[0]["num_aus"], (i, info[i], ev[0])
+        assert np.array_equal(out[i], sfs[i])

@@ -511,6 +511,7 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
     if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
     if (sc->length_cu < 1 || sc->length_cu > ctx->max_cu || sc->start_cu < 0 || sc->start_cu + sc->length_cu > 864) { ctx->err = "sub-channel does not fit (raise dabb_config.max_subch_cu)"; return DABB_E_ARG; }
     if (prof.in_bits > sc->length_cu * 64) { ctx->err = "protection profile needs more bits than the sub-channel holds"; return DABB_E_ARG; }
+    if (sc->dabplus && sc->bitrate / 8 > 64) { ctx->err = "DAB+ sub-channels above 512 kbit/s are not supported"; return DABB_E_UNSUPPORTED; }
     auto& sl = ctx->slot[slot];
     const int S = ctx->S;
     int rc = 0;
@@ -887,6 +888,7 @@ int dabb_msc_decode(dabb_ctx* ctx, const dabb_subchannel* sc, const int8_t* soft
 int dabb_rs_superframes(dabb_ctx* ctx, uint8_t* sf, int32_t n, int32_t sf_len, int32_t* info)
 {
     if (!ctx || !sf || !info || n < 1 || sf_len < 120 || (sf_len % 120)) return DABB_E_ARG;
+    if (sf_len / 120 > 64) { ctx->err = "superframes above 512 kbit/s (64 interleaved codewords) are not supported"; return DABB_E_UNSUPPORTED; }
     cudaSetDevice(ctx->device);
     sync_all(ctx);
     launch_rs_superframes(sf, n, sf_len, info, ctx->dev.gf_exp, ctx->dev.gf_log, ctx->stream);

@@ -20,8 +20,6 @@ namespace {
 struct __align__(16) OfdmSmem {
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
     float2 tw[TwLayout::TOTAL];      // ~16 KB per-stage twiddles
-    int8_t sbuf[3072];               // one symbol of softbits
-    float red[16];
 };
 
 // ---- NCO (ofdm-processor.cpp:211-214): sample idx of the frame is multiplied by osc[(lp0 - idx*ph) mod 2 048 000].
@@ -352,13 +350,14 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
 struct __align__(16) SyncSmem {
     OfdmSmem o;
     float cir[TU];
-    float pk[TU];
+    float2 spec[128];
+    float cand[128];
     float wmax[4]; int wmin[4];
     float sum;
 };
 
 template <bool EXACT, bool NCO>
-__global__ void __launch_bounds__(OFDM_THREADS, 2)
+__global__ void __launch_bounds__(OFDM_THREADS, 4)
 find_index_kernel(DevTables tb, SyncParams p)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -372,8 +371,9 @@ find_index_kernel(DevTables tb, SyncParams p)
     const XIdx xi = make_xidx(t);
     float2 v[16];
     fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb.osc, nco);
-    // res = X * conj(ref), staged to global-order in a second buffer: reuse cir/pk as a float2[2048] scratch
-    float2* scratch = reinterpret_cast<float2*>(sm.cir);   // cir+pk are contiguous: 2*2048 floats
+    // res = X * conj(ref), written in natural order into the exchange buffer (free between the two transforms)
+    float2* scratch = sm.o.xbuf;
+    __syncthreads();             // pass C of the forward transform has read xbuf
 #pragma unroll
     for (int c = 0; c < 16; c++) {
         const int bin = t + 128 * c;
@@ -424,18 +424,37 @@ find_index_kernel(DevTables tb, SyncParams p)
     }
     __syncthreads();
     if (p.cir_out) for (int i = t; i < TU; i += OFDM_THREADS) p.cir_out[(int64_t)f * TU + i] = sm.cir[i];
-    if (t == 0) { float s = 0.f; for (int i = 0; i < TU; i++) s = __fadd_rn(s, sm.cir[i]); sm.sum = s; }
-    // sliding maximum over 100 samples for i < 1948, 0 beyond (phasereference.cpp:222-238)
-    float gmax = -10000.f;
-    for (int i = t; i < TU; i += OFDM_THREADS) {
-        float m = 0.f;
-        if (i + 100 < TU) {
-            m = -10000.f;
-            for (int j = 0; j < 100; j++) m = fmaxf(m, sm.cir[i + j]);
-            gmax = fmaxf(gmax, m);
+    // sliding maximum over 100 samples for i < 1948, 0 beyond (phasereference.cpp:222-238).  max() is exact, so the
+    // window maximum is built by doubling (2, 4, .. 64 samples, then max(m64[i], m64[i+36])) through the two halves of
+    // the exchange buffer instead of 100 compares per output.  The sequential sum of |.| (same order as the CPU loop, so
+    // the same float) is spread by thread 0 over the seven phases.
+    float* ma = reinterpret_cast<float*>(sm.o.xbuf);
+    float* mb = ma + TU;
+    float* pk = ma;
+    float ssum = 0.f;
+    {
+        const float* srcm = sm.cir;
+        float* dstm = ma;
+#pragma unroll 1
+        for (int lvl = 0; lvl < 6; lvl++) {
+            const int sh = 1 << lvl;
+#pragma unroll
+            for (int c = 0; c < 16; c++) { const int i = t + 128 * c; dstm[i] = fmaxf(srcm[i], srcm[min(i + sh, TU - 1)]); }
+            if (t == 0) { for (int i = 293 * lvl; i < 293 * (lvl + 1); i++) ssum = __fadd_rn(ssum, sm.cir[i]); }
+            __syncthreads();
+            srcm = dstm; dstm = (dstm == ma) ? mb : ma;
         }
-        sm.pk[i] = m;
     }
+    // six levels: cir -> ma -> mb -> ma -> mb -> ma -> mb; m64 now in mb, result into ma
+    float gmax = -10000.f;
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const int i = t + 128 * c;
+        float m = 0.f;
+        if (i + 100 < TU) { m = fmaxf(mb[i], mb[i + 36]); gmax = fmaxf(gmax, m); }
+        pk[i] = m;
+    }
+    if (t == 0) { for (int i = 293 * 6; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
     if ((t & 31) == 0) sm.wmax[t >> 5] = gmax;
@@ -445,7 +464,7 @@ find_index_kernel(DevTables tb, SyncParams p)
     // `3 * sum / Tu`: float 3*sum, then / (size_t Tu converted to float)
     if (gmax > __fdiv_rn(__fmul_rn(3.0f, sm.sum), 2048.0f)) {
         const float thresh = gmax / 2;
-        for (int i = t; i + 100 < TU; i += OFDM_THREADS) if (sm.pk[i + 100] > thresh) { best = min(best, i); }
+        for (int i = t; i + 100 < TU; i += OFDM_THREADS) if (pk[i + 100] > thresh) { best = min(best, i); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
@@ -465,7 +484,7 @@ find_index_kernel(DevTables tb, SyncParams p)
     Nco nco2 = nco;
     if (nco.mix) nco2.lp0 = nco.lp0;       // fetch indices are relative to the window start, so the same lp0/ph apply with w0 = best
     fft2048_from_global<EXACT, false>(src, best, v, sm.o, t, xi, tb.osc, nco2);
-    float2* spec = reinterpret_cast<float2*>(sm.cir);     // 128 entries: [0..35] = bins 2012..2047, [36..94] = bins 0..58
+    float2* spec = sm.spec;     // [0..35] = bins 2012..2047, [36..94] = bins 0..58
     if (t < 59) spec[36 + t] = v[0];
     if (t >= 92) spec[t - 92] = v[15];
     __syncthreads();
@@ -486,11 +505,11 @@ find_index_kernel(DevTables tb, SyncParams p)
         const float b2 = fabsf(ap(t + 19, t + 20)), b3 = fabsf(ap(t + 20, t + 21)), b4 = fabsf(ap(t + 21, t + 22));
         mysum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4), a5), b1), b2), b3), b4);
     }
-    sm.pk[t] = mysum;
+    sm.cand[t] = mysum;
     __syncthreads();
     if (t == 0) {
         float mmin = 1000.f; int index = 100;      // sequential first-minimum like the CPU loop
-        for (int i = 0; i < 72; i++) if (sm.pk[i] < mmin) { mmin = sm.pk[i]; index = TU - 36 + i; }
+        for (int i = 0; i < 72; i++) if (sm.cand[i] < mmin) { mmin = sm.cand[i]; index = TU - 36 + i; }
         p.coarse_out[f] = index - TU;
     }
 }

@@ -106,29 +106,49 @@ fic_prep_kernel(const int8_t* __restrict__ soft, int64_t soft_stride, const int3
 }
 
 // MSC collect: copy the sub-channel's slice of each of this frame's 4 CIFs into the de-interleaver ring, residue-major:
-// ring[(stream*slots + slot)][cif mod 20][r][j] = softbit (start_cu*64 + r + 16 j) of that CIF
+// ring[(stream*slots + slot)][cif mod 20][r][j] = softbit (start_cu*64 + r + 16 j) of that CIF.
+// One thread per capacity unit (64 softbits = 4 values of j for each of the 16 residues): four 16-byte loads, a 4x4 byte
+// transpose per word with PRMT, sixteen 4-byte stores that are lane-consecutive in j.
 __global__ void __launch_bounds__(128)
 msc_collect_kernel(MscCollectParams p)
 {
-    extern __shared__ __align__(16) int8_t seg[];
     const int s = blockIdx.x / 4, c = blockIdx.x % 4, t = threadIdx.x;
     if (p.active && !p.active[s]) return;
     const MscSlotState st = p.slots[s * p.n_slots + p.slot];
     if (!st.enabled) return;
-    const int frag = st.frag;
+    const int frag = st.frag, per = frag / 16;
     // CIF c of this frame = symbols 4+18c .. 21+18c -> softbits [(3+18c)*3072, +55296)
-    const int8_t* src = p.soft + (int64_t)s * p.soft_stride + (int64_t)(3 + 18 * c) * 3072 + (int64_t)st.start_cu * 64;
-    for (int i = t; i < frag / 4; i += 128) reinterpret_cast<uint32_t*>(seg)[i] = reinterpret_cast<const uint32_t*>(src)[i];
-    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(p.soft + (int64_t)s * p.soft_stride + (int64_t)(3 + 18 * c) * 3072 + (int64_t)st.start_cu * 64);
     const int slice = (int)((st.cif_count + c) % MSC_RING);
-    int8_t* dst = p.ring + ((int64_t)s * MSC_RING + slice) * p.ring_pitch;
-    const int per = frag / 16;
-    for (int o = t; o < frag; o += 128) { const int r = o / per, j = o % per; dst[o] = seg[r + 16 * j]; }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.ring + ((int64_t)s * MSC_RING + slice) * p.ring_pitch);
+    const int per_w = per / 4;
+    for (int jq = t; jq < per_w; jq += 128) {
+        const uint4 a0 = __ldg(src + 4 * jq), a1 = __ldg(src + 4 * jq + 1), a2 = __ldg(src + 4 * jq + 2), a3 = __ldg(src + 4 * jq + 3);
+        const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w}, w1[4] = {a1.x, a1.y, a1.z, a1.w}, w2[4] = {a2.x, a2.y, a2.z, a2.w}, w3[4] = {a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t t0 = __byte_perm(w0[q], w1[q], 0x5140), t1 = __byte_perm(w2[q], w3[q], 0x5140);
+            const uint32_t t2 = __byte_perm(w0[q], w1[q], 0x7362), t3 = __byte_perm(w2[q], w3[q], 0x7362);
+            dst[(4 * q + 0) * per_w + jq] = __byte_perm(t0, t1, 0x5410);
+            dst[(4 * q + 1) * per_w + jq] = __byte_perm(t0, t1, 0x7632);
+            dst[(4 * q + 2) * per_w + jq] = __byte_perm(t2, t3, 0x5410);
+            dst[(4 * q + 3) * per_w + jq] = __byte_perm(t2, t3, 0x7632);
+        }
+    }
 }
 
-// MSC prep: one CTA per (stream, CIF c).  Gathers the time-de-interleaved fragment into shared memory
-// (out[i] = CIF[n - (16 - map[i & 15])][i], dab-audio.cpp:113-143) and writes the de-punctured symbol row.
+// MSC prep: one CTA per (stream, CIF c).  Copies the 16 residue rows of the time-de-interleaved fragment
+// (out[i] = CIF[n - (16 - map[i & 15])][i], dab-audio.cpp:113-143) from the ring into shared memory, still residue-major
+// (row r at word stride `sw`, odd so that the 16 rows start in different banks), and writes the de-punctured symbol row:
+// softbit i of the fragment sits at (i & 15) * 4 sw + (i >> 4).
 __constant__ int c_deint_delay[16] = {16, 8, 12, 4, 14, 6, 10, 2, 15, 7, 11, 3, 13, 5, 9, 1};   // 16 - map[r]
+__device__ __forceinline__ uint32_t gather_sym4_rm(const int8_t* seg, uint2 m, int sb)
+{
+    const int i0 = (int16_t)(m.x & 0xFFFF), i1 = (int16_t)(m.x >> 16), i2 = (int16_t)(m.y & 0xFFFF), i3 = (int16_t)(m.y >> 16);
+    const uint32_t b0 = i0 >= 0 ? (uint8_t)seg[(i0 & 15) * sb + (i0 >> 4)] : 0u, b1 = i1 >= 0 ? (uint8_t)seg[(i1 & 15) * sb + (i1 >> 4)] : 0u;
+    const uint32_t b2 = i2 >= 0 ? (uint8_t)seg[(i2 & 15) * sb + (i2 >> 4)] : 0u, b3 = i3 >= 0 ? (uint8_t)seg[(i3 & 15) * sb + (i3 >> 4)] : 0u;
+    return sym4(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+}
 __global__ void __launch_bounds__(128)
 msc_prep_kernel(MscPrepParams p)
 {
@@ -139,24 +159,26 @@ msc_prep_kernel(MscPrepParams p)
     if (!st.enabled) return;
     const int64_t n = st.cif_count + c;           // index (since selection) of the CIF being completed
     if (n < 16) return;                           // de-interleaver not yet filled (dab-audio.cpp:146-149)
-    const int frag = st.frag, per = frag / 16;
+    const int frag = st.frag, per_w = frag / 64, sw = per_w | 1;
     const int8_t* ring = p.ring + (int64_t)s * MSC_RING * p.ring_pitch;
-    for (int o = t; o < frag; o += 128) {
-        const int r = o / per, j = o % per;
+    uint32_t* frag_w = reinterpret_cast<uint32_t*>(frag_s);
+#pragma unroll 4
+    for (int r = 0; r < 16; r++) {
         const int slice = (int)((n - c_deint_delay[r]) % MSC_RING);
-        frag_s[r + 16 * j] = ring[(int64_t)slice * p.ring_pitch + o];
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w;
+        for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
     }
     __syncthreads();
     const int cw = s * 4 + c;
     uint32_t* dst = p.rows + (int64_t)cw * p.row_words;
-    const int groups = p.row_words / 8, nsteps = p.nsteps;
+    const int groups = p.row_words / 8, nsteps = p.nsteps, sb = 4 * sw;
     const uint2* map2 = reinterpret_cast<const uint2*>(p.map);
     for (int w = t; w < groups * 8; w += 128) {
         const int g = w >> 3, q = w & 7, stp = 6 * g + q;
         uint32_t v = 0;
         if (q < 6) {
             v = 0x7F7F7F7Fu;
-            if (stp < nsteps) v = gather_sym4(frag_s, map2[stp]);
+            if (stp < nsteps) v = gather_sym4_rm(frag_s, __ldg(map2 + stp), sb);
         }
         dst[w] = v;
     }
@@ -334,8 +356,13 @@ void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_strid
     fic_prep_kernel<<<n_frames * 4, 128, 0, st>>>(soft, soft_stride, active, tb.fic_map, rows, vit_row_words(774));
 }
 
-void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
-void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st) { msc_prep_kernel<<<n_streams * 4, 128, p.ring_pitch, st>>>(p); }
+void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, 0, st>>>(p); }
+void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st)
+{
+    const int smem = p.ring_pitch + 64;      // 16 residue rows, each padded to an odd word count
+    if (smem > 48 * 1024) cudaFuncSetAttribute(msc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    msc_prep_kernel<<<n_streams * 4, 128, smem, st>>>(p);
+}
 
 void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
 {
