@@ -19,8 +19,23 @@ namespace {
 
 struct __align__(16) OfdmSmem {
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
-    float2 tw[TwLayout::TOTAL];      // ~16 KB per-stage twiddles
+    float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
 };
+
+// pass C with both stages' twiddles read through the read-only path (lane-consecutive, L1 resident across CTAs)
+template <bool EXACT, bool INV>
+__device__ __forceinline__ void passC_ldg(float2 v[16], int t, const float2* __restrict__ tw_c5)
+{
+    const float2* tw_c4 = tw_c5 - 384;
+    const float2 w1 = __ldg(tw_c4 + t), w2 = __ldg(tw_c4 + 128 + t), w3 = __ldg(tw_c4 + 256 + t);
+#pragma unroll
+    for (int b = 0; b < 4; b++) bfly4<EXACT, INV>(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3], w1, w2, w3);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int k5 = t + 128 * a;
+        bfly4<EXACT, INV>(v[a], v[a + 4], v[a + 8], v[a + 12], __ldg(tw_c5 + k5), __ldg(tw_c5 + 512 + k5), __ldg(tw_c5 + 1024 + k5));
+    }
+}
 
 // ---- NCO (ofdm-processor.cpp:211-214): sample idx of the frame is multiplied by osc[(lp0 - idx*ph) mod 2 048 000].
 // Per symbol one 64-bit modulo gives the phase of the thread's first sample; the other samples follow by modular
@@ -76,7 +91,7 @@ __device__ __forceinline__ constexpr int xc_of(int c) { return ((c & 1) << 3) | 
 // FFT of the 2048 samples at src[w0 .. w0+2048) -> v[a+4b] = X[t + 128a + 512b].  Contains two __syncthreads.
 template <bool EXACT, bool INV>
 __device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ src, int64_t w0, float2 v[16], OfdmSmem& sm, int t, const XIdx& xi,
-                                                    const float2* __restrict__ osc, const Nco& nco)
+                                                    const float2* __restrict__ osc, const Nco& nco, const float2* __restrict__ tw_c5)
 {
     // pass A: two blocks n0 = t, t+128; loads are lane-consecutive for each c
     float2 x[16];
@@ -118,7 +133,7 @@ __device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ s
     // pass C
 #pragma unroll
     for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
-    passC<EXACT, INV>(v, t, sm.tw);
+    passC_ldg<EXACT, INV>(v, t, tw_c5);
 }
 
 // ---- TMA / mbarrier helpers (SASS: UBLKCP, SYNCS) ----
@@ -194,18 +209,7 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
-    // pass C with the m=512 twiddles read through the read-only path (12 KB, L1 resident, lane-consecutive)
-    {
-        const float2* tw_c4 = tw_c5 - 384;
-        const float2 w1 = __ldg(tw_c4 + t), w2 = __ldg(tw_c4 + 128 + t), w3 = __ldg(tw_c4 + 256 + t);
-#pragma unroll
-        for (int b = 0; b < 4; b++) bfly4<EXACT, false>(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3], w1, w2, w3);
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int k5 = t + 128 * a;
-            bfly4<EXACT, false>(v[a], v[a + 4], v[a + 8], v[a + 12], __ldg(tw_c5 + k5), __ldg(tw_c5 + 512 + k5), __ldg(tw_c5 + 1024 + k5));
-        }
-    }
+    passC_ldg<EXACT, false>(v, t, tw_c5);
 }
 
 template <bool EXACT, bool TAP, bool DIRECT>
@@ -357,20 +361,20 @@ struct __align__(16) SyncSmem {
 };
 
 template <bool EXACT, bool NCO>
-__global__ void __launch_bounds__(OFDM_THREADS, 4)
+__global__ void __launch_bounds__(OFDM_THREADS, 5)
 find_index_kernel(DevTables tb, SyncParams p)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     SyncSmem& sm = *reinterpret_cast<SyncSmem*>(smraw);
     const int t = threadIdx.x, f = blockIdx.x;
     if (p.active && !p.active[f]) return;
-    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_fwd[i];
+    if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_fwd[t];
     __syncthreads();
     const float2* src = p.iq + (int64_t)f * p.stride + p.win_start[f];
     const Nco nco = make_nco((NCO && p.nco) ? p.nco[2 * f] : 0, (NCO && p.nco) ? p.nco[2 * f + 1] : 0);
     const XIdx xi = make_xidx(t);
     float2 v[16];
-    fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb.osc, nco);
+    fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb.osc, nco, tb.tw_fwd + TwLayout::C5);
     // res = X * conj(ref), written in natural order into the exchange buffer (free between the two transforms)
     float2* scratch = sm.o.xbuf;
     __syncthreads();             // pass C of the forward transform has read xbuf
@@ -383,7 +387,7 @@ find_index_kernel(DevTables tb, SyncParams p)
                                    fadd_<EXACT>(fmul_<EXACT>(v[c].x, d), fmul_<EXACT>(v[c].y, cc)));
     }
     __syncthreads();
-    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_inv[i];
+    if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_inv[t];
     // inverse FFT reading its input from shared memory: same pass structure (load pattern n0 + 256 c)
     {
         float2 x[16];
@@ -412,7 +416,7 @@ find_index_kernel(DevTables tb, SyncParams p)
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 16; c++) v[c] = sm.o.xbuf[(t ^ xc_of(c)) + 128 * c];
-        passC<EXACT, true>(v, t, sm.o.tw);
+        passC_ldg<EXACT, true>(v, t, tb.tw_inv + TwLayout::C5);
     }
     // scale by 1/2048 (fft.cpp:146-158) and take the magnitude the way glibc's hypotf does (double sqrt, narrowed)
     const float factor = 1.0f / 2048.0f;
@@ -478,12 +482,12 @@ find_index_kernel(DevTables tb, SyncParams p)
     // ---- coarse AFC: FFT of the aligned PRS (window start + index), then the "pattern of zeros" search over +-36 carriers
     // (ofdm-processor.cpp:537-545,582-613).  Needs bins 2012..2047 and 0..58 in natural order: staged in sm.cir (as float2).
     __syncthreads();
-    for (int i = t; i < TwLayout::TOTAL; i += OFDM_THREADS) sm.o.tw[i] = tb.tw_fwd[i];
+    if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_fwd[t];
     __syncthreads();
     // the PRS useful part starts `best` samples into the window; its samples continue the NCO phase sequence
     Nco nco2 = nco;
     if (nco.mix) nco2.lp0 = nco.lp0;       // fetch indices are relative to the window start, so the same lp0/ph apply with w0 = best
-    fft2048_from_global<EXACT, false>(src, best, v, sm.o, t, xi, tb.osc, nco2);
+    fft2048_from_global<EXACT, false>(src, best, v, sm.o, t, xi, tb.osc, nco2, tb.tw_fwd + TwLayout::C5);
     float2* spec = sm.spec;     // [0..35] = bins 2012..2047, [36..94] = bins 0..58
     if (t < 59) spec[36 + t] = v[0];
     if (t >= 92) spec[t - 92] = v[15];

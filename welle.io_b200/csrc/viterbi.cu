@@ -162,9 +162,11 @@ msc_prep_kernel(MscPrepParams p)
     const int frag = st.frag, per_w = frag / 64, sw = per_w | 1;
     const int8_t* ring = p.ring + (int64_t)s * MSC_RING * p.ring_pitch;
     uint32_t* frag_w = reinterpret_cast<uint32_t*>(frag_s);
+    const int nm = (int)(n % MSC_RING);           // one 64-bit modulo; the 16 slices follow with 32-bit arithmetic
 #pragma unroll 4
     for (int r = 0; r < 16; r++) {
-        const int slice = (int)((n - c_deint_delay[r]) % MSC_RING);
+        int slice = nm - c_deint_delay[r];        // delay <= 16 < MSC_RING
+        if (slice < 0) slice += MSC_RING;
         const uint32_t* srow = reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w;
         for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
     }
@@ -173,20 +175,25 @@ msc_prep_kernel(MscPrepParams p)
     uint32_t* dst = p.rows + (int64_t)cw * p.row_words;
     const int groups = p.row_words / 8, nsteps = p.nsteps, sb = 4 * sw;
     const uint2* map2 = reinterpret_cast<const uint2*>(p.map);
+    // thread t always handles word q = t & 7 of a group (128 is a multiple of 8): lanes with q >= 6 only write the padding
+    const int q = t & 7;
+    const uint32_t fill = q < 6 ? 0x7F7F7F7Fu : 0u;
+#pragma unroll 4
     for (int w = t; w < groups * 8; w += 128) {
-        const int g = w >> 3, q = w & 7, stp = 6 * g + q;
-        uint32_t v = 0;
-        if (q < 6) {
-            v = 0x7F7F7F7Fu;
-            if (stp < nsteps) v = gather_sym4_rm(frag_s, __ldg(map2 + stp), sb);
-        }
+        const int stp = 6 * (w >> 3) + q;
+        uint32_t v = fill;
+        if (q < 6 && stp < nsteps) v = gather_sym4_rm(frag_s, __ldg(map2 + stp), sb);
         dst[w] = v;
     }
     if (t == 0 && p.valid) p.valid[cw] = 1;
 }
 
 // ------------------------------------------------------------------------------------------------ the decoder
-constexpr int VIT_THREADS = 128;
+#ifndef VIT_THREADS_N
+#define VIT_THREADS_N 128
+#endif
+constexpr int VIT_THREADS = VIT_THREADS_N;     // codewords per CTA
+constexpr int VIT_MIN_CTAS = 512 / VIT_THREADS;   // 512 threads of 128 registers per SM
 constexpr int VIT_STAGES_MAX = 3;
 constexpr int VIT_ROW_PITCH = 144;      // 128 B of symbols + 16 B pad: 16-byte reads of 8 consecutive rows hit 32 distinct banks
 constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
@@ -272,12 +279,12 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
 }
 
 template <int VIT_STAGES>
-__global__ void __launch_bounds__(VIT_THREADS, 4)
+__global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
 viterbi_kernel(ViterbiParams p) { viterbi_cta<VIT_STAGES>(p, blockIdx.x); }
 
 // several independent codeword sets (FIC + one per selected sub-channel slot) in one launch, so that their CTAs share the SMs
 template <int VIT_STAGES>
-__global__ void __launch_bounds__(VIT_THREADS, 4)
+__global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
 viterbi_batch_kernel(ViterbiBatch b)
 {
     int k = 0;

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdab_b200.so")
+LIB_PATH = os.environ.get("DABB_LIB") or os.path.join(HERE, "libdab_b200.so")   # DABB_LIB: build-variant experiments only
 
 L, K, TU, TS, TG, TNULL, TF = 76, 1536, 2048, 2552, 504, 2656, 196608
 SOFT_PER_FRAME = 75 * 3072
