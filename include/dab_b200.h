@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DABB_ABI_VERSION 1
+#define DABB_ABI_VERSION 2
 
 enum {
     DABB_OK = 0,
@@ -47,6 +47,11 @@ typedef struct dabb_ctx dabb_ctx;
  * (<= 1e-6 relative difference, faster). */
 enum { DABB_FFT_EXACT = 0, DABB_FFT_FMA = 1 };
 
+/* RadioReceiverOptions::fftPlacementMethod / freqsyncMethod (backend/radio-receiver-options.h:35-64).  0 is the reference's
+ * default in both enums (the reference's own enumerator values differ: see INTEGRATION.md for the mapping). */
+enum { DABB_PLACEMENT_THRESHOLD_BEFORE_PEAK = 0, DABB_PLACEMENT_STRONGEST_PEAK = 1, DABB_PLACEMENT_EARLIEST_PEAK_WITH_BINNING = 2 };
+enum { DABB_FREQSYNC_PATTERN_OF_ZEROS = 0, DABB_FREQSYNC_GET_MIDDLE = 1, DABB_FREQSYNC_CORRELATE_PRS = 2 };
+
 typedef struct {
     int32_t abi_version;        /* DABB_ABI_VERSION */
     int32_t device;             /* CUDA device ordinal */
@@ -54,12 +59,22 @@ typedef struct {
     int32_t transmission_mode;  /* only 1 (RadioReceiver ctor arg, backend/radio-receiver.cpp:66-80) */
     int32_t fft_mode;           /* DABB_FFT_* */
     int32_t disable_coarse;     /* RadioReceiverOptions::disableCoarseCorrector (radio-receiver-options.h:66-85) */
-    int32_t keep_taps;          /* 1: keep CIR / softbits of the last frame readable via dabb_read_tap */
+    int32_t keep_taps;          /* 1: keep CIR / softbits / constellation / null symbol of the last frame readable via dabb_read_tap */
     int32_t n_subch_slots;      /* sub-channels decodable per stream at once (1..DABB_MAX_SUBCH), 0 -> 1 */
     int32_t max_subch_cu;       /* largest selectable sub-channel in capacity units, 0 -> 144 */
     int32_t ofdm_groups;        /* CTAs per frame in the OFDM kernel (divisor of 75), 0 -> chosen from n_streams */
-    int32_t reserved[6];
+    int32_t fft_placement;      /* DABB_PLACEMENT_* (PhaseReference::findIndex variant) */
+    int32_t freqsync_method;    /* DABB_FREQSYNC_* (OFDMProcessor::processPRS variant) */
+    int32_t reserved[4];
 } dabb_config;
+
+/* replaces: RadioReceiver::setReceiverOptions (backend/radio-receiver.cpp:119-124): takes effect from the next frame */
+typedef struct {
+    int32_t disable_coarse;
+    int32_t fft_placement;      /* DABB_PLACEMENT_* */
+    int32_t freqsync_method;    /* DABB_FREQSYNC_* */
+    int32_t reserved[5];
+} dabb_options;
 
 /* replaces: RadioReceiver::RadioReceiver / ~RadioReceiver (backend/radio-receiver.h:52-116) */
 int dabb_create(const dabb_config* cfg, dabb_ctx** out);
@@ -70,6 +85,7 @@ int dabb_abi_version(void);
 /* replaces: OFDMProcessor::restart (backend/ofdm-processor.cpp:115-132): stream goes back to acquisition at
  * logical sample position `pos` with zeroed correctors, cleared FIC counter, de-interleaver and superframe window */
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first_stream, int32_t count, int64_t pos);
+int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt);
 
 /* replaces: MscHandler::addSubchannel / removeSubchannel (backend/msc-handler.cpp:61-127) + DabAudio ctor
  * (backend/dab-audio.cpp:46-85).  slot in [0, DABB_MAX_SUBCH).  Protection exactly as ProtectionSettings
@@ -148,8 +164,11 @@ int64_t dabb_kernel_launches(const dabb_ctx* ctx);  /* number of CUDA kernels th
 int dabb_profile(dabb_ctx* ctx, int32_t enable);
 int dabb_profile_read(dabb_ctx* ctx, char* json_out, size_t cap);
 
-/* taps (valid after a dabb_process when keep_taps=1): 0 = softbits int8 [n_streams][75*3072],
- * 1 = CIR float [n_streams][2048] (RadioControllerInterface::onNewImpulseResponse) */
+/* taps (valid after a dabb_process when keep_taps=1):
+ *   0 = softbits int8 [n_streams][75*3072]
+ *   1 = CIR float [n_streams][2048]                     RadioControllerInterface::onNewImpulseResponse (phasereference.cpp:93)
+ *   2 = constellation cf32 [n_streams][75][16]          onConstellationPoints: r1 of every 96th carrier (ofdm-decoder.cpp:216-218)
+ *   3 = null symbol cf32 [n_streams][2656], NCO applied  onNewNullSymbol (ofdm-processor.cpp:462-469) */
 int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -168,6 +187,14 @@ int dabb_ofdm_demod(dabb_ctx* ctx, const float* iq, int64_t stride_samples, cons
  * at iq + f*stride + win_start[f]; index_out int32[n]; cir_out (may be NULL) float [n][2048] */
 int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride_samples, const int64_t* win_start, int32_t n,
                     int32_t* index_out, float* cir_out);
+/* the same with any of the three placements (phasereference.cpp:93-256); negative index_out = no synchronisation, with the
+ * reference's own negative value for StrongestPeak */
+int dabb_find_index_ex(dabb_ctx* ctx, const float* iq, int64_t stride_samples, const int64_t* win_start, int32_t n,
+                       int32_t placement, int32_t* index_out, float* cir_out);
+/* OFDMProcessor::processPRS (ofdm-processor.cpp:537-644): coarse frequency estimate, in carriers, of n aligned phase reference
+ * symbols (2048 samples at iq + f*stride + prs_start[f]); offset_out int32[n]; 100 = no estimate */
+int dabb_coarse_estimate(dabb_ctx* ctx, const float* iq, int64_t stride_samples, const int64_t* prs_start, int32_t n,
+                         int32_t freqsync_method, int32_t* offset_out);
 
 /* Viterbi::deconvolve (viterbi.cpp:227-245) for n codewords: soft int8 [n][(nbits+6)*4] (already de-punctured,
  * 0 = punctured), bits_out uint8 [n][nbits] (one bit per byte) */

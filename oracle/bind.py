@@ -36,7 +36,7 @@ class ProtT(C.Structure):
 
 
 class RxCfg(C.Structure):
-    _fields_ = [("disable_coarse", C.c_int), ("subch_start_cu", C.c_int), ("subch_len_cu", C.c_int),
+    _fields_ = [("disable_coarse", C.c_int), ("fft_placement", C.c_int), ("freqsync_method", C.c_int), ("subch_start_cu", C.c_int), ("subch_len_cu", C.c_int),
                 ("prot", ProtT), ("dabplus", C.c_int), ("select_after_frames", C.c_int), ("select_after_symbol", C.c_int)]
 
 
@@ -87,13 +87,15 @@ class Oracle:
         x = np.ascontiguousarray(x, np.complex64); o = np.empty_like(x)
         self.lib.orc_ifft_scaled(len(x), _p(x), _p(o)); return o
 
-    def find_index(self, v):
+    def find_index(self, v, placement=0):
+        """placement: 0 ThresholdBeforePeak, 1 StrongestPeak, 2 EarliestPeakWithBinning"""
         v = np.ascontiguousarray(v, np.complex64); cir = np.zeros(TU, np.float32)
-        return self.lib.orc_find_index(_p(v), _p(cir)), cir
+        return self.lib.orc_find_index_m(_p(v), _p(cir), int(placement)), cir
 
-    def coarse(self, prs):
+    def coarse(self, prs, method=0):
+        """method: 0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS"""
         prs = np.ascontiguousarray(prs, np.complex64)
-        return self.lib.orc_coarse_pattern_of_zeros(_p(prs))
+        return self.lib.orc_coarse(_p(prs), int(method))
 
     def demod_frame(self, prs, syms, want_r1=False):
         prs = np.ascontiguousarray(prs, np.complex64); syms = np.ascontiguousarray(syms, np.complex64)
@@ -182,9 +184,10 @@ class Oracle:
 
     # ---- closed-loop receiver
     def rx_run(self, iq, prot=None, start_cu=0, len_cu=0, dabplus=True, select_after_frames=1, disable_coarse=True,
-               want_soft=0):
+               want_soft=0, fft_placement=0, freqsync_method=0):
         iq = np.ascontiguousarray(iq, np.complex64)
         cfg = RxCfg(); cfg.disable_coarse = int(disable_coarse); cfg.subch_start_cu = start_cu; cfg.subch_len_cu = len_cu
+        cfg.fft_placement = int(fft_placement); cfg.freqsync_method = int(freqsync_method)
         if prot is not None:
             cfg.prot = prot
         cfg.dabplus = int(dabplus); cfg.select_after_frames = select_after_frames
@@ -238,7 +241,13 @@ class Ref:
         b = np.array(x, np.complex64).copy()
         (self.lib.ref_fft_backward if inverse else self.lib.ref_fft_forward)(len(b), _p(b)); return b
 
+    def process_prs(self, prs, method=0):
+        """OFDMProcessor::processPRS; method in this repository's numbering (0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS)"""
+        prs = np.ascontiguousarray(prs, np.complex64)
+        return self.lib.ref_process_prs(_p(prs), {0: 2, 1: 0, 2: 1}[int(method)])
+
     def find_index(self, v, method=2):
+        # method in the reference's enum order: 0 StrongestPeak, 1 EarliestPeakWithBinning, 2 ThresholdBeforePeak
         v = np.ascontiguousarray(v, np.complex64); cir = np.zeros(TU, np.float32)
         return self.lib.ref_find_index(1, method, _p(v), _p(cir)), cir
 
@@ -299,11 +308,13 @@ class Ref:
         k = self.lib.ref_superframe_filter(_p(frames), n, flen, _p(fec), n + 1, C.byref(au_err), C.byref(good))
         return fec[:2 * k].reshape(-1, 2), au_err.value, good.value
 
-    def e2e(self, iq, disable_coarse=True, select_at_fib=24, dump_path="/tmp/ref_e2e.msc", keep_cir=False):
+    def e2e(self, iq, disable_coarse=True, select_at_fib=24, dump_path="/tmp/ref_e2e.msc", keep_cir=False, fft_placement=0, freqsync_method=0):
+        """fft_placement / freqsync_method use this repository's numbering (0 = the reference's defaults), see Oracle.find_index / coarse"""
         iq = np.ascontiguousarray(iq, np.complex64)
         if os.path.exists(dump_path):
             os.remove(dump_path)
-        n = self.lib.ref_e2e_run(_p(iq), C.c_long(len(iq)), int(disable_coarse), select_at_fib, dump_path.encode(), int(keep_cir))
+        n = self.lib.ref_e2e_run2(_p(iq), C.c_long(len(iq)), int(disable_coarse), select_at_fib, dump_path.encode(), int(keep_cir),
+                                  {0: 2, 1: 0, 2: 1}[int(fft_placement)], {0: 2, 1: 0, 2: 1}[int(freqsync_method)])
 
         def get(what, dt):
             sz = self.lib.ref_e2e_get(what, None, C.c_long(0))

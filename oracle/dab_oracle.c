@@ -241,8 +241,82 @@ int orc_find_index(const float* v, float* cir_out)
     return ret;
 }
 
+/* The two non-default FFT placements of PhaseReference::findIndex (phasereference.cpp:93-211) */
+int orc_find_index_m(const float* v, float* cir_out, int placement)
+{
+    if (placement == 0) return orc_find_index(v, cir_out);
+    ensure_tables();
+    const int Tu = ORC_TU;
+    cf* spec = (cf*)malloc(sizeof(cf) * Tu);
+    cf* res = (cf*)malloc(sizeof(cf) * Tu);
+    float* cir = (float*)calloc(Tu, sizeof(float));
+    orc_fft(Tu, v, (float*)spec, 0);
+    for (int i = 0; i < Tu; i++) {
+        float a = spec[i].r, b = spec[i].i, c = g_prs[2 * i], d = -g_prs[2 * i + 1];
+        res[i].r = a * c - b * d;
+        res[i].i = a * d + b * c;
+    }
+    orc_ifft_scaled(Tu, (const float*)res, (float*)res);
+    int ret = -1;
+    if (placement == 1) {
+        /* StrongestPeak (:93-123): running sum and first maximum in one pass */
+        float sum = 0, max = -10000; int maxIndex = -1;
+        for (int i = 0; i < Tu; i++) {
+            const float value = hypotf(res[i].r, res[i].i);
+            sum += value; cir[i] = value;
+            if (value > max) { maxIndex = i; max = value; }
+        }
+        if (sum == 0) ret = -1;
+        else if (max < 3.0f * sum / (float)Tu) ret = (int)(-fabsf(max * (float)Tu / sum) - 1);
+        else ret = maxIndex;
+    } else {
+        /* EarliestPeakWithBinning (:124-211): peaks of 20-sample bins (the last 8 samples are never looked at), the four
+         * strongest bins within 500 samples of the strongest, those above 3 x mean, the earliest of them.
+         * std::sort is not stable: bins of exactly equal value may come out in another order than here (ties broken
+         * towards the earlier bin). */
+        enum { BIN = 20, KEEP = 4, MAXB = 128 };
+        int idx[MAXB]; float val[MAXB]; int nb = 0;
+        float mean = 0;
+        for (int i = 0; i + BIN < Tu; i += BIN) {
+            int pi = -1; float pv = 0;
+            for (int j = 0; j < BIN; j++) {
+                const float value = hypotf(res[i + j].r, res[i + j].i);
+                mean += value; cir[i + j] = value;
+                if (value > pv) { pv = value; pi = i + j; }
+            }
+            idx[nb] = pi; val[nb] = pv; nb++;
+        }
+        mean /= (float)Tu;
+        /* descending selection, stable */
+        int order[MAXB]; char used[MAXB]; memset(used, 0, sizeof used);
+        for (int k = 0; k < nb; k++) {
+            int best = -1;
+            for (int b = 0; b < nb; b++) if (!used[b] && (best < 0 || val[b] > val[best])) best = b;
+            used[best] = 1; order[k] = best;
+        }
+        const int peak_index = idx[order[0]];
+        int kept[KEEP], nk = 0;
+        for (int k = 0; k < nb && nk < KEEP; k++) if (abs(idx[order[k]] - peak_index) <= 500) kept[nk++] = order[k];
+        const float thresh = 3 * mean;
+        int earliest = -1, have = 0;
+        for (int k = 0; k < nk; k++) {
+            if (val[kept[k]] < thresh) continue;
+            if (!have || idx[kept[k]] < earliest) { earliest = idx[kept[k]]; have = 1; }
+        }
+        ret = have ? earliest : -1;
+    }
+    if (cir_out) memcpy(cir_out, cir, sizeof(float) * Tu);
+    free(spec); free(res); free(cir);
+    return ret;
+}
+
 /* OFDMProcessor::processPRS, FreqsyncMethod::PatternOfZeros, ofdm-processor.cpp:582-613.
- * std::arg -> atan2f; divisions by M_PI are double. Returns carrier offset, 100 = "no estimate". */
+ * std::arg -> atan2f.  IMPORTANT: in that translation unit the unqualified `abs` applied to a float or a double resolves
+ * to the C library's `int abs(int)` (libstdc++'s <cmath> only declares the floating overloads inside namespace std, and
+ * nothing there says `using namespace std`), so every `abs(arg(..))` TRUNCATES its argument to int first — verified with the
+ * reference's own headers (typeid(abs(0.7f)) is int) and pinned against the compiled reference (ref_process_prs).
+ * The metric is therefore a small integer: a1, a2, b1 are 1 unless the argument is exactly +-(float)pi, the other six terms
+ * are trunc|arg| in 0..3.  Returns carrier offset, 100 = "no estimate". */
 static float argprod(const cf* s, int i, int j)
 {
     const int Tu = ORC_TU;
@@ -251,6 +325,8 @@ static float argprod(const cf* s, int i, int j)
     float re = a.r * c - a.i * d, im = a.r * d + a.i * c;
     return atan2f(im, re);
 }
+static int iabs_f(float x) { int v = (int)x; return v < 0 ? -v : v; }           /* abs(float)  -> int abs(int) */
+static int iabs_pi(float x) { int v = (int)((double)x / M_PI); v = v < 0 ? -v : v; v -= 1; return v < 0 ? -v : v; }   /* abs(abs(x / M_PI) - 1) */
 int orc_coarse_pattern_of_zeros(const float* prs)
 {
     const int Tu = ORC_TU, RANGE2 = 72;
@@ -259,20 +335,64 @@ int orc_coarse_pattern_of_zeros(const float* prs)
     int index = 100;
     float Mmin = 1000;
     for (int i = Tu - RANGE2 / 2; i < Tu + RANGE2 / 2; i++) {
-        float a1 = (float)fabs(fabs(argprod(s, i + 1, i + 2) / M_PI) - 1);
-        float a2 = (float)fabs(fabs(argprod(s, i + 2, i + 3) / M_PI) - 1);
-        float a3 = fabsf(argprod(s, i + 3, i + 4));
-        float a4 = fabsf(argprod(s, i + 4, i + 5));
-        float a5 = fabsf(argprod(s, i + 5, i + 6));
-        float b1 = (float)fabs(fabs(argprod(s, i + 16 + 1, i + 16 + 3) / M_PI) - 1);
-        float b2 = fabsf(argprod(s, i + 16 + 3, i + 16 + 4));
-        float b3 = fabsf(argprod(s, i + 16 + 4, i + 16 + 5));
-        float b4 = fabsf(argprod(s, i + 16 + 5, i + 16 + 6));
+        float a1 = (float)iabs_pi(argprod(s, i + 1, i + 2));
+        float a2 = (float)iabs_pi(argprod(s, i + 2, i + 3));
+        float a3 = (float)iabs_f(argprod(s, i + 3, i + 4));
+        float a4 = (float)iabs_f(argprod(s, i + 4, i + 5));
+        float a5 = (float)iabs_f(argprod(s, i + 5, i + 6));
+        float b1 = (float)iabs_pi(argprod(s, i + 16 + 1, i + 16 + 3));
+        float b2 = (float)iabs_f(argprod(s, i + 16 + 3, i + 16 + 4));
+        float b3 = (float)iabs_f(argprod(s, i + 16 + 4, i + 16 + 5));
+        float b4 = (float)iabs_f(argprod(s, i + 16 + 5, i + 16 + 6));
         float sum = a1 + a2 + a3 + a4 + a5 + b1 + b2 + b3 + b4;
         if (sum < Mmin) { Mmin = sum; index = i; }
     }
     free(s);
     return index - Tu;   /* :612 returns index - T_u unconditionally */
+}
+
+/* FreqsyncMethod::GetMiddle (ofdm-processor.cpp:617-644, including its `sum = oldMax` assignment) and
+ * FreqsyncMethod::CorrelatePRS (:546-581; refArg from the ctor :96-101) */
+int orc_coarse(const float* prs, int method)
+{
+    if (method == 0) return orc_coarse_pattern_of_zeros(prs);
+    ensure_tables();
+    const int Tu = ORC_TU, K = ORC_K;
+    cf* s = (cf*)malloc(sizeof(cf) * Tu);
+    orc_fft(Tu, prs, (float*)s, 0);
+    int ret;
+    if (method == 1) {
+        float sum = 0, oldMax = 0; int maxIndex = 0;
+        for (int i = 40; i < K + 40; i++) { const cf z = s[(Tu / 2 + i) % Tu]; sum += hypotf(z.r, z.i); }
+        for (int i = 40; i < Tu - (K - 40); i++) {
+            const cf a = s[(Tu / 2 + i) % Tu], b = s[(Tu / 2 + i + K) % Tu];
+            sum -= hypotf(a.r, a.i);
+            sum += hypotf(b.r, b.i);
+            if (sum > oldMax) { sum = oldMax; maxIndex = i; }
+        }
+        ret = (int16_t)(maxIndex - (Tu - K) / 2);
+    } else {
+        enum { SEARCH = 72, CORR = 24 };
+        float refArg[CORR], cv[SEARCH + CORR];
+        const cf* ref = (const cf*)g_prs;
+        for (int i = 0; i < CORR; i++) {
+            const cf a = ref[(Tu + i) % Tu], b = ref[(Tu + i + 1) % Tu];
+            const float c = b.r, d = -b.i;
+            refArg[i] = atan2f(a.r * d + a.i * c, a.r * c - a.i * d);
+        }
+        for (int i = 0; i < SEARCH + CORR; i++) cv[i] = argprod(s, Tu - SEARCH / 2 + i, Tu - SEARCH / 2 + i + 1);
+        float MMax = 0; int index = 100;
+        for (int i = 0; i < SEARCH; i++) {
+            float sum = 0;
+            for (int j = 0; j < CORR; j++) {
+                sum += (float)iabs_f(refArg[j] * cv[i + j]);       /* `abs` is int abs(int) here too, see above */
+                if (sum > MMax) { MMax = sum; index = i; }
+            }
+        }
+        ret = (int16_t)(Tu - SEARCH / 2 + index - Tu);
+    }
+    free(s);
+    return ret;
 }
 
 /* ============================================================================================
@@ -858,12 +978,12 @@ long orc_rx_run(orc_rx_t* r, const float* iq, long nsamples,
         /* SyncOnPhase */
         long fpos = src.pos;
         if (!rx_get(r, &src, prsbuf, ORC_TU, r->coarse + r->fine)) goto done;
-        int start = orc_find_index((const float*)prsbuf, NULL);
+        int start = orc_find_index_m((const float*)prsbuf, NULL, r->cfg.fft_placement);
         if (start < 0) { r->acquired = 0; continue; }
         memmove(prsbuf, prsbuf + start, sizeof(cf) * (ORC_TU - start));
         if (!rx_get(r, &src, prsbuf + (ORC_TU - start), start, r->coarse + r->fine)) goto done;
         if (!r->cfg.disable_coarse && r->fic_ratio * 10 < 50) {
-            int corr = orc_coarse_pattern_of_zeros((const float*)prsbuf);
+            int corr = orc_coarse((const float*)prsbuf, r->cfg.freqsync_method);
             if (corr != 100) {
                 r->coarse += corr * ORC_CARRIER_DIFF;
                 if (abs(r->coarse) > 35000) r->coarse = 0;

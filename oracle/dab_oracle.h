@@ -38,8 +38,12 @@ void orc_ifft_scaled(int n, const float* in, float* out);            /* various/
 
 /* ---- time sync: PhaseReference::findIndex, ThresholdBeforePeak, phasereference.cpp:73-97,212-253 ---- */
 int orc_find_index(const float* v /* T_u complex */, float* cir /* T_u, may be NULL */);
+/* placement: 0 ThresholdBeforePeak (default), 1 StrongestPeak, 2 EarliestPeakWithBinning (phasereference.cpp:93-256) */
+int orc_find_index_m(const float* v, float* cir, int placement);
 /* coarse AFC: OFDMProcessor::processPRS, PatternOfZeros, ofdm-processor.cpp:537-616 */
 int orc_coarse_pattern_of_zeros(const float* prs /* T_u complex */);
+/* method: 0 PatternOfZeros (default), 1 GetMiddle, 2 CorrelatePRS (ofdm-processor.cpp:537-644) */
+int orc_coarse(const float* prs, int method);
 
 /* ---- OFDM demod of one aligned frame: ofdm-decoder.cpp:144-230 ---- */
 void orc_ofdm_demod_frame(const float* prs /* T_u cpx */, const float* syms /* 75*T_s cpx */,
@@ -111,6 +115,8 @@ void orc_sff_feed(orc_sff_t*, const uint8_t* frame, int len, orc_sff_result_t* r
 typedef struct orc_rx orc_rx_t;
 typedef struct {
     int disable_coarse;
+    int fft_placement;        /* see orc_find_index_m */
+    int freqsync_method;      /* see orc_coarse */
     /* one selected sub-channel (optional: set subch_len_cu = 0 for FIC only) */
     int subch_start_cu, subch_len_cu;
     orc_prot_t prot;

@@ -20,8 +20,26 @@
 #include <thread>
 #include <vector>
 #include <sys/stat.h>
+#include <algorithm>
+#include <complex>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
 
+/* SURVEY 8c option (iii): OFDMProcessor::processPRS (the coarse frequency estimators) is a private member; this
+ * harness translation unit alone sees the reference's classes with private members accessible.  The reference objects
+ * themselves are compiled unmodified. */
+#define private public
 #include "radio-receiver.h"
+#undef private
 #include "virtual_input.h"
 #include "freq-interleaver.h"
 #include "phasereference.h"
@@ -36,6 +54,11 @@
 #include "fft.h"
 #include "MathHelper.h"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void segv_bt(int sig) { void* a[64]; int n = backtrace(a, 64); backtrace_symbols_fd(a, n, 2); _exit(139); }
+extern "C" void ref_debug_segv(void) { signal(SIGSEGV, segv_bt); signal(SIGABRT, segv_bt); }
 extern "C" {
 #include "fec.h"
 }
@@ -340,6 +363,11 @@ int ref_superframe_filter(const uint8_t* frames, int nframes, int frame_len, int
     return n;
 }
 
+/* ---------------- OFDMProcessor::processPRS (coarse frequency estimate) on one aligned PRS ----------------
+ * freqsync in the reference's enum order: 0 GetMiddle, 1 CorrelatePRS, 2 PatternOfZeros */
+namespace { struct NullInput; }
+extern "C" int ref_process_prs(const float* prs, int freqsync);
+
 /* ---------------- end-to-end: RadioReceiver on an in-memory stream ---------------- */
 namespace {
 
@@ -419,7 +447,13 @@ E2EResult g_last;
 } // namespace
 
 /* Runs the reference receiver over iq[0..nsamples). Returns number of FIB callbacks. */
+int ref_e2e_run2(const float* iq, long nsamples, int disable_coarse, int select_at_fib, const char* msc_dump_path, int keep_cir, int fft_placement, int freqsync);
 int ref_e2e_run(const float* iq, long nsamples, int disable_coarse, int select_at_fib, const char* msc_dump_path, int keep_cir)
+{
+    return ref_e2e_run2(iq, nsamples, disable_coarse, select_at_fib, msc_dump_path, keep_cir, 2, 2);
+}
+/* fft_placement / freqsync in the reference's enum order (radio-receiver-options.h:35-64) */
+int ref_e2e_run2(const float* iq, long nsamples, int disable_coarse, int select_at_fib, const char* msc_dump_path, int keep_cir, int fft_placement, int freqsync)
 {
     g_last = E2EResult();
     DABParams p(1);
@@ -432,6 +466,8 @@ int ref_e2e_run(const float* iq, long nsamples, int disable_coarse, int select_a
         Session(const float* iq, long n, long tf, RadioReceiverOptions rro) : in(iq, (size_t)n, tf), rx(ri, in, rro) {}
     };
     RadioReceiverOptions rro; rro.disableCoarseCorrector = disable_coarse != 0; rro.decodeTII = false;
+    rro.fftPlacementMethod = fft_placement == 0 ? FFTPlacementMethod::StrongestPeak : fft_placement == 1 ? FFTPlacementMethod::EarliestPeakWithBinning : FFTPlacementMethod::ThresholdBeforePeak;
+    rro.freqsyncMethod = freqsync == 0 ? FreqsyncMethod::GetMiddle : freqsync == 1 ? FreqsyncMethod::CorrelatePRS : FreqsyncMethod::PatternOfZeros;
     auto t0 = std::chrono::steady_clock::now();
     Session* S = new Session(iq, nsamples, p.T_F, rro);
     GatedMemInput& in = S->in; E2EController& ri = S->ri; NullProgramme& ph = S->ph; RadioReceiver& rx = S->rx;
@@ -480,3 +516,17 @@ void ref_e2e_stats(double* out /* sync_true, sync_false, select_ok, frames_done,
 }
 
 } // extern "C"
+
+extern "C" int ref_process_prs(const float* prs, int freqsync)
+{
+    static const float dummy[16] = {0};
+    DABParams p(1);
+    GatedMemInput in(dummy, 0, p.T_F);
+    E2EController ri;
+    RadioReceiverOptions rro;
+    RadioReceiver rx(ri, in, rro);          /* never started: only the OFDMProcessor member's tables are used */
+    std::vector<DSPCOMPLEX> v(p.T_u);
+    memcpy(v.data(), prs, sizeof(DSPCOMPLEX) * p.T_u);
+    const FreqsyncMethod m = freqsync == 0 ? FreqsyncMethod::GetMiddle : freqsync == 1 ? FreqsyncMethod::CorrelatePRS : FreqsyncMethod::PatternOfZeros;
+    return rx.ofdmProcessor.processPRS(v.data(), m);
+}

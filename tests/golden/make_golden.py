@@ -69,6 +69,47 @@ def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")
+    make_sync_options(r, iq)
+
+
+def sync_windows(iq):
+    """the windows golden_sync_v1.npz is quoted on: (name, 2048 samples) in a fixed order"""
+    base = 3 * TF + TNULL
+    out = []
+    for hz in (0, 2000, -3000, 7000):
+        sh = dabtx.freq_shift(iq[3 * TF: 4 * TF], hz)
+        nz = dabtx.add_awgn(sh, 6.0, seed=(hz & 0xFF) + 1)
+        for d in (0, 100, 327, -200):
+            out.append((f"clean{hz}/{d}", sh[TNULL + 504 - d: TNULL + 504 - d + TU]))
+            out.append((f"noisy{hz}/{d}", nz[TNULL + 504 - d: TNULL + 504 - d + TU]))
+    return out
+
+
+def make_sync_options(r, iq):
+    """non-default receiver options: the other two FFT placements, the three coarse frequency estimators (stage level through
+    OFDMProcessor::processPRS, and in the closed loop with the coarse corrector on)"""
+    g = {}
+    wins = sync_windows(iq)
+    g["win_sha"] = sha(np.stack([w for _, w in wins]))
+    for pl in (1, 2):
+        res = [r.find_index(w, {1: 0, 2: 1}[pl]) for _, w in wins]
+        g[f"find_index_p{pl}"] = np.array([x[0] for x in res], np.int32)
+        lim = TU if pl == 1 else 2040
+        g[f"cir_sha_p{pl}"] = np.stack([sha(x[1][:lim]) for x in res])
+    for m in (0, 1, 2):
+        g[f"coarse_m{m}"] = np.array([r.process_prs(w, m) for _, w in wins], np.int32)
+    tx = dabtx.DabTx(seed=0x51)
+    sig = dabtx.freq_shift(tx.frames(12), 2000)
+    g["loop_sha"] = sha(sig)
+    for m in (0, 1, 2):
+        e = r.e2e(sig, disable_coarse=False, select_at_fib=10 ** 9, dump_path="/tmp/golden_c.msc", freqsync_method=m)
+        g[f"loop_fibs_m{m}"] = e["fibs"]
+    for pl in (1, 2):
+        e = r.e2e(iq[:10 * TF], disable_coarse=True, select_at_fib=10 ** 9, dump_path="/tmp/golden_p.msc", fft_placement=pl)
+        g[f"loop_fibs_p{pl}"] = e["fibs"]
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_sync_v1.npz")
+    np.savez_compressed(out, **g)
+    print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

@@ -24,13 +24,13 @@ def test_exports_match_header():
     for f in fns:
         assert hasattr(lib, f), f"{f} declared in include/dab_b200.h but not exported"
     assert sorted(pkg.EXPORTS) == fns
-    assert lib.dabb_abi_version() == 1
+    assert lib.dabb_abi_version() == 2
 
 
 def test_struct_sizes():
     pkg = load_pkg()
     from welle_io_b200 import dabb200 as d
-    assert C.sizeof(d.Config) == 64 and C.sizeof(d.Subchannel) == 36
+    assert C.sizeof(d.Config) == 64 and C.sizeof(d.Subchannel) == 36 and C.sizeof(d.Options) == 32
     assert C.sizeof(d.FrameResult) == d.RESULT_DTYPE.itemsize == 224
 
 

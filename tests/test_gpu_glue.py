@@ -35,3 +35,6 @@ def test_radio_receiver_glue(oracle, tmp_path):
     k = min(len(rs), len(o["rs"]))
     assert k >= 5 and np.array_equal(rs[:k], o["rs"][:k])
     assert summary["selected"] == "1" and int(summary["services"]) == 1 and int(summary["superframes"]) >= 5
+    # one impulse response, one set of (L-1) K / 96 constellation points and one null symbol per decoded frame
+    nfr = len(fibs) // 12
+    assert int(summary["cirs"]) == int(summary["consts"]) == int(summary["nulls"]) == nfr and summary["tapsizes"] == "1"

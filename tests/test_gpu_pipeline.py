@@ -12,13 +12,14 @@ pytestmark = pytest.mark.gpu
 TF = 196608
 
 
-def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0, disable_coarse=True):
+def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0, disable_coarse=True, fft_placement=0, freqsync_method=0, taps=None):
     S = len(sigs)
     n = max(len(s) for s in sigs)
     buf = np.zeros((S, n), np.complex64)
     for i, s in enumerate(sigs):
         buf[i, :len(s)] = s
-    ctx = pkg.Context(n_streams=S, keep_taps=True, n_subch_slots=n_slots, fft_mode=fft_mode, disable_coarse=disable_coarse)
+    ctx = pkg.Context(n_streams=S, keep_taps=True, n_subch_slots=n_slots, fft_mode=fft_mode, disable_coarse=disable_coarse,
+                      fft_placement=fft_placement, freqsync_method=freqsync_method)
     d = ctx.dev(buf)
     res = [dict(info=[], fibs=[], crc=[], msc=[], rs=[], soft=[], sf=[]) for _ in range(S)]
     selected = False
@@ -27,6 +28,8 @@ def run_gpu(pkg, sigs, bitrate=96, cu=72, level=3, n_slots=1, fft_mode=0, disabl
         out = ctx.process(d, n, np.zeros(S, np.int64), n, msc_stride=3 * bitrate, sf_stride=15 * bitrate)
         r = out["results"]
         soft = ctx.read_tap(0)
+        if taps is not None:
+            taps.append((r.copy(), ctx.read_tap(1), ctx.read_tap(2), ctx.read_tap(3)))
         decoded = 0
         for i in range(S):
             if r["status"][i] != pkg.FRAME_DECODED:
@@ -189,3 +192,74 @@ def test_two_subchannel_slots_and_remove(oracle):
     lf = np.concatenate(tx.logical); g0 = np.concatenate(got0)
     hits = [k for k in range(40) if np.array_equal(g0[:288], lf[k * 288:(k + 1) * 288])]
     assert hits and np.array_equal(g0, lf[hits[0] * 288: hits[0] * 288 + len(g0)])
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_coarse_methods_closed_loop(oracle, method):
+    """all three FreqsyncMethods in the closed loop on frequency-shifted streams: coarse trajectory and FIB CRC masks like the
+    oracle (which is pinned to the reference RadioReceiver with the same option, tests/test_oracle_vs_ref.py)"""
+    pkg = load_pkg()
+    sigs = [dabtx.freq_shift(dabtx.DabTx(seed=0x51).frames(12), 2000.0), dabtx.freq_shift(dabtx.DabTx(seed=3).frames(12), -3000.0),
+            dabtx.freq_shift(dabtx.DabTx(seed=4).frames(12), 1000.0)]
+    res = run_gpu(pkg, sigs, disable_coarse=False, freqsync_method=method)
+    for i, sig in enumerate(sigs):
+        orc = oracle.rx_run(sig, disable_coarse=False, freqsync_method=method)
+        n = min(len(res[i]["info"]), orc["frames"])
+        assert n >= 8
+        assert [x[2] for x in res[i]["info"][:n]] == [x["coarse"] for x in orc["info"][:n]], (i, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
+        assert [x[0] for x in res[i]["info"][:n]] == [x["start_index"] for x in orc["info"][:n]]
+        crc_o = [int(sum(int(o) << k for k, o in enumerate(orc["fibs"][12 * f: 12 * f + 12, 0]))) for f in range(n)]
+        assert res[i]["crc"][:n] == crc_o
+
+
+@pytest.mark.parametrize("placement", [1, 2])
+def test_other_placements_closed_loop(oracle, placement):
+    pkg = load_pkg()
+    tx = dabtx.DabTx(seed=0x61); s0 = tx.frames(10)
+    s1 = np.concatenate([np.zeros(777, np.complex64), dabtx.add_awgn(dabtx.DabTx(seed=0x62).frames(10), 12.0, seed=9)])
+    sigs = [s0, s1]
+    res = run_gpu(pkg, sigs, fft_placement=placement)
+    prot = oracle.prot_eep(96, 1, 3)
+    for i, sig in enumerate(sigs):
+        orc = oracle.rx_run(sig, prot=prot, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True, fft_placement=placement)
+        compare(res[i], orc, f"placement{placement}/{i}")
+
+
+def test_diagnostic_taps(oracle):
+    """taps behind onNewImpulseResponse / onConstellationPoints / onNewNullSymbol: CIR = oracle findIndex CIR, constellation = every
+    96th r1 of the oracle demap of the same frame, null symbol = the 2656 samples after the frame times the corrected oscillator"""
+    pkg = load_pkg()
+    TU, TS, TNULL = 2048, 2552, 2656
+    s0 = dabtx.DabTx(seed=0x71).frames(8)
+    s1 = dabtx.freq_shift(dabtx.DabTx(seed=0x72).frames(8), 137.0)           # fine corrector becomes non-zero
+    sigs = [s0, s1]
+    taps = []
+    res = run_gpu(pkg, sigs, taps=taps)
+    checked = 0
+    for i, sig in enumerate(sigs):
+        orc = oracle.rx_run(sig, disable_coarse=True)
+        f = 0
+        for (r, cir, con, nul) in taps:
+            if r["status"][i] != pkg.FRAME_DECODED or r["next_pos"][i] > len(sig) or f >= orc["frames"]:
+                continue
+            info = orc["info"][f]; f += 1
+            assert int(r["start_index"][i]) == info["start_index"]
+            null_start = int(r["next_pos"][i]) - TNULL
+            prs0 = null_start - 75 * TS - TU
+            if i == 0:
+                # NCO idle: the taps are plain functions of the input samples
+                s_o, r1 = oracle.demod_frame(sig[prs0: prs0 + TU], sig[prs0 + TU: prs0 + TU + 75 * TS], True)
+                assert np.array_equal(con[i].view(np.uint32), np.ascontiguousarray(r1[:, ::96]).view(np.uint32))
+                assert np.array_equal(nul[i], sig[null_start: null_start + TNULL])
+                _, c_o = oracle.find_index(sig[info["pos"]: info["pos"] + TU])
+                assert np.array_equal(cir[i].view(np.uint32), c_o.view(np.uint32))
+            else:
+                # corrected oscillator: unit-modulus rotation whose phase falls by 2 pi (coarse + fine) / 2 048 000 per sample
+                raw = sig[null_start: null_start + TNULL]
+                rot = nul[i][100:] * np.conj(raw[100:])
+                assert np.allclose(np.abs(nul[i]), np.abs(raw), rtol=1e-5, atol=1e-7)
+                step = np.angle(np.sum(rot[1:] * np.conj(rot[:-1])))
+                hz = int(r["fine_corr"][i]) + int(r["coarse_corr"][i])
+                assert abs(step + 2 * np.pi * hz / 2048000.0) < 1e-6, (step, hz)
+            checked += 1
+    assert checked >= 10

@@ -90,6 +90,41 @@ def test_find_index(ctx, oracle, iq12):
     assert idx[0] == 504
 
 
+@pytest.mark.parametrize("placement", [1, 2])
+def test_find_index_other_placements(ctx, oracle, iq12, placement):
+    """StrongestPeak / EarliestPeakWithBinning (phasereference.cpp:93-211): index (incl. the negative scores) and CIR bit-equal"""
+    tx, iq = iq12
+    rng = np.random.default_rng(placement)
+    noisy = dabtx.add_awgn(iq, 3.0, seed=3)
+    echo = (iq[2 * TF: 3 * TF] + 0.7 * np.roll(iq[2 * TF: 3 * TF], -180)).astype(np.complex64)       # pre-echo 180 samples early
+    noise = ((rng.standard_normal(TF) + 1j * rng.standard_normal(TF)) * 0.05).astype(np.complex64)
+    frames = np.stack([iq[2 * TF: 3 * TF]] * 4 + [noisy[2 * TF: 3 * TF], echo, noise, np.zeros(TF, np.complex64)])
+    starts = np.array([TNULL - 199, TNULL - 100, TNULL - 700, TNULL + 3000, TNULL - 250, TNULL - 300, 1000, 0], np.int64)
+    idx, cir = ctx.find_index(frames, starts, want_cir=True, placement=placement)
+    for i, s in enumerate(starts):
+        i_o, c_o = oracle.find_index(frames[i, s: s + TU], placement)
+        assert idx[i] == i_o, (i, idx[i], i_o)
+        assert np.array_equal(cir[i].view(np.uint32), c_o.view(np.uint32)), i
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_coarse_estimate(ctx, oracle, iq12, method):
+    """OFDMProcessor::processPRS: PatternOfZeros / GetMiddle / CorrelatePRS on aligned, misaligned and noisy phase reference symbols
+    at several carrier offsets.  GetMiddle is bit-exact arithmetic; the two arg()-based methods truncate atan2f results to integers
+    (see oracle/dab_oracle.c), so a CUDA/glibc atan2f difference can only matter within an ulp of an integer: none may show here."""
+    tx, iq = iq12
+    frames, starts = [], []
+    for hz in (0, 1000, 2000, -3000, 7000, -12000, 333):
+        sh = dabtx.freq_shift(iq[2 * TF: 3 * TF], hz)
+        for k, src in enumerate((sh, dabtx.add_awgn(sh, 6.0, seed=hz & 0xFF))):
+            for d in (0, 100, 327, -200):
+                frames.append(src); starts.append(TNULL + 504 - d)
+    frames = np.stack(frames); starts = np.array(starts, np.int64)
+    got = ctx.coarse_estimate(frames, starts, method)
+    exp = np.array([oracle.coarse(frames[i, s: s + TU], method) for i, s in enumerate(starts)])
+    assert np.array_equal(got, exp), np.nonzero(got != exp)
+
+
 @pytest.mark.parametrize("nbits", [768, 2304, 192])
 def test_viterbi_bit_exact(ctx, oracle, nbits):
     rng = np.random.default_rng(nbits)

@@ -97,3 +97,55 @@ def test_round_trips(oracle):
     e = cw.copy(); e[[3, 40, 77, 101, 119]] ^= 0x5A
     cnt, out, pos = oracle.rs_decode_codeword(e)
     assert cnt == 5 and np.array_equal(out, cw) and sorted(p - 135 for p in pos[:5]) == [3, 40, 77, 101, 119]
+
+
+# ---- non-default receiver options (golden_sync_v1.npz): FFT placements and coarse frequency estimators
+GS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_sync_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def sync_wins(iq):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    src = open(spec.origin).read()
+    ns = {"dabtx": dabtx, "np": np, "TU": TU, "TS": TS, "TF": TF, "TNULL": TNULL}
+    start = src.index("def sync_windows"); end = src.index("def make_sync_options")
+    exec(src[start:end], ns)                      # the window list is defined once, next to the generator
+    wins = ns["sync_windows"](iq)
+    if not np.array_equal(sha(np.stack([w for _, w in wins])), GS["win_sha"]):
+        pytest.skip("synthetic windows differ from the ones the fixtures were made with (numpy version?)")
+    return wins
+
+
+@pytest.mark.parametrize("placement", [1, 2])
+def test_find_index_placements_golden(oracle, sync_wins, placement):
+    lim = TU if placement == 1 else 2040
+    for k, (name, w) in enumerate(sync_wins):
+        idx, cir = oracle.find_index(w, placement)
+        assert idx == int(GS[f"find_index_p{placement}"][k]), name
+        assert np.array_equal(sha(cir[:lim]), GS[f"cir_sha_p{placement}"][k]), name
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_coarse_estimators_golden(oracle, sync_wins, method):
+    got = np.array([oracle.coarse(w, method) for _, w in sync_wins], np.int32)
+    assert np.array_equal(got, GS[f"coarse_m{method}"]), (got, GS[f"coarse_m{method}"])
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_closed_loop_coarse_golden(oracle, method):
+    sig = dabtx.freq_shift(dabtx.DabTx(seed=0x51).frames(12), 2000)
+    if not np.array_equal(sha(sig), GS["loop_sha"]):
+        pytest.skip("synthetic stream differs from the fixture's")
+    m = oracle.rx_run(sig, disable_coarse=False, freqsync_method=method)
+    ref = GS[f"loop_fibs_m{method}"]
+    n = min(len(ref), len(m["fibs"]))
+    assert n >= 12 * 8 and np.array_equal(m["fibs"][:n], ref[:n])
+
+
+@pytest.mark.parametrize("placement", [1, 2])
+def test_closed_loop_placement_golden(oracle, iq, placement):
+    m = oracle.rx_run(iq[:10 * TF], disable_coarse=True, fft_placement=placement)
+    ref = GS[f"loop_fibs_p{placement}"]
+    n = min(len(ref), len(m["fibs"]))
+    assert n >= 12 * 7 and np.array_equal(m["fibs"][:n], ref[:n])

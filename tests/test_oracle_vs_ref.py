@@ -158,3 +158,53 @@ def test_closed_loop_with_noise(oracle, ref, tmp_path):
     assert np.array_equal(m["fibs"][:len(e["fibs"])], e["fibs"])
     n = min(len(m["msc"]), len(e["msc"]))
     assert n > 0 and np.array_equal(m["msc"][:n], e["msc"][:n])
+
+
+@pytest.mark.parametrize("placement", [1, 2])
+def test_find_index_other_placements(oracle, ref, sig, placement):
+    """StrongestPeak / EarliestPeakWithBinning (phasereference.cpp:93-211): index and CIR, on aligned, shifted, noisy,
+    signal-free and all-zero windows"""
+    tx, iq = sig
+    base = 3 * TF + TNULL
+    rng = np.random.default_rng(placement)
+    wins = [iq[base - off: base - off + TU] for off in (199, 100, 350, 700, -3000)]
+    wins.append(dabtx.add_awgn(iq, 3.0, seed=3)[base - 250: base - 250 + TU])
+    wins.append((rng.standard_normal(TU) + 1j * rng.standard_normal(TU)).astype(np.complex64) * 0.05)      # no PRS at all
+    wins.append(np.zeros(TU, np.complex64))
+    echo = iq[base - 300: base - 300 + TU] + 0.7 * iq[base - 300 - 180: base - 300 - 180 + TU]            # pre-echo 180 samples earlier
+    wins.append(echo.astype(np.complex64))
+    for k, v in enumerate(wins):
+        i1, c1 = oracle.find_index(v, placement)
+        i2, c2 = ref.find_index(v, {1: 0, 2: 1}[placement])
+        assert i1 == i2, (k, i1, i2)
+        lim = TU if placement == 1 else 2040          # the binning variant never looks at the last 8 samples
+        assert np.array_equal(c1[:lim].view(np.uint32), c2[:lim].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("method,shift_hz", [(0, 2000), (1, 2000), (2, 2000), (2, -3000), (0, 0)])
+def test_closed_loop_coarse_corrector(oracle, ref, tmp_path, method, shift_hz):
+    """coarse frequency corrector on (welle-cli default): PatternOfZeros / GetMiddle / CorrelatePRS (ofdm-processor.cpp:537-644)
+    in the closed loop - identical FIB stream (flags and payloads) and identical final correctors"""
+    tx = dabtx.DabTx(seed=0x51 + method)
+    iq = dabtx.freq_shift(tx.frames(12), shift_hz)
+    e = ref.e2e(iq, disable_coarse=False, select_at_fib=10 ** 9, dump_path=str(tmp_path / "c.msc"), freqsync_method=method)
+    m = oracle.rx_run(iq, disable_coarse=False, freqsync_method=method)
+    assert len(e["fibs"]) >= 12 * 8
+    n = min(len(m["fibs"]), len(e["fibs"]))
+    assert np.array_equal(m["fibs"][:n], e["fibs"][:n])
+    if len(e["corr"]):
+        # onFrequencyCorrectorChange samples the state every 0.2 s of input, i.e. also between the coarse update of a frame and
+        # its fine update: (fine of frame k-1, coarse of frame k) is as legitimate as the end-of-frame pair
+        inf = m["info"]
+        pairs = [(i["fine"], i["coarse"]) for i in inf] + [(inf[k - 1]["fine"], inf[k]["coarse"]) for k in range(1, len(inf))] + [(0, inf[0]["coarse"])]
+        assert tuple(int(x) for x in e["corr"][-1]) in pairs
+
+
+@pytest.mark.parametrize("placement", [1, 2])
+def test_closed_loop_other_placements(oracle, ref, tmp_path, placement):
+    tx = dabtx.DabTx(seed=0x61)
+    iq = tx.frames(10)
+    e = ref.e2e(iq, disable_coarse=True, select_at_fib=10 ** 9, dump_path=str(tmp_path / "p.msc"), fft_placement=placement)
+    m = oracle.rx_run(iq, disable_coarse=True, fft_placement=placement)
+    n = min(len(m["fibs"]), len(e["fibs"]))
+    assert n >= 12 * 7 and np.array_equal(m["fibs"][:n], e["fibs"][:n])

@@ -39,6 +39,8 @@ struct StepScratch {        // per stream, rewritten every step
     int32_t r_start_index, r_fine, r_coarse;
     float r_fx, r_fy, r_slevel;
     int64_t r_next_pos;
+    int64_t null_pos;       // logical index of the first sample of the null symbol that follows this frame
+    int32_t null_lp, null_ph;   // NCO phase before that sample, and the increment the null is read with
 };
 
 std::string g_create_error;
@@ -48,14 +50,14 @@ std::string g_create_error;
 struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
-    cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
     int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
-    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr;
     int8_t* d_soft = nullptr; uint32_t* d_fic_rows = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
     dabb_frame_result* d_results = nullptr;
     // per slot
@@ -272,7 +274,9 @@ __global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int gro
         const double upd = 0.1 * (double)(float)atan2((double)fy, (double)fx) / 3.14159265358979323846 * 500;
         z.fine = (int32_t)(int16_t)((double)z.fine + upd);
         const int32_t p3 = z.coarse + z.fine;
-        const int64_t lp = (int64_t)z.local_phase - (int64_t)(TU + idx) * p1 - (int64_t)75 * TS * p2 - (int64_t)TNULL * p3;
+        const int64_t lpn = (int64_t)z.local_phase - (int64_t)(TU + idx) * p1 - (int64_t)75 * TS * p2;
+        c.null_pos = z.pos + (int64_t)TU + idx + 75 * (int64_t)TS; c.null_lp = mod_rate(lpn); c.null_ph = p3;
+        const int64_t lp = lpn - (int64_t)TNULL * p3;
         z.local_phase = mod_rate(lp);
         z.pos += (int64_t)TU + idx + 75 * (int64_t)TS + TNULL;
         if (z.fine > 500) { z.coarse += 1000; z.fine -= 1000; }
@@ -283,6 +287,28 @@ __global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int gro
     }
     c.r_fine = z.fine; c.r_coarse = z.coarse; c.r_next_pos = z.pos; c.r_slevel = z.slevel;
     scr[s] = c;
+}
+
+// diagnostics tap: the null symbol as OFDMProcessor::run hands it to onNewNullSymbol (ofdm-processor.cpp:462-469): T_null
+// samples read with the NCO at coarse + fine (after this frame's fine update)
+__global__ void null_tap_kernel(const StepScratch* scr, const float2* iq, int64_t stride, const int64_t* buf_start, int64_t buf_len, const float2* osc, float2* out)
+{
+    const int s = blockIdx.x;
+    const StepScratch c = scr[s];
+    float2* dst = out + (int64_t)s * TNULL;
+    const int64_t p0 = c.null_pos - buf_start[s];
+    const bool mix = c.null_lp != 0 || c.null_ph != 0;
+    for (int i = threadIdx.x; i < TNULL; i += blockDim.x) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c.active && p0 >= 0 && p0 + i < buf_len) {
+            v = iq[(int64_t)s * stride + p0 + i];
+            if (mix) {
+                const float2 o = osc[mod_rate((int64_t)c.null_lp - (int64_t)(i + 1) * c.null_ph)];
+                v = make_float2(__fsub_rn(__fmul_rn(v.x, o.x), __fmul_rn(v.y, o.y)), __fadd_rn(__fmul_rn(v.x, o.y), __fmul_rn(v.y, o.x)));
+            }
+        }
+        dst[i] = v;
+    }
 }
 
 // lane B, after FIC / MSC / RS of the frame: decoder-side state and the result record
@@ -390,7 +416,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device: this library has no CPU fallback"; return DABB_E_NODEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return DABB_E_ARG; }
     dabb_ctx* ctx = new dabb_ctx();
-    ctx->device = cfg->device; ctx->S = cfg->n_streams; ctx->fft_mode = cfg->fft_mode; ctx->disable_coarse = cfg->disable_coarse; ctx->keep_taps = cfg->keep_taps;
+    ctx->device = cfg->device; ctx->S = cfg->n_streams; ctx->fft_mode = cfg->fft_mode; ctx->disable_coarse = cfg->disable_coarse; ctx->keep_taps = cfg->keep_taps; ctx->placement = cfg->fft_placement; ctx->freqsync = cfg->freqsync_method;
     ctx->n_slots = cfg->n_subch_slots > 0 ? (cfg->n_subch_slots > DABB_MAX_SUBCH ? DABB_MAX_SUBCH : cfg->n_subch_slots) : 1;
     ctx->max_cu = cfg->max_subch_cu > 0 ? cfg->max_subch_cu : 144;
     ctx->groups = cfg->ofdm_groups > 0 ? cfg->ofdm_groups : (ctx->S >= 1024 ? 1 : (ctx->S >= 64 ? 5 : 25));
@@ -448,7 +474,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         (rc = dalloc(ctx, &ctx->d_fibs, (size_t)S * 12 * 32)) || (rc = dalloc(ctx, &ctx->d_crc, S)) || (rc = dalloc(ctx, &ctx->d_results, S)) ||
         (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)))
         return fail(rc);
-    if (ctx->keep_taps && (rc = dalloc(ctx, &ctx->d_cir, (size_t)S * TU))) return fail(rc);
+    if (ctx->keep_taps && ((rc = dalloc(ctx, &ctx->d_cir, (size_t)S * TU)) || (rc = dalloc(ctx, &ctx->d_r1, (size_t)S * 75 * 1536)) || (rc = dalloc(ctx, &ctx->d_null, (size_t)S * TNULL)))) return fail(rc);
     if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, 774)))) return fail(rc);
     { void* q = nullptr; if (cudaMalloc(&q, vit_dec_bytes(S * 4, 774)) != cudaSuccess) { ctx->err = "cudaMalloc(FIC decisions)"; return fail(DABB_E_NOMEM); } ctx->allocs.push_back(q); ctx->d_dec_fic = (uint2*)q; }
     ctx->h_slots.assign((size_t)S * ctx->n_slots, MscSlotState{});
@@ -651,19 +677,23 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     plan_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, ctx->d_buf_start, io->buf_len, S, d_win, d_nco_sync, d_active);
     if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
     SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = d_win; sp.nco = d_nco_sync; sp.active = d_active; sp.index_out = d_index; sp.cir_out = ctx->d_cir; sp.n = S;
-    sp.fic_ratio = ctx->d_fic_ratio; sp.coarse_out = ctx->disable_coarse ? nullptr : ctx->d_coarse;
+    sp.fic_ratio = ctx->d_fic_ratio; sp.coarse_out = ctx->disable_coarse ? nullptr : ctx->d_coarse; sp.placement = ctx->placement; sp.freqsync = ctx->freqsync;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
     post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, ctx->disable_coarse ? nullptr : ctx->d_coarse, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
-    op.r1 = nullptr; op.freqcorr = d_fc; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
     // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
     op.smem_floor = serial ? 0 : ctx->ofdm_smem_floor;
     launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
     advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->groups, d_fc);
     if ((rc = check_launch(ctx, "advance_kernel"))) return rc;
+    if (ctx->d_null) {
+        null_tap_kernel<<<S, 256, 0, A>>>(scr, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, ctx->d_null);
+        if ((rc = check_launch(ctx, "null_tap_kernel"))) return rc;
+    }
     if (!serial) { CK(cudaEventRecord(ctx->evA[par], A)); CK(cudaStreamWaitEvent(B, ctx->evA[par], 0)); }
     // ---------------- lane B: FIC chain forked onto its own stream, MSC chain per slot (longest first), then the result record.
     // (One fused Viterbi launch over FIC + MSC codewords was measured slower: 1.44 ms vs 0.34 + 1.02 ms.)
@@ -770,6 +800,13 @@ int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes)
     sync_all(ctx);
     if (what == 0) { const size_t n = (size_t)ctx->S * DABB_SOFT_PER_FRAME; CK(cudaMemcpy(host_out, ctx->d_soft + (size_t)ctx->last_parity * n, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     if (what == 1 && ctx->d_cir) { const size_t n = (size_t)ctx->S * TU * 4; CK(cudaMemcpy(host_out, ctx->d_cir, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
+    if (what == 2 && ctx->d_r1) {      // every 96th logical carrier of every data symbol (constellationDecimation, ofdm-decoder.h:87)
+        const size_t n = (size_t)ctx->S * 75 * 16;
+        if (bytes < n * 8) { ctx->err = "constellation tap needs n_streams * 1200 * 8 bytes"; return DABB_E_ARG; }
+        CK(cudaMemcpy2D(host_out, 8, ctx->d_r1, 96 * 8, 8, n, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (what == 3 && ctx->d_null) { const size_t n = (size_t)ctx->S * TNULL * 8; CK(cudaMemcpy(host_out, ctx->d_null, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     ctx->err = "tap not available (keep_taps = 0?)";
     return DABB_E_STATE;
 }
@@ -799,14 +836,35 @@ int dabb_ofdm_demod(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_
     return rc;
 }
 
-int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* win_start, int32_t n, int32_t* index_out, float* cir_out)
+int dabb_find_index_ex(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* win_start, int32_t n, int32_t placement, int32_t* index_out, float* cir_out)
 {
-    if (!ctx || !iq || !win_start || !index_out || n < 1) return DABB_E_ARG;
+    if (!ctx || !iq || !win_start || !index_out || n < 1 || placement < 0 || placement > 2) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
-    SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n; sp.fic_ratio = nullptr; sp.coarse_out = nullptr;
+    SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n; sp.fic_ratio = nullptr; sp.coarse_out = nullptr; sp.placement = placement; sp.freqsync = 0;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
     return check_launch(ctx, "find_index_kernel");
+}
+
+int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* win_start, int32_t n, int32_t* index_out, float* cir_out)
+{
+    return dabb_find_index_ex(ctx, iq, stride, win_start, n, DABB_PLACEMENT_THRESHOLD_BEFORE_PEAK, index_out, cir_out);
+}
+
+int dabb_coarse_estimate(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* prs_start, int32_t n, int32_t method, int32_t* offset_out)
+{
+    if (!ctx || !iq || !prs_start || !offset_out || n < 1 || method < 0 || method > 2) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    sync_all(ctx);
+    launch_coarse(ctx->dev, reinterpret_cast<const float2*>(iq), stride, prs_start, n, method, offset_out, ctx->stream);
+    return check_launch(ctx, "coarse_kernel");
+}
+
+int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt)
+{
+    if (!ctx || !opt || opt->fft_placement < 0 || opt->fft_placement > 2 || opt->freqsync_method < 0 || opt->freqsync_method > 2) return DABB_E_ARG;
+    ctx->disable_coarse = opt->disable_coarse != 0; ctx->placement = opt->fft_placement; ctx->freqsync = opt->freqsync_method;
+    return DABB_OK;
 }
 
 int dabb_viterbi(dabb_ctx* ctx, const int8_t* soft, int32_t n_cw, int32_t nbits, uint8_t* bits_out)

@@ -43,10 +43,13 @@ struct SyncParams {
     // coarse frequency corrector (OFDMProcessor::processPRS, PatternOfZeros): evaluated for streams whose FIC success
     // counter is below 5 (ofdm-processor.cpp:397); result = carrier offset, or 0 when not evaluated
     const int32_t* fic_ratio; int32_t* coarse_out;
+    int placement;      // DABB_PLACEMENT_*: 0 ThresholdBeforePeak, 1 StrongestPeak, 2 EarliestPeakWithBinning
+    int freqsync;       // DABB_FREQSYNC_*: 0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS
 };
 
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
 void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
+void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st);
 
 // ---- host-side table builders (tables.cpp) ----
 struct HostTables {

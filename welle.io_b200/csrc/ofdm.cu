@@ -356,9 +356,113 @@ struct __align__(16) SyncSmem {
     float cir[TU];
     float2 spec[128];
     float cand[128];
+    float cv[96]; float refarg[24];
     float wmax[4]; int wmin[4];
     float sum;
 };
+
+// coarse frequency estimate of one aligned PRS = the T_u samples at src[off ..]; collective over the CTA, result via *out
+template <bool EXACT>
+__device__ __forceinline__ void coarse_estimate(const DevTables& tb, SyncSmem& sm, const float2* __restrict__ src, int64_t off, const Nco& nco, const XIdx& xi,
+                                                int t, int freqsync, int32_t* out)
+{
+    // ---- coarse AFC (OFDMProcessor::processPRS, ofdm-processor.cpp:537-644): FFT of the aligned PRS (window start + index).
+    // NOTE on `abs`: in the reference's translation unit the unqualified abs() of a float/double is the C library's
+    // int abs(int) - the argument is truncated to int first (see oracle/dab_oracle.c, pinned against the compiled reference).
+    float2 v[16];
+    __syncthreads();
+    if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_fwd[t];
+    __syncthreads();
+    // the PRS useful part starts `off` samples into the window; its samples continue the NCO phase sequence
+    fft2048_from_global<EXACT, false>(src, off, v, sm.o, t, xi, tb.osc, nco, tb.tw_fwd + TwLayout::C5);
+    if (freqsync == 1) {
+        // ---- GetMiddle (:617-644), including its `sum = oldMax` assignment: moving sum of |X| over K carriers
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int bin = t + 128 * (c & 3) + 512 * (c >> 2);
+            const double m = __dsqrt_rn(__dadd_rn(__dmul_rn((double)v[c].x, (double)v[c].x), __dmul_rn((double)v[c].y, (double)v[c].y)));
+            sm.cir[bin] = (float)m;
+        }
+        __syncthreads();
+        if (t == 0) {
+            float sum = 0.f, oldMax = 0.f; int maxIndex = 0;
+            for (int i = 40; i < 1536 + 40; i++) sum = __fadd_rn(sum, sm.cir[(TU / 2 + i) % TU]);
+            for (int i = 40; i < TU - (1536 - 40); i++) {
+                sum = __fsub_rn(sum, sm.cir[(TU / 2 + i) % TU]);
+                sum = __fadd_rn(sum, sm.cir[(TU / 2 + i + 1536) % TU]);
+                if (sum > oldMax) { sum = oldMax; maxIndex = i; }
+            }
+            *out = (int16_t)(maxIndex - (TU - 1536) / 2);
+        }
+        return;
+    }
+    // bins 2012..2047 and 0..63 in natural order
+    float2* spec = sm.spec;     // [0..35] = bins 2012..2047, [36..99] = bins 0..63
+    if (t < 64) spec[36 + t] = v[0];
+    if (t >= 92) spec[t - 92] = v[15];
+    __syncthreads();
+    auto ap = [&](int a, int b) -> float {       // arg(X[a] * conj(X[b]))
+        const float2 A = spec[a], B = spec[b];
+        const float c = B.x, d = -B.y;
+        const float re = __fsub_rn(__fmul_rn(A.x, c), __fmul_rn(A.y, d)), im = __fadd_rn(__fmul_rn(A.x, d), __fmul_rn(A.y, c));
+        return atan2f(im, re);
+    };
+    auto iabs_f = [](float x) -> float { return (float)abs(__float2int_rz(x)); };                       // abs(float) -> int abs(int)
+    auto iabs_pi = [](float x) -> float {                                                                 // abs(abs(x / M_PI) - 1)
+        const int q = abs(__double2int_rz(__ddiv_rn((double)x, 3.14159265358979323846)));
+        return (float)abs(q - 1);
+    };
+    if (freqsync == 2) {
+        // ---- CorrelatePRS (:546-581): phase differences of adjacent carriers against those of the reference table
+        if (t < 24) {
+            const float2 A = tb.prs_ref[t], B = tb.prs_ref[t + 1];
+            const float c = B.x, d = -B.y;
+            sm.refarg[t] = atan2f(__fadd_rn(__fmul_rn(A.x, d), __fmul_rn(A.y, c)), __fsub_rn(__fmul_rn(A.x, c), __fmul_rn(A.y, d)));
+        }
+        if (t < 96) sm.cv[t] = ap(t, t + 1);
+        __syncthreads();
+        float mysum = 0.f;
+        if (t < 72) for (int j = 0; j < 24; j++) mysum = __fadd_rn(mysum, iabs_f(__fmul_rn(sm.refarg[j], sm.cv[t + j])));
+        sm.cand[t] = mysum;
+        __syncthreads();
+        if (t == 0) {
+            // the partial sums only grow, so `sum > MMax` inside the j loop is decided by the full sum: first strict maximum
+            float MMax = 0.f; int index = 100;
+            for (int i = 0; i < 72; i++) if (sm.cand[i] > MMax) { MMax = sm.cand[i]; index = i; }
+            *out = (int16_t)(TU - 36 + index - TU);
+        }
+        return;
+    }
+    // ---- PatternOfZeros (:582-613) over +-36 carriers
+    float mysum = 1e30f;
+    if (t < 72) {
+        // candidate i = Tu - 36 + t; fft_buffer[(i + k) % Tu] = spec[t + k]
+        const float a1 = iabs_pi(ap(t + 1, t + 2)), a2 = iabs_pi(ap(t + 2, t + 3));
+        const float a3 = iabs_f(ap(t + 3, t + 4)), a4 = iabs_f(ap(t + 4, t + 5)), a5 = iabs_f(ap(t + 5, t + 6));
+        const float b1 = iabs_pi(ap(t + 17, t + 19));
+        const float b2 = iabs_f(ap(t + 19, t + 20)), b3 = iabs_f(ap(t + 20, t + 21)), b4 = iabs_f(ap(t + 21, t + 22));
+        mysum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4), a5), b1), b2), b3), b4);
+    }
+    sm.cand[t] = mysum;
+    __syncthreads();
+    if (t == 0) {
+        float mmin = 1000.f; int index = 100;      // sequential first-minimum like the CPU loop
+        for (int i = 0; i < 72; i++) if (sm.cand[i] < mmin) { mmin = sm.cand[i]; index = TU - 36 + i; }
+        *out = index - TU;
+    }
+}
+
+// stage-level processPRS: one CTA per aligned PRS
+__global__ void __launch_bounds__(OFDM_THREADS, 5)
+coarse_kernel(DevTables tb, const float2* iq, int64_t stride, const int64_t* prs_start, int freqsync, int32_t* out)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    SyncSmem& sm = *reinterpret_cast<SyncSmem*>(smraw);
+    const int t = threadIdx.x, f = blockIdx.x;
+    const Nco nco = make_nco(0, 0);
+    const XIdx xi = make_xidx(t);
+    coarse_estimate<true>(tb, sm, iq + (int64_t)f * stride, prs_start[f], nco, xi, t, freqsync, out + f);
+}
 
 template <bool EXACT, bool NCO>
 __global__ void __launch_bounds__(OFDM_THREADS, 5)
@@ -427,99 +531,126 @@ find_index_kernel(DevTables tb, SyncParams p)
         sm.cir[t + 128 * c] = (float)m;
     }
     __syncthreads();
-    if (p.cir_out) for (int i = t; i < TU; i += OFDM_THREADS) p.cir_out[(int64_t)f * TU + i] = sm.cir[i];
-    // sliding maximum over 100 samples for i < 1948, 0 beyond (phasereference.cpp:222-238).  max() is exact, so the
-    // window maximum is built by doubling (2, 4, .. 64 samples, then max(m64[i], m64[i+36])) through the two halves of
-    // the exchange buffer instead of 100 compares per output.  The sequential sum of |.| (same order as the CPU loop, so
-    // the same float) is spread by thread 0 over the seven phases.
+    // the binning placement never computes the last 8 magnitudes (loop bound i + 20 < Tu, phasereference.cpp:148)
+    if (p.cir_out) for (int i = t; i < TU; i += OFDM_THREADS) p.cir_out[(int64_t)f * TU + i] = (p.placement == 2 && i >= 2040) ? 0.f : sm.cir[i];
     float* ma = reinterpret_cast<float*>(sm.o.xbuf);
     float* mb = ma + TU;
-    float* pk = ma;
-    float ssum = 0.f;
-    {
-        const float* srcm = sm.cir;
-        float* dstm = ma;
+    int result;                 // what findIndex returns: >= 0 sample index, < 0 no synchronisation
+    if (p.placement == 0) {
+        // ---- ThresholdBeforePeak (phasereference.cpp:212-253).
+        // sliding maximum over 100 samples for i < 1948, 0 beyond (:222-238).  max() is exact, so the window maximum is
+        // built by doubling (2, 4, .. 64 samples, then max(m64[i], m64[i+36])) through the two halves of the exchange
+        // buffer instead of 100 compares per output.  The sequential sum of |.| (same order as the CPU loop, so the same
+        // float) is spread by thread 0 over the seven phases.
+        float* pk = ma;
+        float ssum = 0.f;
+        {
+            const float* srcm = sm.cir;
+            float* dstm = ma;
 #pragma unroll 1
-        for (int lvl = 0; lvl < 6; lvl++) {
-            const int sh = 1 << lvl;
+            for (int lvl = 0; lvl < 6; lvl++) {
+                const int sh = 1 << lvl;
 #pragma unroll
-            for (int c = 0; c < 16; c++) { const int i = t + 128 * c; dstm[i] = fmaxf(srcm[i], srcm[min(i + sh, TU - 1)]); }
-            if (t == 0) { for (int i = 293 * lvl; i < 293 * (lvl + 1); i++) ssum = __fadd_rn(ssum, sm.cir[i]); }
-            __syncthreads();
-            srcm = dstm; dstm = (dstm == ma) ? mb : ma;
+                for (int c = 0; c < 16; c++) { const int i = t + 128 * c; dstm[i] = fmaxf(srcm[i], srcm[min(i + sh, TU - 1)]); }
+                if (t == 0) { for (int i = 293 * lvl; i < 293 * (lvl + 1); i++) ssum = __fadd_rn(ssum, sm.cir[i]); }
+                __syncthreads();
+                srcm = dstm; dstm = (dstm == ma) ? mb : ma;
+            }
         }
-    }
-    // six levels: cir -> ma -> mb -> ma -> mb -> ma -> mb; m64 now in mb, result into ma
-    float gmax = -10000.f;
+        // six levels: cir -> ma -> mb -> ma -> mb -> ma -> mb; m64 now in mb, result into ma
+        float gmax = -10000.f;
 #pragma unroll
-    for (int c = 0; c < 16; c++) {
-        const int i = t + 128 * c;
-        float m = 0.f;
-        if (i + 100 < TU) { m = fmaxf(mb[i], mb[i + 36]); gmax = fmaxf(gmax, m); }
-        pk[i] = m;
-    }
-    if (t == 0) { for (int i = 293 * 6; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
+        for (int c = 0; c < 16; c++) {
+            const int i = t + 128 * c;
+            float m = 0.f;
+            if (i + 100 < TU) { m = fmaxf(mb[i], mb[i + 36]); gmax = fmaxf(gmax, m); }
+            pk[i] = m;
+        }
+        if (t == 0) { for (int i = 293 * 6; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
-    if ((t & 31) == 0) sm.wmax[t >> 5] = gmax;
-    __syncthreads();
-    gmax = fmaxf(fmaxf(sm.wmax[0], sm.wmax[1]), fmaxf(sm.wmax[2], sm.wmax[3]));
-    int best = 1 << 30;
-    // `3 * sum / Tu`: float 3*sum, then / (size_t Tu converted to float)
-    if (gmax > __fdiv_rn(__fmul_rn(3.0f, sm.sum), 2048.0f)) {
-        const float thresh = gmax / 2;
-        for (int i = t; i + 100 < TU; i += OFDM_THREADS) if (pk[i + 100] > thresh) { best = min(best, i); }
-    }
+        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
+        if ((t & 31) == 0) sm.wmax[t >> 5] = gmax;
+        __syncthreads();
+        gmax = fmaxf(fmaxf(sm.wmax[0], sm.wmax[1]), fmaxf(sm.wmax[2], sm.wmax[3]));
+        int best = 1 << 30;
+        // `3 * sum / Tu`: float 3*sum, then / (size_t Tu converted to float)
+        if (gmax > __fdiv_rn(__fmul_rn(3.0f, sm.sum), 2048.0f)) {
+            const float thresh = gmax / 2;
+            for (int i = t; i + 100 < TU; i += OFDM_THREADS) if (pk[i + 100] > thresh) { best = min(best, i); }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
-    if ((t & 31) == 0) sm.wmin[t >> 5] = best;
-    __syncthreads();
-    best = min(min(sm.wmin[0], sm.wmin[1]), min(sm.wmin[2], sm.wmin[3]));
-    if (t == 0) p.index_out[f] = best == (1 << 30) ? -1 : best;
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_down_sync(0xffffffffu, best, o));
+        if ((t & 31) == 0) sm.wmin[t >> 5] = best;
+        __syncthreads();
+        best = min(min(sm.wmin[0], sm.wmin[1]), min(sm.wmin[2], sm.wmin[3]));
+        result = best == (1 << 30) ? -1 : best;
+    } else if (p.placement == 1) {
+        // ---- StrongestPeak (:93-123): sequential sum, first maximum (strict >), negative score when below 3 x mean
+        float mx = -10000.f; int mi = -1;
+#pragma unroll
+        for (int c = 0; c < 16; c++) { const int i = t + 128 * c; const float val = sm.cir[i]; if (val > mx) { mx = val; mi = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, mx, o); const int oi = __shfl_down_sync(0xffffffffu, mi, o);
+            if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+        }
+        if ((t & 31) == 0) { sm.wmax[t >> 5] = mx; sm.wmin[t >> 5] = mi; }
+        if (t == 32) { float ssum = 0.f; for (int i = 0; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
+        __syncthreads();
+        mx = sm.wmax[0]; mi = sm.wmin[0];
+#pragma unroll
+        for (int w = 1; w < 4; w++) if (sm.wmax[w] > mx || (sm.wmax[w] == mx && sm.wmin[w] < mi)) { mx = sm.wmax[w]; mi = sm.wmin[w]; }
+        const float sum = sm.sum;
+        if (sum == 0.f) result = -1;
+        else if (mx < __fdiv_rn(__fmul_rn(3.0f, sum), 2048.0f)) result = (int)__fsub_rn(-fabsf(__fdiv_rn(__fmul_rn(mx, 2048.0f), sum)), 1.0f);
+        else result = mi;
+    } else {
+        // ---- EarliestPeakWithBinning (:124-211): 102 bins of 20 samples; the 4 strongest bins within 500 samples of the
+        // strongest one; of those above 3 x mean, the earliest.  Bins of exactly equal value are ordered by position
+        // (the reference's std::sort leaves that order unspecified).
+        float* bval = ma; int* bidx = reinterpret_cast<int*>(mb);
+        constexpr int NB = 102;
+        if (t < NB) {
+            float pv = 0.f; int pi = -1;
+            for (int j = 0; j < 20; j++) { const float val = sm.cir[20 * t + j]; if (val > pv) { pv = val; pi = 20 * t + j; } }
+            bval[t] = pv; bidx[t] = pi;
+        }
+        if (t == 127) { float ssum = 0.f; for (int i = 0; i < 20 * NB; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = __fdiv_rn(ssum, 2048.0f); }
+        __syncthreads();
+        if (t == 0) {
+            int top = 0;
+            for (int b = 1; b < NB; b++) if (bval[b] > bval[top]) top = b;
+            const int peak_index = bidx[top];
+            const float thresh = __fmul_rn(3.0f, sm.sum);
+            unsigned long long used0 = 0, used1 = 0;      // 102 flags
+            int earliest = -1; bool have = false;
+            for (int k = 0; k < 4; k++) {
+                int best = -1;
+                for (int b = 0; b < NB; b++) {
+                    const bool u = b < 64 ? (used0 >> b) & 1 : (used1 >> (b - 64)) & 1;
+                    if (u || abs(bidx[b] - peak_index) > 500) continue;
+                    if (best < 0 || bval[b] > bval[best]) best = b;
+                }
+                if (best < 0) break;
+                if (best < 64) used0 |= 1ull << best; else used1 |= 1ull << (best - 64);
+                if (bval[best] < thresh) continue;
+                if (!have || bidx[best] < earliest) { earliest = bidx[best]; have = true; }
+            }
+            sm.wmin[0] = have ? earliest : -1;
+        }
+        __syncthreads();
+        result = sm.wmin[0];
+    }
+    if (t == 0) p.index_out[f] = result;
     if (!p.coarse_out) return;
     if (t == 0) p.coarse_out[f] = 0;
-    if (best == (1 << 30) || p.fic_ratio[f] * 10 >= 50) return;      // CTA-uniform
-    // ---- coarse AFC: FFT of the aligned PRS (window start + index), then the "pattern of zeros" search over +-36 carriers
-    // (ofdm-processor.cpp:537-545,582-613).  Needs bins 2012..2047 and 0..58 in natural order: staged in sm.cir (as float2).
-    __syncthreads();
-    if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_fwd[t];
-    __syncthreads();
-    // the PRS useful part starts `best` samples into the window; its samples continue the NCO phase sequence
-    Nco nco2 = nco;
-    if (nco.mix) nco2.lp0 = nco.lp0;       // fetch indices are relative to the window start, so the same lp0/ph apply with w0 = best
-    fft2048_from_global<EXACT, false>(src, best, v, sm.o, t, xi, tb.osc, nco2, tb.tw_fwd + TwLayout::C5);
-    float2* spec = sm.spec;     // [0..35] = bins 2012..2047, [36..94] = bins 0..58
-    if (t < 59) spec[36 + t] = v[0];
-    if (t >= 92) spec[t - 92] = v[15];
-    __syncthreads();
-    float mysum = 1e30f;
-    if (t < 72) {
-        // candidate i = Tu - 36 + t; fft_buffer[(i + k) % Tu] = spec[t + k]
-        auto ap = [&](int a, int b) -> float {       // arg(X[a] * conj(X[b]))
-            const float2 A = spec[a], B = spec[b];
-            const float c = B.x, d = -B.y;
-            const float re = __fsub_rn(__fmul_rn(A.x, c), __fmul_rn(A.y, d)), im = __fadd_rn(__fmul_rn(A.x, d), __fmul_rn(A.y, c));
-            return atan2f(im, re);
-        };
-        const double PI = 3.14159265358979323846;
-        const float a1 = (float)fabs(fabs((double)ap(t + 1, t + 2) / PI) - 1);
-        const float a2 = (float)fabs(fabs((double)ap(t + 2, t + 3) / PI) - 1);
-        const float a3 = fabsf(ap(t + 3, t + 4)), a4 = fabsf(ap(t + 4, t + 5)), a5 = fabsf(ap(t + 5, t + 6));
-        const float b1 = (float)fabs(fabs((double)ap(t + 17, t + 19) / PI) - 1);
-        const float b2 = fabsf(ap(t + 19, t + 20)), b3 = fabsf(ap(t + 20, t + 21)), b4 = fabsf(ap(t + 21, t + 22));
-        mysum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4), a5), b1), b2), b3), b4);
-    }
-    sm.cand[t] = mysum;
-    __syncthreads();
-    if (t == 0) {
-        float mmin = 1000.f; int index = 100;      // sequential first-minimum like the CPU loop
-        for (int i = 0; i < 72; i++) if (sm.cand[i] < mmin) { mmin = sm.cand[i]; index = TU - 36 + i; }
-        p.coarse_out[f] = index - TU;
-    }
+    if (result < 0 || p.fic_ratio[f] * 10 >= 50) return;      // CTA-uniform
+    coarse_estimate<EXACT>(tb, sm, src, result, nco, xi, t, p.freqsync, &p.coarse_out[f]);
 }
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------------------------
 template <typename K> static void set_smem(K k, size_t bytes)
 {
     // every template instantiation is its own function: set the attribute per launch (it is a cheap host-side call)
@@ -536,6 +667,12 @@ void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, c
     if (fft_mode == 0) { if (tap) LAUNCH(true, true, false); else if (direct) LAUNCH(true, false, true); else LAUNCH(true, false, false); }
     else { if (tap) LAUNCH(false, true, false); else LAUNCH(false, false, false); }
 #undef LAUNCH
+}
+
+void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st)
+{
+    set_smem(coarse_kernel, sizeof(SyncSmem));
+    coarse_kernel<<<n, OFDM_THREADS, sizeof(SyncSmem), st>>>(tb, iq, stride, prs_start, freqsync, out);
 }
 
 void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st)

@@ -26,7 +26,16 @@ class DabbError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_streams", C.c_int32), ("transmission_mode", C.c_int32),
                 ("fft_mode", C.c_int32), ("disable_coarse", C.c_int32), ("keep_taps", C.c_int32), ("n_subch_slots", C.c_int32),
-                ("max_subch_cu", C.c_int32), ("ofdm_groups", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("max_subch_cu", C.c_int32), ("ofdm_groups", C.c_int32), ("fft_placement", C.c_int32), ("freqsync_method", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class Options(C.Structure):
+    _fields_ = [("disable_coarse", C.c_int32), ("fft_placement", C.c_int32), ("freqsync_method", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+PLACEMENT_THRESHOLD_BEFORE_PEAK, PLACEMENT_STRONGEST_PEAK, PLACEMENT_EARLIEST_PEAK_WITH_BINNING = 0, 1, 2
+FREQSYNC_PATTERN_OF_ZEROS, FREQSYNC_GET_MIDDLE, FREQSYNC_CORRELATE_PRS = 0, 1, 2
 
 
 class Subchannel(C.Structure):
@@ -58,9 +67,9 @@ class IO(C.Structure):
                 ("iq_format", C.c_int32), ("reserved", C.c_int32)]
 
 
-EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_select_subchannel",
+EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_select_subchannel",
            "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_cuda_stream", "dabb_kernel_launches",
-           "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
+           "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_find_index_ex", "dabb_coarse_estimate", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
            "dabb_rs_superframes", "dabb_dev_alloc", "dabb_dev_free", "dabb_memcpy_h2d", "dabb_memcpy_d2h"]
 
 
@@ -139,13 +148,14 @@ class DevBuf:
 
 class Context:
     def __init__(self, n_streams=1, device=0, fft_mode=FFT_EXACT, disable_coarse=True, keep_taps=False, n_subch_slots=1,
-                 max_subch_cu=0, ofdm_groups=0, coresident=False):
+                 max_subch_cu=0, ofdm_groups=0, coresident=False, fft_placement=0, freqsync_method=0):
         self.lib = load_library()
         cfg = Config()
         cfg.abi_version = self.lib.dabb_abi_version()
         cfg.device, cfg.n_streams, cfg.transmission_mode = device, n_streams, 1
         cfg.fft_mode, cfg.disable_coarse, cfg.keep_taps = fft_mode, int(disable_coarse), int(keep_taps)
         cfg.n_subch_slots, cfg.max_subch_cu, cfg.ofdm_groups = n_subch_slots, max_subch_cu, ofdm_groups
+        cfg.fft_placement, cfg.freqsync_method = int(fft_placement), int(freqsync_method)
         cfg.reserved[0] = 2 if coresident else 0      # 2: cap the OFDM kernel at 4 CTAs/SM so that lane-B CTAs fit beside it (experimental)
         h = C.c_void_p()
         rc = self.lib.dabb_create(C.byref(cfg), C.byref(h))
@@ -233,9 +243,18 @@ class Context:
         io.iq, io.iq_is_host, io.stride_samples, io.buf_len, io.buf_start = iq_ptr, 0, stride, buf_len, bs.ctypes.data
         self._ck(self.lib.dabb_process_async(self.h, C.byref(io)))
 
+    def set_options(self, disable_coarse=True, fft_placement=0, freqsync_method=0):
+        o = Options(); o.disable_coarse, o.fft_placement, o.freqsync_method = int(disable_coarse), int(fft_placement), int(freqsync_method)
+        self._ck(self.lib.dabb_set_options(self.h, C.byref(o)))
+
     def read_tap(self, what):
+        """0 softbits, 1 CIR, 2 constellation points (75 x 16 per stream), 3 null symbol (2656 samples, NCO applied)"""
         if what == 0:
             out = np.zeros((self.n_streams, 75, 3072), np.int8)
+        elif what == 2:
+            out = np.zeros((self.n_streams, 75, 16), np.complex64)
+        elif what == 3:
+            out = np.zeros((self.n_streams, 2656), np.complex64)
         else:
             out = np.zeros((self.n_streams, TU), np.float32)
         self._ck(self.lib.dabb_read_tap(self.h, what, _vp(out), C.c_size_t(out.nbytes)))
@@ -264,12 +283,23 @@ class Context:
                 b.free()
         return out[0] if len(out) == 1 else tuple(out)
 
-    def find_index(self, iq_frames, win_start, want_cir=False):
+    def coarse_estimate(self, iq_frames, prs_start, method=0):
+        """OFDMProcessor::processPRS on aligned phase reference symbols; method = FREQSYNC_*"""
+        iq = np.ascontiguousarray(iq_frames, np.complex64); n, stride = iq.shape
+        d_iq = self.dev(iq); d_ps = self.dev(np.ascontiguousarray(prs_start, np.int64)); d_out = self.dev(4 * n)
+        self._ck(self.lib.dabb_coarse_estimate(self.h, C.c_void_p(d_iq.ptr), C.c_int64(stride), C.c_void_p(d_ps.ptr), n, int(method), C.c_void_p(d_out.ptr)))
+        self.sync()
+        out = d_out.download(np.int32)
+        for b in (d_iq, d_ps, d_out):
+            b.free()
+        return out
+
+    def find_index(self, iq_frames, win_start, want_cir=False, placement=0):
         iq = np.ascontiguousarray(iq_frames, np.complex64); n, stride = iq.shape
         d_iq = self.dev(iq); d_ws = self.dev(np.ascontiguousarray(win_start, np.int64)); d_idx = self.dev(4 * n)
         d_cir = self.dev(4 * n * TU) if want_cir else None
-        self._ck(self.lib.dabb_find_index(self.h, C.c_void_p(d_iq.ptr), C.c_int64(stride), C.c_void_p(d_ws.ptr), n, C.c_void_p(d_idx.ptr),
-                                          C.c_void_p(d_cir.ptr) if d_cir else None))
+        self._ck(self.lib.dabb_find_index_ex(self.h, C.c_void_p(d_iq.ptr), C.c_int64(stride), C.c_void_p(d_ws.ptr), n, int(placement), C.c_void_p(d_idx.ptr),
+                                             C.c_void_p(d_cir.ptr) if d_cir else None))
         self.sync()
         idx = d_idx.download(np.int32)
         cir = d_cir.download(np.float32).reshape(n, TU) if want_cir else None

@@ -168,9 +168,9 @@ public:
 enum class FreqsyncMethod { GetMiddle = 0, CorrelatePRS = 1, PatternOfZeros = 2 };
 enum class FFTPlacementMethod { StrongestPeak, EarliestPeakWithBinning, ThresholdBeforePeak };
 struct RadioReceiverOptions {
-    FFTPlacementMethod fftPlacementMethod = FFTPlacementMethod::ThresholdBeforePeak;   /* the only placement implemented on the GPU */
+    FFTPlacementMethod fftPlacementMethod = FFTPlacementMethod::ThresholdBeforePeak;
     bool decodeTII = false;
-    bool disableCoarseCorrector = false;     /* the coarse corrector is not implemented yet: behaves as true */
+    bool disableCoarseCorrector = false;
     FreqsyncMethod freqsyncMethod = FreqsyncMethod::PatternOfZeros;
 };
 const char* fftPlacementMethodToString(FFTPlacementMethod fft_placement);

@@ -27,7 +27,7 @@ struct Prog : ProgrammeHandlerInterface {
 };
 struct Ctl : RadioControllerInterface {
     RadioReceiver* rx = nullptr; Prog* ph = nullptr; FILE* fibs; std::string dump; int select_at = 12, nfib = 0, ok = 0; bool sel = false, selok = false; std::atomic<bool> failed{false};
-    int syncs = 0, services = 0;
+    int syncs = 0, services = 0, cirs = 0, consts = 0, nulls = 0; size_t tapsz_ok = 1;
     void onSNR(float) override {} void onFrequencyCorrectorChange(int, int) override {} void onSyncChange(char s) override { if (s) syncs++; } void onSignalPresence(bool) override {}
     void onServiceDetected(uint32_t) override { services++; } void onNewEnsemble(uint16_t) override {} void onSetEnsembleLabel(DabLabel&) override {} void onDateTimeUpdate(const dab_date_time_t&) override {}
     void onFIBDecodeSuccess(bool o, const uint8_t* fib) override {
@@ -35,7 +35,9 @@ struct Ctl : RadioControllerInterface {
         fwrite(rec, 33, 1, fibs); nfib++; ok += o;
         if (!sel && nfib >= select_at) { auto l = rx->getServiceList(); if (!l.empty()) { sel = true; selok = rx->playSingleProgramme(*ph, dump, l.front()); } }
     }
-    void onNewImpulseResponse(std::vector<float>&&) override {} void onConstellationPoints(std::vector<DSPCOMPLEX>&&) override {} void onNewNullSymbol(std::vector<DSPCOMPLEX>&&) override {}
+    void onNewImpulseResponse(std::vector<float>&& v) override { cirs++; tapsz_ok &= v.size() == 2048; }
+    void onConstellationPoints(std::vector<DSPCOMPLEX>&& v) override { consts++; tapsz_ok &= v.size() == 1200; }   /* (L-1) K / 96 */
+    void onNewNullSymbol(std::vector<DSPCOMPLEX>&& v) override { nulls++; tapsz_ok &= v.size() == 2656; }
     void onTIIMeasurement(tii_measurement_t&&) override {} void onMessage(message_level_t, const std::string& a, const std::string& b) override { fprintf(stderr, "msg: %s %s\n", a.c_str(), b.c_str()); }
     void onInputFailure() override { failed = true; }
 };
@@ -45,7 +47,7 @@ int main(int argc, char** argv)
     FileInput in(argv[1]); Ctl ri; Prog ph; std::string pre = argv[2];
     ri.fibs = fopen((pre + ".fibs").c_str(), "wb"); ph.rs = fopen((pre + ".rs").c_str(), "w"); ri.dump = pre + ".msc"; ri.ph = &ph;
     if (argc > 3) ri.select_at = atoi(argv[3]);
-    RadioReceiverOptions rro; rro.disableCoarseCorrector = true;
+    RadioReceiverOptions rro; rro.disableCoarseCorrector = argc > 4 ? atoi(argv[4]) != 0 : true;    /* default like the parity harness (welle-cli -u) */
     {
         RadioReceiver rx(ri, in, rro);
         ri.rx = &rx;
@@ -54,6 +56,7 @@ int main(int argc, char** argv)
         rx.stop();
     }
     fclose(ri.fibs); fclose(ph.rs);
-    printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs);
+    printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d cirs=%d consts=%d nulls=%d tapsizes=%d\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs,
+           ri.cirs, ri.consts, ri.nulls, (int)ri.tapsz_ok);
     return 0;
 }

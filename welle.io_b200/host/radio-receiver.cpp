@@ -166,14 +166,27 @@ struct RadioReceiver::Impl {
     struct Slot { bool used = false; uint32_t sid = 0; ProgrammeHandlerInterface* handler = nullptr; FILE* dump = nullptr; int bitrate = 0; bool dabplus = false; };
     Slot slots[DABB_MAX_SUBCH];
     std::mutex slotMutex;
+    std::mutex ctxMutex;                    /* serialises dabb_set_options with dabb_process (one submitting thread per handle) */
     bool synced = false; float snr = 0; int snrCount = 0; long sampleCnt = 0;
+
+    /* the reference's enumerators (radio-receiver-options.h:35-64) -> DABB_PLACEMENT_* / DABB_FREQSYNC_* (0 = the reference's default) */
+    static int placementOf(FFTPlacementMethod m) { return m == FFTPlacementMethod::StrongestPeak ? DABB_PLACEMENT_STRONGEST_PEAK : m == FFTPlacementMethod::EarliestPeakWithBinning ? DABB_PLACEMENT_EARLIEST_PEAK_WITH_BINNING : DABB_PLACEMENT_THRESHOLD_BEFORE_PEAK; }
+    static int freqsyncOf(FreqsyncMethod m) { return m == FreqsyncMethod::GetMiddle ? DABB_FREQSYNC_GET_MIDDLE : m == FreqsyncMethod::CorrelatePRS ? DABB_FREQSYNC_CORRELATE_PRS : DABB_FREQSYNC_PATTERN_OF_ZEROS; }
+    void applyOptions(const RadioReceiverOptions& o)
+    {
+        dabb_options op; memset(&op, 0, sizeof op);
+        op.disable_coarse = o.disableCoarseCorrector ? 1 : 0; op.fft_placement = placementOf(o.fftPlacementMethod); op.freqsync_method = freqsyncOf(o.freqsyncMethod);
+        std::lock_guard<std::mutex> l(ctxMutex);
+        dabb_set_options(ctx, &op);
+    }
 
     Impl(RadioControllerInterface& r, InputInterface& i, RadioReceiverOptions o, int mode) : rci(r), input(i), rro(o), params(mode)
     {
         if (mode != 1) throw std::runtime_error("B200 backend: only transmission mode I is implemented");
         dabb_config cfg; memset(&cfg, 0, sizeof cfg);
         cfg.abi_version = DABB_ABI_VERSION; cfg.device = 0; cfg.n_streams = 1; cfg.transmission_mode = 1; cfg.fft_mode = DABB_FFT_EXACT;
-        cfg.disable_coarse = 1; cfg.keep_taps = 1; cfg.n_subch_slots = DABB_MAX_SUBCH; cfg.max_subch_cu = 416; cfg.ofdm_groups = 25;
+        cfg.disable_coarse = o.disableCoarseCorrector ? 1 : 0; cfg.fft_placement = placementOf(o.fftPlacementMethod); cfg.freqsync_method = freqsyncOf(o.freqsyncMethod);
+        cfg.keep_taps = 1; cfg.n_subch_slots = DABB_MAX_SUBCH; cfg.max_subch_cu = 416; cfg.ofdm_groups = 25;
         if (dabb_create(&cfg, &ctx) != DABB_OK) throw std::runtime_error(std::string("B200 backend: ") + dabb_last_error(nullptr));
     }
     ~Impl() { stopWorker(); closeSlots(); if (ctx) dabb_destroy(ctx); }
@@ -225,7 +238,8 @@ struct RadioReceiver::Impl {
             dabb_io io; memset(&io, 0, sizeof io);
             io.iq = reinterpret_cast<const float*>(buf.data()); io.iq_is_host = 1; io.stride_samples = (int64_t)buf.size(); io.buf_start = &buf_start; io.buf_len = have;
             io.results = &res; io.fibs = fibs; io.msc = msc.data(); io.msc_stride = 1152; io.sf = sf.data(); io.sf_stride = 5760;
-            if (dabb_process(ctx, &io) != DABB_OK) { rci.onMessage(message_level_t::Error, "B200 backend", dabb_last_error(ctx)); failed = true; break; }
+            int prc; { std::lock_guard<std::mutex> l(ctxMutex); prc = dabb_process(ctx, &io); }
+            if (prc != DABB_OK) { rci.onMessage(message_level_t::Error, "B200 backend", dabb_last_error(ctx)); failed = true; break; }
             pos = res.next_pos;
             if (res.status == DABB_FRAME_DECODED) {
                 if (!synced) { synced = true; rci.onSyncChange(true); }
@@ -255,6 +269,14 @@ struct RadioReceiver::Impl {
         {
             std::vector<float> cir(DABB_TU);
             if (dabb_read_tap(ctx, 1, cir.data(), cir.size() * sizeof(float)) == DABB_OK) rci.onNewImpulseResponse(std::move(cir));
+        }
+        {   /* OfdmDecoder hands over r1 of every 96th carrier once per frame (ofdm-decoder.cpp:119-125,216-218) */
+            std::vector<DSPCOMPLEX> pts((size_t)(DABB_L - 1) * DABB_K / 96);
+            if (dabb_read_tap(ctx, 2, pts.data(), pts.size() * sizeof(DSPCOMPLEX)) == DABB_OK) rci.onConstellationPoints(std::move(pts));
+        }
+        {   /* the null symbol that follows the frame, as read with the corrected oscillator (ofdm-processor.cpp:462-469) */
+            std::vector<DSPCOMPLEX> nul(DABB_TNULL);
+            if (dabb_read_tap(ctx, 3, nul.data(), nul.size() * sizeof(DSPCOMPLEX)) == DABB_OK) rci.onNewNullSymbol(std::move(nul));
         }
         for (int f = 0; f < 12; f++) {
             uint8_t bits[256];
@@ -346,7 +368,7 @@ void RadioReceiver::stop()
 {
     d->stopWorker(); d->closeSlots(); d->db.clear();
 }
-void RadioReceiver::setReceiverOptions(const RadioReceiverOptions rro) { d->rro = rro; }
+void RadioReceiver::setReceiverOptions(const RadioReceiverOptions rro) { d->rro = rro; d->applyOptions(rro); }
 bool RadioReceiver::playSingleProgramme(ProgrammeHandlerInterface& h, const std::string& dump, const Service& s) { return d->play(h, dump, s, true); }
 bool RadioReceiver::addServiceToDecode(ProgrammeHandlerInterface& h, const std::string& dump, const Service& s) { return d->play(h, dump, s, false); }
 bool RadioReceiver::removeServiceToDecode(const Service& s)
