@@ -47,6 +47,7 @@ struct SyncParams {
     int freqsync;       // DABB_FREQSYNC_*: 0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS
 };
 
+int ofdm_init_constants();     // per-device constants of ofdm.cu (call once after cudaSetDevice)
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
 void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st);

@@ -657,6 +657,16 @@ template <typename K> static void set_smem(K k, size_t bytes)
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+int ofdm_init_constants()
+{
+#if !defined(DABB_NO_F32X2)
+    const float2 mp = make_float2(-1.0f, 1.0f), pm = make_float2(1.0f, -1.0f);
+    return (cudaMemcpyToSymbol(g_sign_mp, &mp, sizeof mp) == cudaSuccess && cudaMemcpyToSymbol(g_sign_pm, &pm, sizeof pm) == cudaSuccess) ? 0 : -1;
+#else
+    return 0;
+#endif
+}
+
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)
 {
     const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
