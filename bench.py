@@ -155,6 +155,7 @@ def config_dict(a, groups):
     return {"workload": f"batch={a.batch} independent Mode-I ensembles per GPU, 1 transmission frame per stream per step: full chain sync+76xFFT+DQPSK -> FIC Viterbi+CRC -> 96 kbit/s EEP-3A DAB+ sub-channel (time de-interleave, Viterbi, RS(120,110)+Fire code) [BASELINE.json configs[3]/[4]]",
             "batch_frames_per_gpu": a.batch, "subchannel": "96 kbit/s EEP 3-A, 72 CU, DAB+", "snr_db": a.snr, "fft_mode": "exact(KISS-bit-identical)" if a.fft_mode == 0 else "fma",
             "parallelism": f"streams sharded over {a.gpus} GPU(s), no data-path collective", "l2_policy": "inputs (12.9 GB/step at batch 8192) far exceed the 126 MB L2; no flush needed",
+            "carrier_offset": "0 Hz (headline): fine corrector stays 0 and the oscillator multiply is skipped; roofline.oscillator_active repeats the run with an offset",
             "ofdm_groups": groups}
 
 
@@ -183,6 +184,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--coresident", action="store_true")
+    ap.add_argument("--cfo-hz", type=float, default=50.0, help="carrier offset of the secondary 'oscillator active' measurement (0 = skip); must keep the 5-frame ring periodic (multiples of 1/0.48 s)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)
@@ -408,6 +410,55 @@ def main():
             ctx_u.close(); del hu
         except Exception as e:  # noqa
             e2e["u8_input"] = {"error": repr(e)}
+
+    # ---- secondary measurement: the same streams with a carrier offset, so that the fine corrector is non-zero and every sample goes
+    # through the oscillator table (the zero-offset streams of the headline run leave the oscillator at (1, 0), which the kernels skip)
+    with_nco = None
+    if a.cfo_hz and world == 1:
+        try:
+            ctx.close()
+            ring_len = RING_FRAMES * TF
+            nidx = torch.arange(BUF_LEN, device=dev, dtype=torch.float64) % ring_len
+            ph = 2 * np.pi * a.cfo_hz * nidx / 2048000.0
+            rc, rs = torch.cos(ph).to(torch.float32), torch.sin(ph).to(torch.float32)
+            del nidx, ph
+            for s0 in range(0, S, 64):
+                blk = buf[s0:s0 + 64]
+                re = blk[..., 0] * rc - blk[..., 1] * rs
+                im = blk[..., 0] * rs + blk[..., 1] * rc
+                blk[..., 0] = re; blk[..., 1] = im
+                del re, im
+            torch.cuda.synchronize()
+            ctx2 = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+            ctx2.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
+            ext2 = torch.cuda.ExternalStream(ctx2.cuda_stream(), device=dev)
+            c2 = 0
+            for _ in range(a.warmup):
+                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+            ctx2.sync()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(ext2)
+            for _ in range(a.steps):
+                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+            g1.record(ext2); torch.cuda.synchronize()
+            ms2 = g0.elapsed_time(g1)
+            ctx2.profile(True)
+            for _ in range(a.steps):
+                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+            ctx2.sync(); ctx2.profile(False)
+            pr2 = ctx2.profile_read()
+            o2 = ctx2.process(buf, BUF_LEN, buf_start_for(c2), BUF_LEN, msc_stride=3 * BITRATE); c2 += 1
+            r2 = o2["results"]
+            k2 = pr2["ofdm_demod_kernel"]["ms"] / pr2["ofdm_demod_kernel"]["n"]
+            with_nco = {"cfo_hz": a.cfo_hz, "value": S * a.steps / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / a.steps, "ofdm_ms_per_launch": k2,
+                        "ofdm_frac": S * OFDM_BYTES_PER_FRAME / (k2 * 1e-3) / 1e9 / hbm_peak,
+                        "frames_decoded": int((r2["status"] == 0).sum()), "fib_crc_ok": int(sum(bin(int(m)).count("1") for m in r2["fib_crc_mask"])),
+                        "fine_corr_median_hz": float(np.median(r2["fine_corr"])),
+                        "note": "same workload with a carrier offset: the numerically controlled oscillator (2 048 000-entry table lookup + complex multiply per sample) is active for every stream"}
+            ctx2.close()
+        except Exception as e:  # noqa
+            with_nco = {"error": repr(e)}
+    roofline["oscillator_active"] = with_nco
 
     if rank == 0:
         line = {"metric": "dab_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
