@@ -86,6 +86,11 @@ int dabb_abi_version(void);
  * logical sample position `pos` with zeroed correctors, cleared FIC counter, de-interleaver and superframe window */
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first_stream, int32_t count, int64_t pos);
 int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt);
+/* introspection.  DABB_INFO_OSC_MODE: 1 = the oscillator of OFDMProcessor::getSamples (ofdm-processor.cpp:92-94,211-214) is
+ * evaluated on the fly (verified bit-identical to the 2 048 000-entry table for every index at dabb_create), 0 = table lookups;
+ * DABB_INFO_OSC_EXCEPTIONS: how many indices needed a patched value for that (3 on IEEE hardware: the quarter turns) */
+enum { DABB_INFO_OSC_MODE = 0, DABB_INFO_OSC_EXCEPTIONS = 1 };
+int dabb_get_info(dabb_ctx* ctx, int32_t what, int64_t* out);
 
 /* replaces: MscHandler::addSubchannel / removeSubchannel (backend/msc-handler.cpp:61-127) + DabAudio ctor
  * (backend/dab-audio.cpp:46-85).  slot in [0, DABB_MAX_SUBCH).  Protection exactly as ProtectionSettings

@@ -194,41 +194,29 @@ def test_two_subchannel_slots_and_remove(oracle):
     assert hits and np.array_equal(g0, lf[hits[0] * 288: hits[0] * 288 + len(g0)])
 
 
+LOCKING_STREAMS = {0: [(0x51, 2000.0), (4, 1000.0), (8, -1000.0)], 1: [(3, -3000.0), (4, 1000.0), (7, 5000.0)], 2: [(4, 1000.0), (8, -1000.0)]}
+
+
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_coarse_methods_closed_loop(oracle, method):
-    """all three FreqsyncMethods in the closed loop on frequency-shifted streams: coarse trajectory and FIB CRC masks like the
-    oracle (which is pinned to the reference RadioReceiver with the same option, tests/test_oracle_vs_ref.py).
-    The fine corrector may differ by 1 Hz (float summation order of the guard-interval correlation); while the
-    loop has not locked, the trajectory is chaotic (the reference's estimators jump by tens of kHz on a mistuned signal), so a
-    1 Hz difference is amplified: the comparison of a stream stops at the first frame whose fine corrector differs, and every
-    stream that locks in the oracle must lock identically."""
+    """all three FreqsyncMethods in the closed loop on frequency-shifted streams on which the estimator locks (most offsets do not
+    lock with PatternOfZeros / CorrelatePRS - in the reference either: their arg() terms are truncated to integers, see
+    oracle/dab_oracle.c): start index, coarse corrector and FIB CRC mask of every frame like the oracle, which is pinned to the
+    reference RadioReceiver with the same option (tests/test_oracle_vs_ref.py); fine corrector within 1 Hz."""
     pkg = load_pkg()
-    sigs = [dabtx.freq_shift(dabtx.DabTx(seed=0x51).frames(12), 2000.0), dabtx.freq_shift(dabtx.DabTx(seed=3).frames(12), -3000.0),
-            dabtx.freq_shift(dabtx.DabTx(seed=4).frames(12), 1000.0)]
+    sigs = [dabtx.freq_shift(dabtx.DabTx(seed=sd).frames(12), hz) for sd, hz in LOCKING_STREAMS[method]]
     res = run_gpu(pkg, sigs, disable_coarse=False, freqsync_method=method)
-    locked = 0
     for i, sig in enumerate(sigs):
         orc = oracle.rx_run(sig, disable_coarse=False, freqsync_method=method)
         n = min(len(res[i]["info"]), orc["frames"])
         assert n >= 8
         crc_o = [int(sum(int(o) << k for k, o in enumerate(orc["fibs"][12 * f: 12 * f + 12, 0]))) for f in range(n)]
-        same_fine = [res[i]["info"][f][1] == orc["info"][f]["fine"] for f in range(n)]
-        m = same_fine.index(False) + 1 if False in same_fine else n       # the frame where fine first differs still saw identical input
-        assert m >= 4, (i, m, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
-        if not all(c == 0xFFF for c in crc_o[-4:]):
-            # never locks (CorrelatePRS on the +2 kHz stream wanders for the whole run): the arg()-based estimators truncate
-            # atan2f results to integers, and CUDA's atan2f is not glibc's; on the near-empty spectra of a stream mistuned by
-            # tens of kHz one such truncation can flip.  At least six identical frames of that walk are required.
-            same_c = [res[i]["info"][f][2] == orc["info"][f]["coarse"] for f in range(m)]
-            m = min(m, same_c.index(False)) if False in same_c else m
-            assert m >= 6, (i, m, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
-        assert [x[2] for x in res[i]["info"][:m]] == [x["coarse"] for x in orc["info"][:m]], (i, res[i]["info"][:n], [(x["fine"], x["coarse"]) for x in orc["info"][:n]])
-        assert [x[0] for x in res[i]["info"][:m]] == [x["start_index"] for x in orc["info"][:m]]
-        assert res[i]["crc"][:m] == crc_o[:m]
-        if all(c == 0xFFF for c in crc_o[-4:]):           # the oracle locked: so must the GPU, on the same corrector
-            locked += 1
-            assert all(c == 0xFFF for c in res[i]["crc"][n - 4: n]) and res[i]["info"][n - 1][2] == orc["info"][n - 1]["coarse"], i
-    assert locked >= 1
+        assert all(c == 0xFFF for c in crc_o[-4:]) and orc["info"][n - 1]["coarse"] == int(LOCKING_STREAMS[method][i][1])
+        msg = (i, res[i]["info"][:n], [(x["start_index"], x["fine"], x["coarse"]) for x in orc["info"][:n]])
+        assert [x[2] for x in res[i]["info"][:n]] == [x["coarse"] for x in orc["info"][:n]], msg
+        assert [x[0] for x in res[i]["info"][:n]] == [x["start_index"] for x in orc["info"][:n]], msg
+        assert all(abs(a[1] - b["fine"]) <= 1 for a, b in zip(res[i]["info"][:n], orc["info"][:n])), msg
+        assert res[i]["crc"][:n] == crc_o, msg
 
 
 @pytest.mark.parametrize("placement", [1, 2])

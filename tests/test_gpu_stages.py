@@ -238,3 +238,9 @@ def test_rs_superframes_au_layouts(ctx, oracle, bitrate):
         assert info[i, 2] == ev[0]["sync"] == 1, i
         assert (info[i, 3] & 0xFF) == ev[0]["au_ok"] and (info[i, 3] >> 8) == ev[0]["num_aus"], (i, info[i], ev[0])
         assert np.array_equal(out[i], sfs[i])
+
+
+def test_oscillator_on_the_fly_is_verified(ctx):
+    """dabb_create compares the on-the-fly oscillator (three double-precision factors) with the reference's 2 048 000-entry float table
+    for EVERY index and only then switches the table lookups off; on IEEE hardware exactly the three quarter-turn entries need a patch"""
+    assert ctx.get_info(0) == 1 and ctx.get_info(1) == 3

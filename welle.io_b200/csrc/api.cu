@@ -52,7 +52,7 @@ struct dabb_ctx {
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
-    std::string err; int64_t launches = 0;
+    std::string err; int64_t launches = 0; int osc_mismatches = -1;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
@@ -462,6 +462,27 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.fic_map = fm;
     ctx->dev.gf_exp = ge; ctx->dev.gf_log = gl; ctx->dev.prbs = pb;
     {
+        // on-the-fly oscillator: upload the factors, compare against the table for every index, adopt it when the (at most 8)
+        // differing entries can be patched cheaply; DABB_OSC_TABLE=1 in the environment forces the table lookups (A/B measurements)
+        double2 *hi, *mid, *lo;
+        if ((rc = dalloc(ctx, &hi, 2000)) || (rc = dalloc(ctx, &mid, 32)) || (rc = dalloc(ctx, &lo, 32))) return fail(rc);
+        std::vector<double2> h_hi(2000), h_mid(32), h_lo(32);
+        build_osc_factors(h_hi.data(), h_mid.data(), h_lo.data());
+        cudaMemcpyAsync(hi, h_hi.data(), sizeof(double2) * 2000, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(mid, h_mid.data(), sizeof(double2) * 32, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(lo, h_lo.data(), sizeof(double2) * 32, cudaMemcpyHostToDevice, ctx->stream);
+        ctx->dev.osc_hi = hi; ctx->dev.osc_mid = mid; ctx->dev.osc_lo = lo; ctx->dev.osc_mode = 0; ctx->dev.osc_nexc = 0;
+        int32_t eidx[8]; float2 eval[8];
+        const int nbad = launch_osc_verify(ctx->dev, eidx, eval, ctx->stream);
+        bool ok = nbad >= 0 && nbad <= 8;
+        for (int k = 0; ok && k < nbad; k++) ok = (eidx[k] & 1023) == 0;
+        ctx->osc_mismatches = nbad;
+        if (ok && !getenv("DABB_OSC_TABLE")) {
+            ctx->dev.osc_mode = 1; ctx->dev.osc_nexc = nbad;
+            for (int k = 0; k < nbad; k++) { ctx->dev.osc_exc_idx[k] = eidx[k]; ctx->dev.osc_exc_val[k] = eval[k]; }
+        }
+    }
+    {
         std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, 768, w);
         if ((rc = dalloc(ctx, &ctx->d_fic_prbs_words, w.size()))) return fail(rc);
         cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
@@ -859,6 +880,16 @@ int dabb_coarse_estimate(dabb_ctx* ctx, const float* iq, int64_t stride, const i
     sync_all(ctx);
     launch_coarse(ctx->dev, reinterpret_cast<const float2*>(iq), stride, prs_start, n, method, offset_out, ctx->stream);
     return check_launch(ctx, "coarse_kernel");
+}
+
+int dabb_get_info(dabb_ctx* ctx, int32_t what, int64_t* out)
+{
+    if (!ctx || !out) return DABB_E_ARG;
+    switch (what) {
+        case DABB_INFO_OSC_MODE: *out = ctx->dev.osc_mode; return DABB_OK;
+        case DABB_INFO_OSC_EXCEPTIONS: *out = ctx->osc_mismatches; return DABB_OK;
+        default: return DABB_E_ARG;
+    }
 }
 
 int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt)

@@ -53,9 +53,28 @@ __device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
     return n;
 }
 __device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
-__device__ __forceinline__ float2 mix_sample(float2 v, const float2* __restrict__ osc, int32_t lp)
+// oscillator sample m without the table: three factors in double (two complex products with explicitly rounded operations,
+// so that every kernel - and the start-up verification against the table - executes the identical arithmetic), rounded to float
+__device__ __forceinline__ float2 osc_onthefly(const DevTables& tb, int32_t m)
 {
-    return cmul_<true>(v, __ldg(osc + lp));   // std::complex product, separately rounded
+    const double2 h = __ldg(tb.osc_hi + (m >> 10)), md = __ldg(tb.osc_mid + ((m >> 5) & 31)), l = __ldg(tb.osc_lo + (m & 31));
+    const double zr = __fma_rn(h.x, md.x, -__dmul_rn(h.y, md.y)), zi = __fma_rn(h.x, md.y, __dmul_rn(h.y, md.x));
+    const double wr = __fma_rn(zr, l.x, -__dmul_rn(zi, l.y)), wi = __fma_rn(zr, l.y, __dmul_rn(zi, l.x));
+    return make_float2(__double2float_rn(wr), __double2float_rn(wi));
+}
+__device__ __forceinline__ float2 osc_value(const DevTables& tb, int32_t m)
+{
+    if (tb.osc_mode == 0) return __ldg(tb.osc + m);          // kernel-uniform
+    float2 o = osc_onthefly(tb, m);
+    if ((m & 1023) == 0 && tb.osc_nexc) {
+#pragma unroll 1
+        for (int e = 0; e < tb.osc_nexc; e++) if (m == tb.osc_exc_idx[e]) o = tb.osc_exc_val[e];
+    }
+    return o;
+}
+__device__ __forceinline__ float2 mix_sample(float2 v, const DevTables& tb, int32_t lp)
+{
+    return cmul_<true>(v, osc_value(tb, lp));   // std::complex product, separately rounded
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red, int t)
@@ -91,7 +110,7 @@ __device__ __forceinline__ constexpr int xc_of(int c) { return ((c & 1) << 3) | 
 // FFT of the 2048 samples at src[w0 .. w0+2048) -> v[a+4b] = X[t + 128a + 512b].  Contains two __syncthreads.
 template <bool EXACT, bool INV>
 __device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ src, int64_t w0, float2 v[16], OfdmSmem& sm, int t, const XIdx& xi,
-                                                    const float2* __restrict__ osc, const Nco& nco, const float2* __restrict__ tw_c5)
+                                                    const DevTables& tb, const Nco& nco, const float2* __restrict__ tw_c5)
 {
     // pass A: two blocks n0 = t, t+128; loads are lane-consecutive for each c
     float2 x[16];
@@ -104,8 +123,8 @@ __device__ __forceinline__ void fft2048_from_global(const float2* __restrict__ s
         int32_t lp = mod_rate64((int64_t)nco.lp0 - (w0 + t) * (int64_t)nco.ph);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            x[c] = mix_sample(x[c], osc, lp);
-            x[8 + c] = mix_sample(x[8 + c], osc, sub_mod(lp, nco.d128));
+            x[c] = mix_sample(x[c], tb, lp);
+            x[8 + c] = mix_sample(x[8 + c], tb, sub_mod(lp, nco.d128));
             lp = sub_mod(lp, nco.d256);
         }
     }
@@ -170,7 +189,7 @@ template <bool DIRECT> __device__ __forceinline__ float2 ld_in(const float2* in,
 
 template <bool EXACT, bool DIRECT>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
-                                                  const float2* __restrict__ tw_c5, const float2* __restrict__ osc, const Nco& nco)
+                                                  const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco)
 {
     float2 x[16];
 #pragma unroll
@@ -181,8 +200,8 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
         int32_t lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            x[c] = mix_sample(x[c], osc, lp);
-            x[8 + c] = mix_sample(x[8 + c], osc, sub_mod(lp, nco.d128));
+            x[c] = mix_sample(x[c], tb, lp);
+            x[8 + c] = mix_sample(x[8 + c], tb, sub_mod(lp, nco.d128));
             lp = sub_mod(lp, nco.d256);
         }
     }
@@ -264,7 +283,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         if (!DIRECT) { mbar_wait(&sm.full, parity); parity ^= 1; }
         const float2* in = DIRECT ? (src + s0) : (sm.inbuf + shift);
         float2 v[16];
-        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb.osc, nco);
+        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco);
         if (l >= l_first) {
             // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
             // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = t + 128 r).
@@ -275,7 +294,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 const int i = t + 128 * r;
                 if (i < TG) {
                     float2 a = ld_in<DIRECT>(in, TU + i), b = ld_in<DIRECT>(in, i);
-                    if (nco.mix) { a = mix_sample(a, tb.osc, lpa); b = mix_sample(b, tb.osc, lpb); }
+                    if (nco.mix) { a = mix_sample(a, tb, lpa); b = mix_sample(b, tb, lpb); }
                     fc.x += a.x * b.x + a.y * b.y;
                     fc.y += a.y * b.x - a.x * b.y;
                 }
@@ -374,7 +393,7 @@ __device__ __forceinline__ void coarse_estimate(const DevTables& tb, SyncSmem& s
     if (t < TwLayout::C4) sm.o.tw[t] = tb.tw_fwd[t];
     __syncthreads();
     // the PRS useful part starts `off` samples into the window; its samples continue the NCO phase sequence
-    fft2048_from_global<EXACT, false>(src, off, v, sm.o, t, xi, tb.osc, nco, tb.tw_fwd + TwLayout::C5);
+    fft2048_from_global<EXACT, false>(src, off, v, sm.o, t, xi, tb, nco, tb.tw_fwd + TwLayout::C5);
     if (freqsync == 1) {
         // ---- GetMiddle (:617-644), including its `sum = oldMax` assignment: moving sum of |X| over K carriers
 #pragma unroll
@@ -478,7 +497,7 @@ find_index_kernel(DevTables tb, SyncParams p)
     const Nco nco = make_nco((NCO && p.nco) ? p.nco[2 * f] : 0, (NCO && p.nco) ? p.nco[2 * f + 1] : 0);
     const XIdx xi = make_xidx(t);
     float2 v[16];
-    fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb.osc, nco, tb.tw_fwd + TwLayout::C5);
+    fft2048_from_global<EXACT, false>(src, 0, v, sm.o, t, xi, tb, nco, tb.tw_fwd + TwLayout::C5);
     // res = X * conj(ref), written in natural order into the exchange buffer (free between the two transforms)
     float2* scratch = sm.o.xbuf;
     __syncthreads();             // pass C of the forward transform has read xbuf
@@ -655,6 +674,36 @@ template <typename K> static void set_smem(K k, size_t bytes)
 {
     // every template instantiation is its own function: set the attribute per launch (it is a cheap host-side call)
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+namespace {
+__global__ void osc_verify_kernel(DevTables tb, int32_t* count, int32_t* exc_idx, float2* exc_val)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= INPUT_RATE) return;
+    const float2 a = osc_onthefly(tb, m), b = tb.osc[m];
+    if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y)) {
+        const int k = atomicAdd(count, 1);
+        if (k < 8) { exc_idx[k] = m; exc_val[k] = b; }
+    }
+}
+} // namespace
+
+int launch_osc_verify(const DevTables& tb, int32_t* exc_idx, float2* exc_val, cudaStream_t st)
+{
+    int32_t* d = nullptr; float2* dv = nullptr;
+    if (cudaMalloc((void**)&d, 16 * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void**)&dv, 8 * sizeof(float2)) != cudaSuccess) return -1;
+    cudaMemsetAsync(d, 0, 16 * sizeof(int32_t), st);
+    osc_verify_kernel<<<(INPUT_RATE + 255) / 256, 256, 0, st>>>(tb, d, d + 1, dv);
+    int32_t h[16];
+    int rc = -1;
+    if (cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaMemcpyAsync(exc_val, dv, 8 * sizeof(float2), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+        rc = h[0];
+        for (int k = 0; k < 8; k++) exc_idx[k] = h[1 + k];
+    }
+    cudaFree(d); cudaFree(dv);
+    return rc;
 }
 
 int ofdm_init_constants()

@@ -67,7 +67,7 @@ class IO(C.Structure):
                 ("iq_format", C.c_int32), ("reserved", C.c_int32)]
 
 
-EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_select_subchannel",
+EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_get_info", "dabb_select_subchannel",
            "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_cuda_stream", "dabb_kernel_launches",
            "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_find_index_ex", "dabb_coarse_estimate", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
            "dabb_rs_superframes", "dabb_dev_alloc", "dabb_dev_free", "dabb_memcpy_h2d", "dabb_memcpy_d2h"]
@@ -242,6 +242,11 @@ class Context:
         io = IO()
         io.iq, io.iq_is_host, io.stride_samples, io.buf_len, io.buf_start = iq_ptr, 0, stride, buf_len, bs.ctypes.data
         self._ck(self.lib.dabb_process_async(self.h, C.byref(io)))
+
+    def get_info(self, what):
+        v = C.c_int64()
+        self._ck(self.lib.dabb_get_info(self.h, int(what), C.byref(v)))
+        return v.value
 
     def set_options(self, disable_coarse=True, fft_placement=0, freqsync_method=0):
         o = Options(); o.disable_coarse, o.fft_placement, o.freqsync_method = int(disable_coarse), int(fft_placement), int(freqsync_method)
