@@ -464,14 +464,13 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     {
         // on-the-fly oscillator: upload the factors, compare against the table for every index, adopt it when the (at most 8)
         // differing entries can be patched cheaply; DABB_OSC_TABLE=1 in the environment forces the table lookups (A/B measurements)
-        double2 *hi, *mid, *lo;
-        if ((rc = dalloc(ctx, &hi, 2000)) || (rc = dalloc(ctx, &mid, 32)) || (rc = dalloc(ctx, &lo, 32))) return fail(rc);
-        std::vector<double2> h_hi(2000), h_mid(32), h_lo(32);
-        build_osc_factors(h_hi.data(), h_mid.data(), h_lo.data());
+        double2* hi;
+        if ((rc = dalloc(ctx, &hi, 2000))) return fail(rc);
+        std::vector<double2> h_hi(2000);
+        build_osc_factors(h_hi.data(), &ctx->dev.osc_theta);
         cudaMemcpyAsync(hi, h_hi.data(), sizeof(double2) * 2000, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(mid, h_mid.data(), sizeof(double2) * 32, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(lo, h_lo.data(), sizeof(double2) * 32, cudaMemcpyHostToDevice, ctx->stream);
-        ctx->dev.osc_hi = hi; ctx->dev.osc_mid = mid; ctx->dev.osc_lo = lo; ctx->dev.osc_mode = 0; ctx->dev.osc_nexc = 0;
+        cudaStreamSynchronize(ctx->stream);
+        ctx->dev.osc_hi = hi; ctx->dev.osc_mode = 0; ctx->dev.osc_nexc = 0;
         int32_t eidx[8]; float2 eval[8];
         const int nbad = launch_osc_verify(ctx->dev, eidx, eval, ctx->stream);
         bool ok = nbad >= 0 && nbad <= 8;

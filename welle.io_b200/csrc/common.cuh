@@ -14,11 +14,11 @@ struct DevTables {
     const int16_t* invperm;    // [2048] bin -> logical carrier index 0..1535, -1 for unused bins (freq-interleaver.cpp:35-91)
     const float2* prs_ref;     // [2048] PhaseReference::refTable (phasereference.cpp:45-51)
     const float2* osc;         // [2 048 000] oscillator table (ofdm-processor.cpp:92-94)
-    // the same values computed on the fly (osc_mode = 1): osc[m] == float(H[m >> 10] * M[(m >> 5) & 31] * L[m & 31]) in double,
-    // verified for all 2 048 000 m at context creation; the few m where it is not (multiples of a quarter turn) are listed
+    // the same values computed on the fly (osc_mode = 1): osc[m] == float(H[m >> 10] * exp(j theta (m & 1023))) in double, the small
+    // rotation from its Taylor polynomial; verified for all 2 048 000 m at context creation; the few m where it is not
+    // (multiples of a quarter turn, where the reference's own double angle is off by an ulp) are listed
     const double2* osc_hi;     // [2000] exp(j 2 pi 1024 a / 2 048 000), correctly rounded doubles
-    const double2* osc_mid;    // [32]   exp(j 2 pi 32 b / 2 048 000)
-    const double2* osc_lo;     // [32]   exp(j 2 pi c / 2 048 000)
+    double osc_theta;          // 2 pi / 2 048 000, correctly rounded
     int32_t osc_mode;          // 0: table lookups (a scattered 8-byte gather per sample), 1: on the fly
     int32_t osc_nexc; int32_t osc_exc_idx[8]; float2 osc_exc_val[8];     // every exception index has (m & 1023) == 0
     const uint8_t* prbs;       // [9216+] energy-dispersal PRBS bits (fic-handler.cpp:62-71)
@@ -71,7 +71,7 @@ struct HostTables {
 };
 void build_host_tables(HostTables& t);
 void build_osc_table(float2* osc /* INPUT_RATE entries */);
-void build_osc_factors(double2* hi /* 2000 */, double2* mid /* 32 */, double2* lo /* 32 */);
+void build_osc_factors(double2* hi /* 2000 */, double* theta);
 // compares the on-the-fly oscillator with the table for every index; returns the number of differing entries (first 8 in exc_*)
 int launch_osc_verify(const DevTables& tb, int32_t* exc_idx, float2* exc_val, cudaStream_t st);
 

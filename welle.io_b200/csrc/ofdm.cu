@@ -53,13 +53,19 @@ __device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
     return n;
 }
 __device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
-// oscillator sample m without the table: three factors in double (two complex products with explicitly rounded operations,
-// so that every kernel - and the start-up verification against the table - executes the identical arithmetic), rounded to float
+// oscillator sample m without the table: exp(j 2 pi m / 2 048 000) = H[m >> 10] * exp(j theta r), r = m & 1023 < 1024, in double:
+// the small rotation from its Taylor polynomial (theta r < 3.2e-3: the next terms are below 1e-18), one complex product, then
+// rounded to float.  Every operation is explicitly rounded so that every kernel - and the start-up verification against the
+// reference's table - executes the identical arithmetic.  One 16-byte load that is the same for (nearly) all lanes of a warp
+// replaces a scattered 8-byte gather per lane.
 __device__ __forceinline__ float2 osc_onthefly(const DevTables& tb, int32_t m)
 {
-    const double2 h = __ldg(tb.osc_hi + (m >> 10)), md = __ldg(tb.osc_mid + ((m >> 5) & 31)), l = __ldg(tb.osc_lo + (m & 31));
-    const double zr = __fma_rn(h.x, md.x, -__dmul_rn(h.y, md.y)), zi = __fma_rn(h.x, md.y, __dmul_rn(h.y, md.x));
-    const double wr = __fma_rn(zr, l.x, -__dmul_rn(zi, l.y)), wi = __fma_rn(zr, l.y, __dmul_rn(zi, l.x));
+    const double2 h = __ldg(tb.osc_hi + (m >> 10));
+    const double r = __dsub_rn(__hiloint2double(0x43300000, m & 1023), 4503599627370496.0);     // (double)(m & 1023) without a conversion instruction
+    const double y = __dmul_rn(r, tb.osc_theta), y2 = __dmul_rn(y, y);
+    const double c = __fma_rn(y2, __fma_rn(y2, 1.0 / 24, -0.5), 1.0);
+    const double sn = __dmul_rn(y, __fma_rn(y2, __fma_rn(y2, 1.0 / 120, -1.0 / 6), 1.0));
+    const double wr = __fma_rn(h.x, c, -__dmul_rn(h.y, sn)), wi = __fma_rn(h.x, sn, __dmul_rn(h.y, c));
     return make_float2(__double2float_rn(wr), __double2float_rn(wi));
 }
 __device__ __forceinline__ float2 osc_value(const DevTables& tb, int32_t m)
@@ -191,24 +197,22 @@ template <bool EXACT, bool DIRECT>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
                                                   const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco)
 {
-    float2 x[16];
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-#pragma unroll
-        for (int c = 0; c < 8; c++) x[8 * h + c] = ld_in<DIRECT>(in, t + 128 * h + 256 * c);
-    if (nco.mix) {
-        int32_t lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            x[c] = mix_sample(x[c], tb, lp);
-            x[8 + c] = mix_sample(x[8 + c], tb, sub_mod(lp, nco.d128));
-            lp = sub_mod(lp, nco.d256);
-        }
-    }
+    // one 8-point block at a time (load, oscillator, radix-2 + radix-4, store): keeps 8 instead of 16 inputs live while the
+    // oscillator's double-precision temporaries are
+    int32_t lp = 0;
+    if (nco.mix) lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
+        float2 x[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[c] = ld_in<DIRECT>(in, t + 128 * h + 256 * c);
+        if (nco.mix) {
+            int32_t l = h ? sub_mod(lp, nco.d128) : lp;
+#pragma unroll
+            for (int c = 0; c < 8; c++) { x[c] = mix_sample(x[c], tb, l); l = sub_mod(l, nco.d256); }
+        }
         float2 y[8];
-        passA_block<EXACT, false>(x + 8 * h, y, sm.tw);
+        passA_block<EXACT, false>(x, y, sm.tw);
 #pragma unroll
         for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
     }

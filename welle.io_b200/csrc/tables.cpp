@@ -108,13 +108,13 @@ void build_osc_table(float2* osc)
     }
 }
 
-// factors of the on-the-fly oscillator: correctly rounded doubles of exp(j 2 pi k / 2 048 000) (80-bit evaluation, then rounded)
-void build_osc_factors(double2* hi, double2* mid, double2* lo)
+// factors of the on-the-fly oscillator: correctly rounded doubles of exp(j 2 pi 1024 a / 2 048 000) and of the angle step
+// (80-bit evaluation, then rounded)
+void build_osc_factors(double2* hi, double* theta)
 {
     const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
     for (int a = 0; a < 2000; a++) { const long double x = two_pi * (long double)(a * 1024) / INPUT_RATE; hi[a].x = (double)cosl(x); hi[a].y = (double)sinl(x); }
-    for (int b = 0; b < 32; b++) { const long double x = two_pi * (long double)(b * 32) / INPUT_RATE; mid[b].x = (double)cosl(x); mid[b].y = (double)sinl(x); }
-    for (int c = 0; c < 32; c++) { const long double x = two_pi * (long double)c / INPUT_RATE; lo[c].x = (double)cosl(x); lo[c].y = (double)sinl(x); }
+    *theta = (double)(two_pi / INPUT_RATE);
 }
 
 // UEP profiles exactly as the reference applies them (uep-protection.cpp:38-118): bitrate, level, L1..L4, PI1..PI4.
