@@ -87,9 +87,10 @@ int dabb_abi_version(void);
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first_stream, int32_t count, int64_t pos);
 int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt);
 /* introspection.  DABB_INFO_OSC_MODE: 1 = the oscillator of OFDMProcessor::getSamples (ofdm-processor.cpp:92-94,211-214) is
- * evaluated on the fly (verified bit-identical to the 2 048 000-entry table for every index at dabb_create), 0 = table lookups;
- * DABB_INFO_OSC_EXCEPTIONS: how many indices needed a patched value for that (3 on IEEE hardware: the quarter turns) */
-enum { DABB_INFO_OSC_MODE = 0, DABB_INFO_OSC_EXCEPTIONS = 1 };
+ * evaluated on the fly, which dabb_create allows only after comparing it on the device with the 2 048 000-entry table for every
+ * index (DABB_INFO_OSC_MISMATCHES must be 0), 0 = table lookups; DABB_INFO_OSC_PATCHED: how many of the 2000 double-precision
+ * factors had to be replaced by the table's own value for that (3: the quarter turns) */
+enum { DABB_INFO_OSC_MODE = 0, DABB_INFO_OSC_MISMATCHES = 1, DABB_INFO_OSC_PATCHED = 2 };
 int dabb_get_info(dabb_ctx* ctx, int32_t what, int64_t* out);
 
 /* replaces: MscHandler::addSubchannel / removeSubchannel (backend/msc-handler.cpp:61-127) + DabAudio ctor

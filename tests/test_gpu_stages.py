@@ -242,5 +242,5 @@ def test_rs_superframes_au_layouts(ctx, oracle, bitrate):
 
 def test_oscillator_on_the_fly_is_verified(ctx):
     """dabb_create compares the on-the-fly oscillator (three double-precision factors) with the reference's 2 048 000-entry float table
-    for EVERY index and only then switches the table lookups off; on IEEE hardware exactly the three quarter-turn entries need a patch"""
-    assert ctx.get_info(0) == 1 and ctx.get_info(1) == 3
+    for EVERY index and only then switches the table lookups off; exactly the three quarter-turn factors take the table's own value"""
+    assert ctx.get_info(0) == 1 and ctx.get_info(1) == 0 and ctx.get_info(2) == 3

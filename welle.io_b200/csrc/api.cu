@@ -52,7 +52,7 @@ struct dabb_ctx {
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
     int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
-    std::string err; int64_t launches = 0; int osc_mismatches = -1;
+    std::string err; int64_t launches = 0; int osc_mismatches = -1; int osc_patched = 0; std::vector<float2> h_osc;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
@@ -446,9 +446,9 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
         return fail(rc);
     {
-        std::vector<float2> h_osc(INPUT_RATE);
-        build_osc_table(h_osc.data());
-        cudaMemcpyAsync(osc, h_osc.data(), sizeof(float2) * INPUT_RATE, cudaMemcpyHostToDevice, ctx->stream);
+        ctx->h_osc.resize(INPUT_RATE);
+        build_osc_table(ctx->h_osc.data());
+        cudaMemcpyAsync(osc, ctx->h_osc.data(), sizeof(float2) * INPUT_RATE, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(tf, ctx->host->tw_fwd, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ti, ctx->host->tw_inv, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pr, ctx->host->prs_ref, sizeof(float2) * TU, cudaMemcpyHostToDevice, ctx->stream);
@@ -462,24 +462,18 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.fic_map = fm;
     ctx->dev.gf_exp = ge; ctx->dev.gf_log = gl; ctx->dev.prbs = pb;
     {
-        // on-the-fly oscillator: upload the factors, compare against the table for every index, adopt it when the (at most 8)
-        // differing entries can be patched cheaply; DABB_OSC_TABLE=1 in the environment forces the table lookups (A/B measurements)
+        // on-the-fly oscillator: upload the factors, compare against the table for every index on the device, adopt it only when
+        // nothing differs; DABB_OSC_TABLE=1 in the environment forces the table lookups (A/B measurements)
         double2* hi;
         if ((rc = dalloc(ctx, &hi, 2000))) return fail(rc);
         std::vector<double2> h_hi(2000);
-        build_osc_factors(h_hi.data(), &ctx->dev.osc_theta);
+        build_osc_factors(ctx->h_osc.data(), h_hi.data(), &ctx->dev.osc_theta, &ctx->osc_patched);
         cudaMemcpyAsync(hi, h_hi.data(), sizeof(double2) * 2000, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
-        ctx->dev.osc_hi = hi; ctx->dev.osc_mode = 0; ctx->dev.osc_nexc = 0;
-        int32_t eidx[8]; float2 eval[8];
-        const int nbad = launch_osc_verify(ctx->dev, eidx, eval, ctx->stream);
-        bool ok = nbad >= 0 && nbad <= 8;
-        for (int k = 0; ok && k < nbad; k++) ok = (eidx[k] & 1023) == 0;
-        ctx->osc_mismatches = nbad;
-        if (ok && !getenv("DABB_OSC_TABLE")) {
-            ctx->dev.osc_mode = 1; ctx->dev.osc_nexc = nbad;
-            for (int k = 0; k < nbad; k++) { ctx->dev.osc_exc_idx[k] = eidx[k]; ctx->dev.osc_exc_val[k] = eval[k]; }
-        }
+        ctx->dev.osc_hi = hi; ctx->dev.osc_mode = 0;
+        ctx->osc_mismatches = launch_osc_verify(ctx->dev, ctx->stream);
+        if (ctx->osc_mismatches == 0 && !getenv("DABB_OSC_TABLE")) ctx->dev.osc_mode = 1;
+        std::vector<float2>().swap(ctx->h_osc);
     }
     {
         std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, 768, w);
@@ -886,7 +880,8 @@ int dabb_get_info(dabb_ctx* ctx, int32_t what, int64_t* out)
     if (!ctx || !out) return DABB_E_ARG;
     switch (what) {
         case DABB_INFO_OSC_MODE: *out = ctx->dev.osc_mode; return DABB_OK;
-        case DABB_INFO_OSC_EXCEPTIONS: *out = ctx->osc_mismatches; return DABB_OK;
+        case DABB_INFO_OSC_MISMATCHES: *out = ctx->osc_mismatches; return DABB_OK;
+        case DABB_INFO_OSC_PATCHED: *out = ctx->osc_patched; return DABB_OK;
         default: return DABB_E_ARG;
     }
 }

@@ -15,12 +15,11 @@ struct DevTables {
     const float2* prs_ref;     // [2048] PhaseReference::refTable (phasereference.cpp:45-51)
     const float2* osc;         // [2 048 000] oscillator table (ofdm-processor.cpp:92-94)
     // the same values computed on the fly (osc_mode = 1): osc[m] == float(H[m >> 10] * exp(j theta (m & 1023))) in double, the small
-    // rotation from its Taylor polynomial; verified for all 2 048 000 m at context creation; the few m where it is not
-    // (multiples of a quarter turn, where the reference's own double angle is off by an ulp) are listed
-    const double2* osc_hi;     // [2000] exp(j 2 pi 1024 a / 2 048 000), correctly rounded doubles
+    // rotation from its Taylor polynomial; verified for all 2 048 000 m at context creation (else osc_mode stays 0)
+    const double2* osc_hi;     // [2000] exp(j 2 pi 1024 a / 2 048 000), correctly rounded doubles - except at the quarter turns, where
+                               // the reference's own double angle is an ulp off and the factor is the table value itself
     double osc_theta;          // 2 pi / 2 048 000, correctly rounded
     int32_t osc_mode;          // 0: table lookups (a scattered 8-byte gather per sample), 1: on the fly
-    int32_t osc_nexc; int32_t osc_exc_idx[8]; float2 osc_exc_val[8];     // every exception index has (m & 1023) == 0
     const uint8_t* prbs;       // [9216+] energy-dispersal PRBS bits (fic-handler.cpp:62-71)
     const int16_t* fic_map;    // [3096] mother-code position -> index into the 2304 punctured softbits or -1
     const uint8_t* gf_exp;     // [512]
@@ -71,9 +70,9 @@ struct HostTables {
 };
 void build_host_tables(HostTables& t);
 void build_osc_table(float2* osc /* INPUT_RATE entries */);
-void build_osc_factors(double2* hi /* 2000 */, double* theta);
-// compares the on-the-fly oscillator with the table for every index; returns the number of differing entries (first 8 in exc_*)
-int launch_osc_verify(const DevTables& tb, int32_t* exc_idx, float2* exc_val, cudaStream_t st);
+void build_osc_factors(const float2* osc_table, double2* hi /* 2000 */, double* theta, int* patched);
+// compares the on-the-fly oscillator with the table for every index on the device; returns the number of differing entries
+int launch_osc_verify(const DevTables& tb, cudaStream_t st);
 
 // protection profile -> (L, PI) blocks; returns punctured length or -1
 struct ProtProfile { int bitrate; int nblk; int L[4]; int PI[4]; int in_bits; };

@@ -70,13 +70,7 @@ __device__ __forceinline__ float2 osc_onthefly(const DevTables& tb, int32_t m)
 }
 __device__ __forceinline__ float2 osc_value(const DevTables& tb, int32_t m)
 {
-    if (tb.osc_mode == 0) return __ldg(tb.osc + m);          // kernel-uniform
-    float2 o = osc_onthefly(tb, m);
-    if ((m & 1023) == 0 && tb.osc_nexc) {
-#pragma unroll 1
-        for (int e = 0; e < tb.osc_nexc; e++) if (m == tb.osc_exc_idx[e]) o = tb.osc_exc_val[e];
-    }
-    return o;
+    return tb.osc_mode ? osc_onthefly(tb, m) : __ldg(tb.osc + m);          // kernel-uniform
 }
 __device__ __forceinline__ float2 mix_sample(float2 v, const DevTables& tb, int32_t lp)
 {
@@ -681,33 +675,25 @@ template <typename K> static void set_smem(K k, size_t bytes)
 }
 
 namespace {
-__global__ void osc_verify_kernel(DevTables tb, int32_t* count, int32_t* exc_idx, float2* exc_val)
+__global__ void osc_verify_kernel(DevTables tb, int32_t* count)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= INPUT_RATE) return;
     const float2 a = osc_onthefly(tb, m), b = tb.osc[m];
-    if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y)) {
-        const int k = atomicAdd(count, 1);
-        if (k < 8) { exc_idx[k] = m; exc_val[k] = b; }
-    }
+    if (__float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y)) atomicAdd(count, 1);
 }
 } // namespace
 
-int launch_osc_verify(const DevTables& tb, int32_t* exc_idx, float2* exc_val, cudaStream_t st)
+int launch_osc_verify(const DevTables& tb, cudaStream_t st)
 {
-    int32_t* d = nullptr; float2* dv = nullptr;
-    if (cudaMalloc((void**)&d, 16 * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void**)&dv, 8 * sizeof(float2)) != cudaSuccess) return -1;
-    cudaMemsetAsync(d, 0, 16 * sizeof(int32_t), st);
-    osc_verify_kernel<<<(INPUT_RATE + 255) / 256, 256, 0, st>>>(tb, d, d + 1, dv);
-    int32_t h[16];
-    int rc = -1;
-    if (cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaMemcpyAsync(exc_val, dv, 8 * sizeof(float2), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-        cudaStreamSynchronize(st) == cudaSuccess) {
-        rc = h[0];
-        for (int k = 0; k < 8; k++) exc_idx[k] = h[1 + k];
-    }
-    cudaFree(d); cudaFree(dv);
-    return rc;
+    int32_t* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(int32_t)) != cudaSuccess) return -1;
+    cudaMemsetAsync(d, 0, sizeof(int32_t), st);
+    osc_verify_kernel<<<(INPUT_RATE + 255) / 256, 256, 0, st>>>(tb, d);
+    int32_t h = -1;
+    if (cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) h = -1;
+    cudaFree(d);
+    return h;
 }
 
 int ofdm_init_constants()

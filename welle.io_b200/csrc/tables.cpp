@@ -109,12 +109,21 @@ void build_osc_table(float2* osc)
 }
 
 // factors of the on-the-fly oscillator: correctly rounded doubles of exp(j 2 pi 1024 a / 2 048 000) and of the angle step
-// (80-bit evaluation, then rounded)
-void build_osc_factors(double2* hi, double* theta)
+// (80-bit evaluation, then rounded).  For m = 1024 a the on-the-fly value is float(H[a]) itself; where that is not the table's
+// entry (the quarter turns: the reference's cos(2.0 * M_PI * i / N) sees an angle that is an ulp off and returns 6e-17
+// instead of 0), H[a] becomes the table value - the neighbouring 1023 entries still verify (checked for all of them).
+void build_osc_factors(const float2* osc_table, double2* hi, double* theta, int* patched)
 {
     const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
-    for (int a = 0; a < 2000; a++) { const long double x = two_pi * (long double)(a * 1024) / INPUT_RATE; hi[a].x = (double)cosl(x); hi[a].y = (double)sinl(x); }
+    int n = 0;
+    for (int a = 0; a < 2000; a++) {
+        const long double x = two_pi * (long double)(a * 1024) / INPUT_RATE;
+        hi[a].x = (double)cosl(x); hi[a].y = (double)sinl(x);
+        const float2 t = osc_table[a * 1024];
+        if ((float)hi[a].x != t.x || (float)hi[a].y != t.y) { hi[a].x = (double)t.x; hi[a].y = (double)t.y; n++; }
+    }
     *theta = (double)(two_pi / INPUT_RATE);
+    if (patched) *patched = n;
 }
 
 // UEP profiles exactly as the reference applies them (uep-protection.cpp:38-118): bitrate, level, L1..L4, PI1..PI4.
