@@ -42,14 +42,14 @@ __device__ __forceinline__ void passC_ldg(float2 v[16], int t, const float2* __r
 // subtraction of per-CTA constants (stride 128 and 256 samples).  `mix` is CTA-uniform; lp0 == ph == 0 means the
 // oscillator is (1, 0) for every sample and the multiplication is skipped.
 struct Nco {
-    int32_t lp0, ph, d128, d256;   // d = (stride * ph) mod RATE
+    int32_t lp0, ph, d128, d256, u2048;   // d = (stride * ph) mod RATE; u2048 = (-2048 * ph) mod RATE
     bool mix;
 };
 __device__ __forceinline__ int32_t mod_rate64(int64_t v) { v %= INPUT_RATE; if (v < 0) v += INPUT_RATE; return (int32_t)v; }
 __device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
 {
     Nco n; n.lp0 = lp0; n.ph = ph; n.mix = (lp0 != 0) || (ph != 0);
-    n.d128 = n.mix ? mod_rate64(128 * (int64_t)ph) : 0; n.d256 = n.mix ? mod_rate64(256 * (int64_t)ph) : 0;
+    n.d128 = n.mix ? mod_rate64(128 * (int64_t)ph) : 0; n.d256 = n.mix ? mod_rate64(256 * (int64_t)ph) : 0; n.u2048 = n.mix ? mod_rate64(-2048 * (int64_t)ph) : 0;
     return n;
 }
 __device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
@@ -187,9 +187,12 @@ struct __align__(16) DemodSmem {
 // fft2048_from_global); idx0 = frame-relative index of in[0] for the NCO phase
 template <bool DIRECT> __device__ __forceinline__ float2 ld_in(const float2* in, int i) { return DIRECT ? __ldg(in + i) : in[i]; }
 
+// With afc: also accumulates the fine-AFC correlation of this symbol, sum x[i] * conj(x[i - T_u]) over its last 504 samples
+// (ofdm-processor.cpp:436-442): those are the transform inputs n = 1544..2047, which the owning thread has just mixed, so only
+// the guard-interval partner (T_u samples earlier, at in[n - 2048]) is loaded and mixed here.
 template <bool EXACT, bool DIRECT>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
-                                                  const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco)
+                                                  const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc)
 {
     // one 8-point block at a time (load, oscillator, radix-2 + radix-4, store): keeps 8 instead of 16 inputs live while the
     // oscillator's double-precision temporaries are
@@ -203,7 +206,28 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
         if (nco.mix) {
             int32_t l = h ? sub_mod(lp, nco.d128) : lp;
 #pragma unroll
-            for (int c = 0; c < 8; c++) { x[c] = mix_sample(x[c], tb, l); l = sub_mod(l, nco.d256); }
+            for (int c = 0; c < 8; c++) {
+                x[c] = mix_sample(x[c], tb, l);
+                if (c >= 6 && afc) {
+                    const int n = t + 128 * h + 256 * c;
+                    if (n >= TU - TG) {
+                        const float2 b = mix_sample(ld_in<DIRECT>(in, n - TU), tb, sub_mod(l, nco.u2048));     // phase of the sample T_u earlier
+                        fc.x += x[c].x * b.x + x[c].y * b.y;
+                        fc.y += x[c].y * b.x - x[c].x * b.y;
+                    }
+                }
+                l = sub_mod(l, nco.d256);
+            }
+        } else if (afc) {
+#pragma unroll
+            for (int c = 6; c < 8; c++) {
+                const int n = t + 128 * h + 256 * c;
+                if (n >= TU - TG) {
+                    const float2 b = ld_in<DIRECT>(in, n - TU);
+                    fc.x += x[c].x * b.x + x[c].y * b.y;
+                    fc.y += x[c].y * b.x - x[c].x * b.y;
+                }
+            }
         }
         float2 y[8];
         passA_block<EXACT, false>(x, y, sm.tw);
@@ -281,24 +305,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         if (!DIRECT) { mbar_wait(&sm.full, parity); parity ^= 1; }
         const float2* in = DIRECT ? (src + s0) : (sm.inbuf + shift);
         float2 v[16];
-        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco);
-        if (l >= l_first) {
-            // fine-AFC correlation over the guard interval: sum x[i] * conj(x[i - T_u]), i = 2048..2551 of the symbol
-            // (ofdm-processor.cpp:436-442).  504 products, 4 per thread (thread t: i = t + 128 r).
-            int32_t lpa = 0, lpb = 0;
-            if (nco.mix) { lpb = mod_rate64((int64_t)nco.lp0 - (s0 + t) * (int64_t)nco.ph); lpa = mod_rate64((int64_t)nco.lp0 - (s0 + TU + t) * (int64_t)nco.ph); }
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int i = t + 128 * r;
-                if (i < TG) {
-                    float2 a = ld_in<DIRECT>(in, TU + i), b = ld_in<DIRECT>(in, i);
-                    if (nco.mix) { a = mix_sample(a, tb, lpa); b = mix_sample(b, tb, lpb); }
-                    fc.x += a.x * b.x + a.y * b.y;
-                    fc.y += a.y * b.x - a.x * b.y;
-                }
-                if (nco.mix) { lpa = sub_mod(lpa, nco.d128); lpb = sub_mod(lpb, nco.d128); }
-            }
-        }
+        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
         __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
         if (!DIRECT && t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
