@@ -64,6 +64,8 @@ def main():
             return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         per = (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / frames
         json.dump({"dram_bytes_per_frame": per, "frames_in_capture": frames, "source": "profiles/r01_ofdm_demod_kernel_summary.txt"}, open(os.path.join(OUT, "r01_ofdm_traffic.json"), "w"))
+    if os.path.exists(os.path.join(g, "prof_ofdm_nco.ncu-rep")):
+        summarize(os.path.join(g, "prof_ofdm_nco.ncu-rep"), "r01_ofdm_demod_kernel_oscillator_active", frames)
     if os.path.exists(os.path.join(g, "prof_viterbi.ncu-rep")):
         summarize(os.path.join(g, "prof_viterbi.ncu-rep"), "r01_viterbi_kernel", frames)
     lc = os.path.join(g, "launches.csv")

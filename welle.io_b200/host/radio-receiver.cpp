@@ -81,8 +81,30 @@ struct FigDb {
     std::map<uint32_t, Service> services;
     std::map<uint32_t, std::vector<ServiceComponent>> comps;
     std::map<int, Subchannel> subch;
+    /* FIBProcessor's acceptance rule (fib-processor.cpp:285-327): a saturating sighting counter per SId (max 4), all counters
+     * decremented once per second of wall clock, a service is listed from its second sighting on.  When a counter reaches zero
+     * the reference calls dropService() with the counter value instead of the SId (:302), i.e. it drops service 0: mirrored. */
+    std::map<uint32_t, int8_t> repeatCount;
+    std::chrono::steady_clock::time_point lastDecrement = std::chrono::steady_clock::now();
 
-    void clear() { std::lock_guard<std::mutex> l(m); eid = 0; haveEns = false; ensLabel = DabLabel(); services.clear(); comps.clear(); subch.clear(); }
+    void clear() { std::lock_guard<std::mutex> l(m); eid = 0; haveEns = false; ensLabel = DabLabel(); services.clear(); comps.clear(); subch.clear(); repeatCount.clear(); }
+
+    bool sighting(uint32_t sid)      /* true when the service becomes listed now */
+    {
+        const auto now = std::chrono::steady_clock::now();
+        if (lastDecrement + std::chrono::seconds(1) < now) {
+            for (auto it = repeatCount.begin(); it != repeatCount.end();) {
+                if (it->second > 0) { it->second--; ++it; }
+                else if (it->second == 0) { services.erase((uint32_t)it->second); comps.erase((uint32_t)it->second); it = repeatCount.erase(it); }
+                else ++it;
+            }
+            lastDecrement = now;
+        }
+        int8_t& c = repeatCount[sid];
+        if (c < 4) c++;
+        if (!services.count(sid) && c >= 2) { services.emplace(sid, Service(sid)); return true; }
+        return false;
+    }
 
     /* returns the list of newly detected service ids */
     std::vector<uint32_t> parseFib(const uint8_t* b /* 30 data bytes */, bool& newEnsemble, bool& newEnsLabel)
@@ -135,7 +157,7 @@ struct FigDb {
                             sc.PS_flag = (q[i + 1] >> 1) & 1; sc.CAflag = q[i + 1] & 1;
                             v.push_back(sc);
                         }
-                        if (!services.count(sid)) { services.emplace(sid, Service(sid)); fresh.push_back(sid); }
+                        if (sighting(sid)) fresh.push_back(sid);
                         comps[sid] = v;
                     }
                 }
