@@ -125,6 +125,45 @@ def run_reference_cpu(n_procs, frames_per_proc):
     return frames / busy, frames, busy, wall, sum(o[2] for o in out), sum(o[3] for o in out)
 
 
+def reference_stage_level():
+    """SURVEY 8(d) CPU timing (i): the reference's own stage functions, single thread, on a few synthetic frames: one frame's
+    OFDM demod (PRS + 75 data symbols: fft::Forward + demap loop), FIC (processFicBlock: 4 Viterbi + CRC), MSC (4 x EEPProtection::
+    deconvolve + dedisperse) and RSDecoder::DecodeSuperframe; seconds per frame and frames/s on one core"""
+    import dabtx
+    from oracle.bind import Ref
+    r = Ref()
+    tx = dabtx.DabTx(seed=0x77)
+    iq = tx.frames(4)
+    st = 2 * TF + TNULL + 504
+    prs, syms = iq[st: st + 2048], iq[st + 2048: st + 2048 + 75 * 2552]
+    sf = tx.superframes[0] if tx.superframes else None
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        soft = r.demod_frame(prs, syms)
+    t_ofdm = (time.perf_counter() - t0) / reps
+    fic = np.ascontiguousarray(soft[:3].reshape(-1))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r.fic_decode(fic)
+    t_fic = (time.perf_counter() - t0) / reps
+    cif = np.ascontiguousarray(soft[3:21].reshape(-1)[:SUBCH_CU * 64])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for _c in range(4):
+            r.eep_deconvolve(BITRATE, 1, 3, cif, True)
+    t_msc = (time.perf_counter() - t0) / reps
+    t_rs = 0.0
+    if sf is not None:
+        t0 = time.perf_counter()
+        for _ in range(reps * 4):
+            r.rs_decode_superframe(sf)
+        t_rs = (time.perf_counter() - t0) / (reps * 4) * 0.8       # 4 superframes per 5 transmission frames
+    tot = t_ofdm + t_fic + t_msc + t_rs
+    return {"seconds_per_frame": {"ofdm_demod": t_ofdm, "fic": t_fic, "msc_96k_eep3a": t_msc, "rs_superframe": t_rs}, "frames_per_s_one_core": 1.0 / tot,
+            "note": "unmodified reference stage functions called in a single-threaded loop (ctypes call overhead included, < 1 %)"}
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,6 +245,10 @@ def main():
                 cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
                        "sample": f"{n_procs} concurrent unmodified reference RadioReceiver instances x {a.ref_frames} synthetic frames (same chain: FIC + one 96 kbit/s DAB+ sub-channel), KISS-FFT build, {busy:.1f} s",
                        "fib_crc_ok": ok, "fibs": tot}
+                try:
+                    cpu["stage_level"] = reference_stage_level()
+                except Exception as e:  # noqa
+                    cpu["stage_level"] = {"error": repr(e)}
                 log(f"cpu baseline done: {v:.1f} frames/s")
         except Exception as e:  # noqa
             cpu = {"error": repr(e)}
