@@ -315,8 +315,26 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
 
         if (l >= l_first) {
             // demap owned bins against the previous symbol, scatter softbits into logical order (branch free)
+#if DABB_PACKED_F32 && defined(DABB_DEMAP_PAIRS)
+#pragma unroll
+            for (int s = 0; s + 1 < (EXACT ? NSLOT : 0); s += 2) {
+                const float2 X0 = v[slot_c(s)], X1 = v[slot_c(s + 1)];
+                int8_t sre0, sim0, sre1, sim1; float2 r10, r11;
+                demap_two(X0, prev[s], X1, prev[s + 1], sre0, sim0, r10, sre1, sim1, r11);
+                sm.sbuf[sidx[s]] = (uint16_t)((uint8_t)sre0 | ((uint16_t)(uint8_t)sim0 << 8));
+                sm.sbuf[sidx[s + 1]] = (uint16_t)((uint8_t)sre1 | ((uint16_t)(uint8_t)sim1 << 8));
+                if (TAP) {
+                    if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r10;
+                    if (sidx[s + 1] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s + 1]] = r11;
+                }
+                prev[s] = X0; prev[s + 1] = X1;
+            }
+#pragma unroll
+            for (int s = (EXACT ? NSLOT - 1 : 0); s < NSLOT; s++) {
+#else
 #pragma unroll
             for (int s = 0; s < NSLOT; s++) {
+#endif
                 const float2 X = v[slot_c(s)];
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
