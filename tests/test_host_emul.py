@@ -38,3 +38,14 @@ def test_packed_viterbi(libs, oracle):
         out = np.zeros(nb, np.uint8)
         libs[1].emul_viterbi(nb, soft.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         assert np.array_equal(out, oracle.viterbi(soft, nb))
+
+
+def test_oscillator_on_the_fly_equals_table_for_every_index():
+    """the formula the device evaluates instead of reading the reference's 2 048 000-entry oscillator table (osc_factors.h), run with
+    IEEE double arithmetic on the CPU: identical to the table for every index; three factors (the quarter turns) carry the table's value"""
+    so = os.path.join(HERE, "libemulo.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "emul_osc.cpp")])
+    lib = C.CDLL(so)
+    patched = C.c_int()
+    assert lib.emul_osc_mismatches(C.byref(patched)) == 0
+    assert patched.value == 3

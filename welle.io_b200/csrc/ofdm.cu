@@ -11,6 +11,7 @@
 // 75*3072 out.  One 128-thread CTA walks `sym_per_cta` consecutive symbols of one frame and keeps
 // the previous symbol's spectrum in registers (differential demodulation needs only that).
 #include "common.cuh"
+#include "osc_factors.h"
 #include <cstdlib>
 
 namespace dabb {
@@ -53,20 +54,21 @@ __device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
     return n;
 }
 __device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
-// oscillator sample m without the table: exp(j 2 pi m / 2 048 000) = H[m >> 10] * exp(j theta r), r = m & 1023 < 1024, in double:
-// the small rotation from its Taylor polynomial (theta r < 3.2e-3: the next terms are below 1e-18), one complex product, then
-// rounded to float.  Every operation is explicitly rounded so that every kernel - and the start-up verification against the
-// reference's table - executes the identical arithmetic.  One 16-byte load that is the same for (nearly) all lanes of a warp
-// replaces a scattered 8-byte gather per lane.
+// oscillator sample m without the table (osc_factors.h): one 16-byte load that is the same for (nearly) all lanes of a warp
+// replaces a scattered 8-byte gather per lane.  Every operation is explicitly rounded so that every kernel - and the start-up
+// verification against the reference's table - executes the identical arithmetic.
+struct OscDevOps {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ float to_float(double a) { return __double2float_rn(a); }
+};
 __device__ __forceinline__ float2 osc_onthefly(const DevTables& tb, int32_t m)
 {
-    const double2 h = __ldg(tb.osc_hi + (m >> 10));
-    const double r = __dsub_rn(__hiloint2double(0x43300000, m & 1023), 4503599627370496.0);     // (double)(m & 1023) without a conversion instruction
-    const double y = __dmul_rn(r, tb.osc_theta), y2 = __dmul_rn(y, y);
-    const double c = __fma_rn(y2, __fma_rn(y2, 1.0 / 24, -0.5), 1.0);
-    const double sn = __dmul_rn(y, __fma_rn(y2, __fma_rn(y2, 1.0 / 120, -1.0 / 6), 1.0));
-    const double wr = __fma_rn(h.x, c, -__dmul_rn(h.y, sn)), wi = __fma_rn(h.x, sn, __dmul_rn(h.y, c));
-    return make_float2(__double2float_rn(wr), __double2float_rn(wi));
+    const double2 h = __ldg(tb.osc_hi + (m >> OSC_LO_BITS));
+    const double r = __dsub_rn(__hiloint2double(0x43300000, m & ((1 << OSC_LO_BITS) - 1)), 4503599627370496.0);     // exact int -> double without a conversion instruction
+    float2 o;
+    osc_formula<OscDevOps>(h.x, h.y, r, tb.osc_theta, o.x, o.y);
+    return o;
 }
 __device__ __forceinline__ float2 osc_value(const DevTables& tb, int32_t m)
 {

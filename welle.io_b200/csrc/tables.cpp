@@ -2,6 +2,7 @@
 // All values are derived from the ETSI EN 300 401 rules the reference implements; each builder cites the
 // reference file:line whose behaviour it reproduces.  (Independent of oracle/: the product never links it.)
 #include "common.cuh"
+#include "osc_factors.h"
 #include <cmath>
 #include <cstring>
 
@@ -100,31 +101,10 @@ void build_host_tables(HostTables& t)
     }
 }
 
-void build_osc_table(float2* osc)
-{
-    for (int i = 0; i < INPUT_RATE; i++) {
-        osc[i].x = (float)cos(2.0 * M_PI * i / INPUT_RATE);
-        osc[i].y = (float)sin(2.0 * M_PI * i / INPUT_RATE);
-    }
-}
+void build_osc_table(float2* osc) { build_osc_table_t(osc); }
 
-// factors of the on-the-fly oscillator: correctly rounded doubles of exp(j 2 pi 1024 a / 2 048 000) and of the angle step
-// (80-bit evaluation, then rounded).  For m = 1024 a the on-the-fly value is float(H[a]) itself; where that is not the table's
-// entry (the quarter turns: the reference's cos(2.0 * M_PI * i / N) sees an angle that is an ulp off and returns 6e-17
-// instead of 0), H[a] becomes the table value - the neighbouring 1023 entries still verify (checked for all of them).
-void build_osc_factors(const float2* osc_table, double2* hi, double* theta, int* patched)
-{
-    const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
-    int n = 0;
-    for (int a = 0; a < 2000; a++) {
-        const long double x = two_pi * (long double)(a * 1024) / INPUT_RATE;
-        hi[a].x = (double)cosl(x); hi[a].y = (double)sinl(x);
-        const float2 t = osc_table[a * 1024];
-        if ((float)hi[a].x != t.x || (float)hi[a].y != t.y) { hi[a].x = (double)t.x; hi[a].y = (double)t.y; n++; }
-    }
-    *theta = (double)(two_pi / INPUT_RATE);
-    if (patched) *patched = n;
-}
+// factors of the on-the-fly oscillator (osc_factors.h)
+void build_osc_factors(const float2* osc_table, double2* hi, double* theta, int* patched) { build_osc_factors_t(osc_table, hi, theta, patched); }
 
 // UEP profiles exactly as the reference applies them (uep-protection.cpp:38-118): bitrate, level, L1..L4, PI1..PI4.
 // (Rows 80/1 and a few others differ from ETSI Table 15; bit-parity is with the reference.)  PI = 0: block unused.
