@@ -244,3 +244,30 @@ def test_oscillator_on_the_fly_is_verified(ctx):
     """dabb_create compares the on-the-fly oscillator (three double-precision factors) with the reference's 2 048 000-entry float table
     for EVERY index and only then switches the table lookups off; exactly the three quarter-turn factors take the table's own value"""
     assert ctx.get_info(0) == 1 and ctx.get_info(1) == 0 and ctx.get_info(2) == 3
+
+
+def test_msc_decode_every_protection_profile(ctx, oracle):
+    """every UEP table entry and every EEP-A / EEP-B profile up to 192 kbit/s through dabb_msc_decode: de-puncturing maps, Viterbi,
+    energy de-dispersal and byte packing bit-identical to the oracle (which matches the reference for all of them,
+    tests/test_oracle_vs_ref.py::test_all_uep_profiles / test_all_eep_profiles)"""
+    import ctypes as C
+    from oracle.bind import ProtT
+    cases = []
+    for br in (32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384):
+        for lv in range(1, 6):
+            p = ProtT()
+            if oracle.lib.orc_prot_uep(br, lv, C.byref(p)) == 0:
+                cases.append((p, br, dict(short_form=True, uep_level=lv)))
+    for pa, step in ((True, 8), (False, 32)):
+        for br in range(step, 193, step):
+            for lv in (1, 2, 3, 4):
+                cases.append((oracle.prot_eep(br, int(pa), lv), br, dict(eep_profile_a=pa, eep_level=lv)))
+    assert len(cases) >= 180
+    for k, (prot, br, kw) in enumerate(cases):
+        rng = np.random.default_rng(k)
+        cu = (prot.in_bits + 63) // 64
+        soft = rng.integers(-127, 128, (2, cu * 64)).astype(np.int8)
+        out = ctx.msc_decode(soft, cu, br, **kw)
+        for i in range(2):
+            bits = oracle.msc_deconvolve(prot, soft[i, :prot.in_bits], True)
+            assert np.array_equal(out[i], oracle.pack_bits(bits)), (br, kw, i)

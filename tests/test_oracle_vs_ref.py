@@ -208,3 +208,35 @@ def test_closed_loop_other_placements(oracle, ref, tmp_path, placement):
     m = oracle.rx_run(iq, disable_coarse=True, fft_placement=placement)
     n = min(len(m["fibs"]), len(e["fibs"]))
     assert n >= 12 * 7 and np.array_equal(m["fibs"][:n], e["fibs"][:n])
+
+
+def test_all_uep_profiles(oracle, ref):
+    """every (bitrate, protection level) pair of the reference's UEP table (uep-protection.cpp:38-118)"""
+    n = 0
+    for br in (32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384):
+        for lv in range(1, 6):
+            from oracle.bind import ProtT
+            import ctypes as C
+            p = ProtT()
+            if oracle.lib.orc_prot_uep(br, lv, C.byref(p)) != 0:
+                continue
+            rng = np.random.default_rng(br * 7 + lv)
+            soft = rng.integers(-127, 128, p.in_bits).astype(np.int8)
+            assert np.array_equal(oracle.msc_deconvolve(p, soft, True), ref.uep_deconvolve(br, lv, soft, True)), (br, lv)
+            n += 1
+    assert n >= 60
+
+
+def test_all_eep_profiles(oracle, ref):
+    """EEP-A at every multiple of 8 kbit/s up to 192 and EEP-B at every multiple of 32 kbit/s up to 192, all four levels
+    (eep-protection.cpp:32-113)"""
+    n = 0
+    for pa, step in ((1, 8), (0, 32)):
+        for br in range(step, 193, step):
+            for lv in (1, 2, 3, 4):
+                p = oracle.prot_eep(br, pa, lv)
+                rng = np.random.default_rng(br * 11 + lv + pa)
+                soft = rng.integers(-127, 128, p.in_bits).astype(np.int8)
+                assert np.array_equal(oracle.msc_deconvolve(p, soft, False), ref.eep_deconvolve(br, pa, lv, soft, False)), (br, pa, lv)
+                n += 1
+    assert n == 4 * 24 + 4 * 6
