@@ -43,14 +43,14 @@ __device__ __forceinline__ void passC_ldg(float2 v[16], int t, const float2* __r
 // subtraction of per-CTA constants (stride 128 and 256 samples).  `mix` is CTA-uniform; lp0 == ph == 0 means the
 // oscillator is (1, 0) for every sample and the multiplication is skipped.
 struct Nco {
-    int32_t lp0, ph, d128, d256, dts, u2048;   // d = (stride * ph) mod RATE (dts: one symbol, 2552 samples); u2048 = (-2048 * ph) mod RATE
+    int32_t lp0, ph, d128, d256, u2048;   // d = (stride * ph) mod RATE; u2048 = (-2048 * ph) mod RATE
     bool mix;
 };
 __device__ __forceinline__ int32_t mod_rate64(int64_t v) { v %= INPUT_RATE; if (v < 0) v += INPUT_RATE; return (int32_t)v; }
 __device__ __forceinline__ Nco make_nco(int32_t lp0, int32_t ph)
 {
     Nco n; n.lp0 = lp0; n.ph = ph; n.mix = (lp0 != 0) || (ph != 0);
-    n.d128 = n.mix ? mod_rate64(128 * (int64_t)ph) : 0; n.d256 = n.mix ? mod_rate64(256 * (int64_t)ph) : 0; n.u2048 = n.mix ? mod_rate64(-2048 * (int64_t)ph) : 0; n.dts = n.mix ? mod_rate64((int64_t)TS * ph) : 0;
+    n.d128 = n.mix ? mod_rate64(128 * (int64_t)ph) : 0; n.d256 = n.mix ? mod_rate64(256 * (int64_t)ph) : 0; n.u2048 = n.mix ? mod_rate64(-2048 * (int64_t)ph) : 0;
     return n;
 }
 __device__ __forceinline__ int32_t sub_mod(int32_t a, int32_t d) { a -= d; return a < 0 ? a + INPUT_RATE : a; }
@@ -193,12 +193,13 @@ template <bool DIRECT> __device__ __forceinline__ float2 ld_in(const float2* in,
 // (ofdm-processor.cpp:436-442): those are the transform inputs n = 1544..2047, which the owning thread has just mixed, so only
 // the guard-interval partner (T_u samples earlier, at in[n - 2048]) is loaded and mixed here.
 template <bool EXACT, bool DIRECT>
-__device__ __forceinline__ void fft2048_from_smem(const float2* in, int32_t lp, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
+__device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
                                                   const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc)
 {
     // one 8-point block at a time (load, oscillator, radix-2 + radix-4, store): keeps 8 instead of 16 inputs live while the
     // oscillator's double-precision temporaries are
-    // lp = oscillator index of this thread's first sample (frame index idx0 + t): (lp0 - (idx0 + t) ph) mod 2 048 000
+    int32_t lp = 0;
+    if (nco.mix) lp = mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         float2 x[8];
@@ -297,7 +298,6 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     float2 prev[NSLOT];
     float2 fc = make_float2(0.f, 0.f);
     uint32_t parity = 0;
-    int32_t lp_carry = 0; bool have_lp = false;
 
     for (int l = l_first - 1; l < l_last; l++) {
         const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
@@ -307,29 +307,11 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         if (!DIRECT) { mbar_wait(&sm.full, parity); parity ^= 1; }
         const float2* in = DIRECT ? (src + s0) : (sm.inbuf + shift);
         float2 v[16];
-        // oscillator index of the thread's first transform input; consecutive data symbols are 2552 samples apart, so one 64-bit
-        // modulo per CTA and corrector setting is enough
-        int32_t lp_sym = 0;
-        if (nco.mix) {
-            lp_sym = (have_lp && l >= 2) ? sub_mod(lp_carry, nco.dts) : mod_rate64((int64_t)nco.lp0 - (s0 + goff + t) * (int64_t)nco.ph);
-            lp_carry = lp_sym; have_lp = true;
-        }
-        fft2048_from_smem<EXACT, DIRECT>(in + goff, lp_sym, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
+        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
         __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
         if (!DIRECT && t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(l + 1);
-        }
-        if (nco.mix && tb.osc_mode && l >= 1 && l + 1 < l_last) {
-            // pull the oscillator factors of the next symbol into L1 while passes B, C and the demap run (their loads head every
-            // sample's dependency chain: ncu showed long-scoreboard stalls dominating when the oscillator is active)
-            int32_t ln = sub_mod(lp_sym, nco.dts);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.osc_hi + (ln >> OSC_LO_BITS)));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.osc_hi + (sub_mod(ln, nco.d128) >> OSC_LO_BITS)));
-                ln = sub_mod(ln, nco.d256);
-            }
         }
         fft2048_finish<EXACT>(v, sm, t, xi, tw_c5);   // contains barrier (2)
 
