@@ -530,3 +530,65 @@ extern "C" int ref_process_prs(const float* prs, int freqsync)
     const FreqsyncMethod m = freqsync == 0 ? FreqsyncMethod::GetMiddle : freqsync == 1 ? FreqsyncMethod::CorrelatePRS : FreqsyncMethod::PatternOfZeros;
     return rx.ofdmProcessor.processPRS(v.data(), m);
 }
+
+/* ---------------- FIBProcessor: service database after a sequence of FIBs, as text (same format as welle.io_b200/host/fig-db.h) ---- */
+namespace {
+struct FibRecorder : RadioControllerInterface {
+    std::string log;
+    void onSNR(float) override {} void onFrequencyCorrectorChange(int, int) override {} void onSyncChange(char) override {} void onSignalPresence(bool) override {}
+    void onServiceDetected(uint32_t s) override { char t[64]; snprintf(t, sizeof t, "cb serviceDetected %u\n", s); log += t; }
+    void onNewEnsemble(uint16_t e) override { char t[64]; snprintf(t, sizeof t, "cb newEnsemble %u\n", e); log += t; }
+    void onSetEnsembleLabel(DabLabel&) override { char t[64]; snprintf(t, sizeof t, "cb ensembleLabel %u\n", eid ? *eid : 0u); log += t; }
+    void onDateTimeUpdate(const dab_date_time_t&) override { log += "cb dateTime 0\n"; }
+    void onFIBDecodeSuccess(bool, const uint8_t*) override {} void onNewImpulseResponse(std::vector<float>&&) override {}
+    void onConstellationPoints(std::vector<DSPCOMPLEX>&&) override {} void onNewNullSymbol(std::vector<DSPCOMPLEX>&&) override {}
+    void onTIIMeasurement(tii_measurement_t&&) override {} void onMessage(message_level_t, const std::string&, const std::string&) override {}
+    void onRestartService() override { log += "cb restartService 0\n"; }
+    const uint16_t* eid = nullptr;
+};
+std::string hexs(const std::string& s) { std::string o; char t[4]; for (unsigned char c : s) { snprintf(t, sizeof t, "%02x", c); o += t; } return o; }
+std::string ext_dump(const char* head, const DabLabel& l)
+{
+    if (l.segments.empty() && l.segment_count == 0) return std::string();
+    std::string o = head; char t[64];
+    snprintf(t, sizeof t, " %d %d %d %d", l.toggle_flag ? 1 : 0, (int)l.segment_count, l.fig2_rfu ? 1 : 0, (int)l.extended_label_charset); o += t;
+    for (const auto& kv : l.segments) { snprintf(t, sizeof t, " %d:", kv.first); o += t; o += hexs(std::string(kv.second.begin(), kv.second.end())); }
+    return o + "\n";
+}
+}
+
+extern "C" int ref_fib_dump(const uint8_t* fibs, int n, char* out, int cap)
+{
+    FibRecorder rec;
+    FIBProcessor fp(rec);
+    rec.eid = &fp.ensembleId;
+    for (int i = 0; i < n; i++) {
+        uint8_t bits[256 + 2048] = {0};           /* zero bits behind the FIB: fields of malformed FIGs that run past it read zeros */
+        for (int k = 0; k < 256; k++) bits[k] = (fibs[32 * i + (k >> 3)] >> (7 - (k & 7))) & 1;
+        try { fp.processFIB(bits, 0); } catch (const std::exception& e) { rec.log += std::string("exception ") + e.what() + "\n"; }
+    }
+    std::string o = rec.log; char t[256];
+    const DabLabel el = fp.getEnsembleLabel();
+    snprintf(t, sizeof t, "E %u %u %d %u [%s]\n", fp.getEnsembleId(), fp.getEnsembleEcc(), (int)el.charset, el.fig1_flag, hexs(el.fig1_label).c_str()); o += t;
+    o += ext_dump("XE 0 0", el);
+    const auto services = fp.getServiceList();
+    for (const auto& s : services) {
+        snprintf(t, sizeof t, "S %u %d %d %d %u [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hexs(s.serviceLabel.fig1_label).c_str()); o += t;
+        snprintf(t, sizeof t, "XS %u 0", s.serviceId); o += ext_dump(t, s.serviceLabel);
+    }
+    for (const auto& s : services) for (const auto& c : fp.getComponents(s)) {
+        snprintf(t, sizeof t, "C %u %d %d %d %d %d %u %d %d %d %d %d %u [%s]\n", c.SId, c.componentNr, c.TMid, c.ASCTy, c.DSCTy, c.subchannelId, c.SCId, c.PS_flag, c.CAflag, c.DGflag,
+                 c.packetAddress, (int)c.componentLabel.charset, c.componentLabel.fig1_flag, hexs(c.componentLabel.fig1_label).c_str()); o += t;
+        snprintf(t, sizeof t, "XC %u %d", c.SId, c.componentNr); o += ext_dump(t, c.componentLabel);
+    }
+    for (const auto& u : fp.subChannels) {
+        if (u.subChId == -1) continue;
+        snprintf(t, sizeof t, "U %d %d %d %d %d %d %d %d %d %d %d\n", u.subChId, u.startAddr, u.length, u.programmeNotData ? 1 : 0, u.protectionSettings.shortForm ? 1 : 0,
+                 u.protectionSettings.uepTableIndex, u.protectionSettings.uepLevel, (int)u.protectionSettings.eepProfile, (int)u.protectionSettings.eepLevel, u.language, u.fecScheme); o += t;
+    }
+    const auto& dt = fp.dateTime;
+    snprintf(t, sizeof t, "T %d %d %d %d %d %d %d %d\n", dt.year, dt.month, dt.day, dt.hour, dt.minutes, dt.seconds, dt.hourOffset, dt.minuteOffset); o += t;
+    if ((int)o.size() + 1 > cap) return -(int)o.size() - 1;
+    memcpy(out, o.c_str(), o.size() + 1);
+    return (int)o.size();
+}

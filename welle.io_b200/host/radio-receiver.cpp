@@ -5,11 +5,11 @@
  * (backend/ofdm-processor.cpp:186-224), hands one frame's worth to dabb_process() (n_streams = 1) and turns the POD
  * results back into the reference's callbacks.  No signal processing happens here.
  *
- * Also contains the small FIG 0/0, 0/1, 0/2, 1/0, 1/1 reader the glue needs to map a Service to its sub-channel
- * (ETSI EN 300 401 §6.2-6.4, §8.1); the reference's full FIBProcessor (backend/fib-processor.cpp) is out of scope
- *  — in particular its two-sightings / time-decay acceptance rule is not reproduced.
+ * The service database behind getServiceList / getComponents / getSubchannel lives in fig-db.h (FIG 0/0-0/3, 0/5, 0/9, 0/10, 0/14,
+ * 0/17, FIG 1, FIG 2 with the reference FIBProcessor's acceptance rule); tests/test_figdb.py compares it with the compiled reference.
  */
 #include "dab_api.h"
+#include "fig-db.h"
 #include "../../include/dab_b200.h"
 
 #include <atomic>
@@ -33,10 +33,8 @@ void DABParams::setMode(int mode)
     }
 }
 
-/* ETSI EN 300 401 Table 8 (short-form sub-channel sizes): size in CU, protection level, bit rate */
-static const int16_t kUepSize[64] = {16,21,24,29,35, 24,29,35,42,52, 29,35,42,52, 32,42,48,58,70, 40,52,58,70,84, 48,58,70,84,104, 58,70,84,104,
-                                     64,84,96,116,140, 80,104,116,140,168, 96,116,140,168,208, 116,140,168,208,232, 128,168,192,232,280, 160,208,280, 192,280,416};
-static const int8_t kUepLevel[64] = {5,4,3,2,1, 5,4,3,2,1, 5,4,3,2, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,2, 5,3,1};
+using dabb_host::FigDb; using dabb_host::FigEvents;
+static const int16_t* const kUepSize = dabb_host::kUepSizeCu;
 static const int16_t kUepRate[64] = {32,32,32,32,32, 48,48,48,48,48, 56,56,56,56, 64,64,64,64,64, 80,80,80,80,80, 96,96,96,96,96, 112,112,112,112,
                                      128,128,128,128,128, 160,160,160,160,160, 192,192,192,192,192, 224,224,224,224,224, 256,256,256,256,256, 320,320,320, 384,384,384};
 
@@ -73,113 +71,6 @@ const char* freqSyncMethodToString(FreqsyncMethod m)
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
-namespace {
-
-struct FigDb {
-    std::mutex m;
-    uint16_t eid = 0; uint8_t ecc = 0; DabLabel ensLabel; bool haveEns = false;
-    std::map<uint32_t, Service> services;
-    std::map<uint32_t, std::vector<ServiceComponent>> comps;
-    std::map<int, Subchannel> subch;
-    /* FIBProcessor's acceptance rule (fib-processor.cpp:285-327): a saturating sighting counter per SId (max 4), all counters
-     * decremented once per second of wall clock, a service is listed from its second sighting on.  When a counter reaches zero
-     * the reference calls dropService() with the counter value instead of the SId (:302), i.e. it drops service 0: mirrored. */
-    std::map<uint32_t, int8_t> repeatCount;
-    std::chrono::steady_clock::time_point lastDecrement = std::chrono::steady_clock::now();
-
-    void clear() { std::lock_guard<std::mutex> l(m); eid = 0; haveEns = false; ensLabel = DabLabel(); services.clear(); comps.clear(); subch.clear(); repeatCount.clear(); }
-
-    bool sighting(uint32_t sid)      /* true when the service becomes listed now */
-    {
-        const auto now = std::chrono::steady_clock::now();
-        if (lastDecrement + std::chrono::seconds(1) < now) {
-            for (auto it = repeatCount.begin(); it != repeatCount.end();) {
-                if (it->second > 0) { it->second--; ++it; }
-                else if (it->second == 0) { services.erase((uint32_t)it->second); comps.erase((uint32_t)it->second); it = repeatCount.erase(it); }
-                else ++it;
-            }
-            lastDecrement = now;
-        }
-        int8_t& c = repeatCount[sid];
-        if (c < 4) c++;
-        if (!services.count(sid) && c >= 2) { services.emplace(sid, Service(sid)); return true; }
-        return false;
-    }
-
-    /* returns the list of newly detected service ids */
-    std::vector<uint32_t> parseFib(const uint8_t* b /* 30 data bytes */, bool& newEnsemble, bool& newEnsLabel)
-    {
-        std::vector<uint32_t> fresh;
-        std::lock_guard<std::mutex> l(m);
-        int p = 0;
-        while (p < 30) {
-            const int type = b[p] >> 5, len = b[p] & 0x1F;
-            if (b[p] == 0xFF || len == 0 || p + 1 + len > 30) break;
-            const uint8_t* d = b + p + 1;
-            if (type == 0 && len >= 1) {
-                const int pd = (d[0] >> 5) & 1, ext = d[0] & 0x1F;
-                const uint8_t* q = d + 1; int n = len - 1;
-                if (ext == 0 && n >= 4) { uint16_t e = q[0] << 8 | q[1]; if (!haveEns || e != eid) { eid = e; haveEns = true; newEnsemble = true; } }
-                else if (ext == 1) {
-                    int i = 0;
-                    while (i + 3 <= n) {
-                        Subchannel s; s.subChId = q[i] >> 2; s.startAddr = ((q[i] & 3) << 8) | q[i + 1];
-                        if (q[i + 2] & 0x80) {      /* long form */
-                            if (i + 4 > n) break;
-                            const int opt = (q[i + 2] >> 4) & 7;
-                            s.protectionSettings.shortForm = false;
-                            s.protectionSettings.eepProfile = opt == 0 ? EEPProtectionProfile::EEP_A : EEPProtectionProfile::EEP_B;
-                            s.protectionSettings.eepLevel = (EEPProtectionLevel)(((q[i + 2] >> 2) & 3) + 1);
-                            s.length = ((q[i + 2] & 3) << 8) | q[i + 3];
-                            i += 4;
-                        } else {
-                            const int idx = q[i + 2] & 0x3F;
-                            s.protectionSettings.shortForm = true; s.protectionSettings.uepTableIndex = idx;
-                            s.protectionSettings.uepLevel = kUepLevel[idx]; s.length = kUepSize[idx];
-                            i += 3;
-                        }
-                        subch[s.subChId] = s;
-                    }
-                } else if (ext == 2) {
-                    int i = 0;
-                    while (i < n) {
-                        uint32_t sid;
-                        if (pd) { if (i + 5 > n) break; sid = (uint32_t)q[i] << 24 | q[i + 1] << 16 | q[i + 2] << 8 | q[i + 3]; i += 4; }
-                        else { if (i + 3 > n) break; sid = q[i] << 8 | q[i + 1]; i += 2; }
-                        const int nc = q[i] & 0x0F; i++;
-                        if (i + 2 * nc > n) break;
-                        std::vector<ServiceComponent> v;
-                        for (int c = 0; c < nc; c++, i += 2) {
-                            ServiceComponent sc; sc.SId = sid; sc.componentNr = c; sc.TMid = q[i] >> 6;
-                            if (sc.TMid == 0) { sc.ASCTy = q[i] & 0x3F; sc.subchannelId = q[i + 1] >> 2; }
-                            else if (sc.TMid == 1) { sc.DSCTy = q[i] & 0x3F; sc.subchannelId = q[i + 1] >> 2; }
-                            else if (sc.TMid == 3) { sc.SCId = ((q[i] & 0x3F) << 6) | (q[i + 1] >> 2); }
-                            sc.PS_flag = (q[i + 1] >> 1) & 1; sc.CAflag = q[i + 1] & 1;
-                            v.push_back(sc);
-                        }
-                        if (sighting(sid)) fresh.push_back(sid);
-                        comps[sid] = v;
-                    }
-                }
-            } else if (type == 1 && len >= 19) {
-                const int ext = d[0] & 7;
-                std::string label((const char*)d + 3, 16);
-                const uint16_t flag = d[19] << 8 | d[20 > len ? len : 20];
-                if (ext == 0) { ensLabel.fig1_label = label; ensLabel.fig1_flag = flag; newEnsLabel = true; }
-                else if (ext == 1) {
-                    const uint32_t sid = d[1] << 8 | d[2];
-                    auto it = services.find(sid);
-                    if (it != services.end()) { it->second.serviceLabel.fig1_label = label; it->second.serviceLabel.fig1_flag = flag; }
-                }
-            }
-            p += 1 + len;
-        }
-        return fresh;
-    }
-};
-
-} // namespace
-
 struct RadioReceiver::Impl {
     RadioControllerInterface& rci; InputInterface& input; RadioReceiverOptions rro; DABParams params;
     dabb_ctx* ctx = nullptr;
@@ -306,11 +197,17 @@ struct RadioReceiver::Impl {
             const bool ok = (r.fib_crc_mask >> f) & 1;
             rci.onFIBDecodeSuccess(ok, bits);
             if (ok) {
-                bool newEns = false, newLabel = false;
-                const auto fresh = db.parseFib(fibs + 32 * f, newEns, newLabel);
-                if (newEns) rci.onNewEnsemble(db.eid);
-                if (newLabel) { DabLabel l = db.ensLabel; rci.onSetEnsembleLabel(l); }
-                for (uint32_t sid : fresh) rci.onServiceDetected(sid);
+                FigEvents ev;
+                db.parseFib(fibs + 32 * f, ev);
+                for (const auto& e : ev.list) {          /* the FIG-derived callbacks, in the order the FIGs appear (fib-processor.cpp) */
+                    switch (e.kind) {
+                        case FigEvents::NewEnsemble: rci.onNewEnsemble((uint16_t)e.id); break;
+                        case FigEvents::ServiceDetected: rci.onServiceDetected(e.id); break;
+                        case FigEvents::EnsembleLabel: { DabLabel l; { std::lock_guard<std::mutex> g(db.m); l = db.ensLabel; } rci.onSetEnsembleLabel(l); break; }
+                        case FigEvents::RestartService: rci.onRestartService(); break;
+                        case FigEvents::DateTime: { dab_date_time_t t; { std::lock_guard<std::mutex> g(db.m); t = db.dateTime; } rci.onDateTimeUpdate(t); break; }
+                    }
+                }
             }
         }
         std::lock_guard<std::mutex> l(slotMutex);
@@ -334,14 +231,11 @@ struct RadioReceiver::Impl {
         Subchannel sub; AudioServiceComponentType at = AudioServiceComponentType::Unknown;
         {
             std::lock_guard<std::mutex> l(db.m);
-            auto it = db.comps.find(srv.serviceId);
-            if (it == db.comps.end()) return false;
-            for (const auto& sc : it->second) {
-                if (sc.transportMode() != TransportMode::Audio) continue;
-                auto st = db.subch.find(sc.subchannelId);
-                if (st == db.subch.end()) continue;
+            for (const auto& sc : db.components) {
+                if (sc.SId != srv.serviceId || sc.transportMode() != TransportMode::Audio) continue;
+                if (sc.subchannelId < 0 || sc.subchannelId >= 64 || !db.subch[sc.subchannelId].valid()) continue;
                 if (sc.audioType() == AudioServiceComponentType::Unknown) continue;
-                sub = st->second; at = sc.audioType();
+                sub = db.subch[sc.subchannelId]; at = sc.audioType();
                 break;
             }
         }
@@ -411,22 +305,19 @@ DabLabel RadioReceiver::getEnsembleLabel(void) const { std::lock_guard<std::mute
 std::vector<Service> RadioReceiver::getServiceList(void) const
 {
     std::lock_guard<std::mutex> l(d->db.m);
-    std::vector<Service> v;
-    for (const auto& kv : d->db.services) v.push_back(kv.second);
-    return v;
+    return d->db.services;
 }
 Service RadioReceiver::getService(uint32_t sId) const
 {
     std::lock_guard<std::mutex> l(d->db.m);
-    auto it = d->db.services.find(sId);
-    return it == d->db.services.end() ? Service(0) : it->second;
+    for (const auto& s : d->db.services) if (s.serviceId == sId) return s;
+    return Service(0);
 }
 std::list<ServiceComponent> RadioReceiver::getComponents(const Service& s) const
 {
     std::lock_guard<std::mutex> l(d->db.m);
     std::list<ServiceComponent> out;
-    auto it = d->db.comps.find(s.serviceId);
-    if (it != d->db.comps.end()) out.assign(it->second.begin(), it->second.end());
+    for (const auto& c : d->db.components) if (c.SId == s.serviceId) out.push_back(c);
     return out;
 }
 bool RadioReceiver::serviceHasAudioComponent(const Service& s) const
@@ -438,8 +329,25 @@ bool RadioReceiver::serviceHasAudioComponent(const Service& s) const
 Subchannel RadioReceiver::getSubchannel(const ServiceComponent& sc) const
 {
     std::lock_guard<std::mutex> l(d->db.m);
-    auto it = d->db.subch.find(sc.subchannelId);
-    return it == d->db.subch.end() ? Subchannel() : it->second;
+    return d->db.subch.at(sc.subchannelId);          /* throws std::out_of_range like the reference's vector::at (fib-processor.cpp:1313) */
 }
 DABParams& RadioReceiver::getParams() { return d->params; }
 RadioReceiverStats RadioReceiver::getReceiverStats() const { return RadioReceiverStats(); }
+
+/* test hook: feeds n FIBs (32 bytes each) to a fresh service database and writes its text dump (callbacks first) */
+extern "C" int welle_b200_figdb_dump(const uint8_t* fibs, int n, char* out, int cap)
+{
+    FigDb db; std::string cb;
+    for (int i = 0; i < n; i++) {
+        FigEvents ev; db.parseFib(fibs + 32 * i, ev);
+        for (const auto& e : ev.list) {
+            char t[64];
+            static const char* const names[] = {"newEnsemble", "serviceDetected", "ensembleLabel", "restartService", "dateTime"};
+            snprintf(t, sizeof t, "cb %s %u\n", names[e.kind], e.kind == FigEvents::DateTime || e.kind == FigEvents::RestartService ? 0u : e.id); cb += t;
+        }
+    }
+    const std::string s = cb + db.dump();
+    if ((int)s.size() + 1 > cap) return -(int)s.size() - 1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
