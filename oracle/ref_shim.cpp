@@ -553,6 +553,7 @@ std::string ext_dump(const char* head, const DabLabel& l)
     std::string o = head; char t[64];
     snprintf(t, sizeof t, " %d %d %d %d", l.toggle_flag ? 1 : 0, (int)l.segment_count, l.fig2_rfu ? 1 : 0, (int)l.extended_label_charset); o += t;
     for (const auto& kv : l.segments) { snprintf(t, sizeof t, " %d:", kv.first); o += t; o += hexs(std::string(kv.second.begin(), kv.second.end())); }
+    o += " utf8="; o += hexs(l.fig2_label());
     return o + "\n";
 }
 }

@@ -44,11 +44,53 @@ public:
 };
 
 struct DabLabel {
+    /* FIG 1 label, encoded according to charset (usually EBU Latin, ETSI TS 101 756 Annex C) */
     CharacterSet charset = CharacterSet::EbuLatin;
     std::string fig1_label;
     uint16_t fig1_flag = 0;
-    std::string fig1_label_utf8() const { return fig1_label; }      /* EBU-Latin -> UTF-8 conversion is a UI concern */
-    std::string utf8_label() const { return fig1_label; }
+    void setCharset(uint8_t charset_id) { charset = static_cast<CharacterSet>(charset_id); }
+    /* the EBU Latin -> UTF-8 table is a UI concern and not part of this backend: bytes >= 0x80 (and the few EBU code points below
+     * 0x80 that differ from ASCII) are returned as they are */
+    std::string fig1_label_utf8() const { return fig1_label; }
+
+    /* extended label from FIG 2 segments (UTF-8 or UCS-2), same fields as the reference (backend/dab-constants.h:88-118) */
+    std::map<int, std::vector<uint8_t>> segments;
+    size_t segment_count = 0;
+    CharacterSet extended_label_charset = CharacterSet::Undefined;
+    uint8_t toggle_flag = 0;
+    bool fig2_rfu = false;
+    /* all segments concatenated as UTF-8; empty until every segment has arrived */
+    std::string fig2_label() const
+    {
+        std::vector<uint8_t> cat;
+        for (size_t i = 0; i < segment_count; i++) {
+            auto it = segments.find((int)i);
+            if (it == segments.end()) return std::string();
+            cat.insert(cat.end(), it->second.begin(), it->second.end());
+        }
+        if (extended_label_charset == CharacterSet::UnicodeUtf8) return std::string(cat.begin(), cat.end());
+        if (extended_label_charset != CharacterSet::UnicodeUcs2) return std::string();
+        /* UCS-2 / UTF-16 -> UTF-8.  The reference reinterprets the segment bytes as host-order char16_t (charsets.cpp:111-121), i.e.
+         * little endian on the machines it runs on although DAB transmits UCS-2 big endian; kept so that labels come out the same */
+        std::string o;
+        auto put = [&o](unsigned c) {
+            if (c < 0x80) o += (char)c;
+            else if (c < 0x800) { o += (char)(0xC0 | (c >> 6)); o += (char)(0x80 | (c & 0x3F)); }
+            else if (c < 0x10000) { o += (char)(0xE0 | (c >> 12)); o += (char)(0x80 | ((c >> 6) & 0x3F)); o += (char)(0x80 | (c & 0x3F)); }
+            else { o += (char)(0xF0 | (c >> 18)); o += (char)(0x80 | ((c >> 12) & 0x3F)); o += (char)(0x80 | ((c >> 6) & 0x3F)); o += (char)(0x80 | (c & 0x3F)); }
+        };
+        for (size_t i = 0; i + 1 < cat.size(); i += 2) {
+            unsigned c = (unsigned)cat[i] | (unsigned)cat[i + 1] << 8;
+            if (c >= 0xD800 && c < 0xDC00 && i + 3 < cat.size()) {
+                const unsigned lo = (unsigned)cat[i + 2] | (unsigned)cat[i + 3] << 8;
+                if (lo >= 0xDC00 && lo < 0xE000) { c = 0x10000 + ((c - 0xD800) << 10) + (lo - 0xDC00); i += 2; }
+            }
+            if (c >= 0xD800 && c < 0xE000) c = 0xFFFD;        /* unpaired surrogate: the reference's converter throws here */
+            put(c);
+        }
+        return o;
+    }
+    std::string utf8_label() const { const std::string f2 = fig2_label(); return f2.empty() ? fig1_label_utf8() : f2; }
 };
 
 struct Service {

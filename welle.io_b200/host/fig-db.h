@@ -32,11 +32,6 @@ static const int16_t kUepSizeCu[64] = {16,21,24,29,35, 24,29,35,42,52, 29,35,42,
                                        64,84,96,116,140, 80,104,116,140,168, 96,116,140,168,208, 116,140,168,208,232, 128,168,192,232,280, 160,208,280, 192,280,416};
 static const int8_t kUepProtLevel[64] = {5,4,3,2,1, 5,4,3,2,1, 5,4,3,2, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,3,2,1, 5,4,2, 5,3,1};
 
-struct ExtLabel {            /* FIG 2 state of one label (DabLabel's extended part, dab-constants.h) */
-    bool toggle = false; int segment_count = 0; int rfu = 0; CharacterSet charset = CharacterSet::Undefined;
-    std::map<int, std::vector<uint8_t>> segments;
-};
-
 struct FigEvents {           /* what one FIB asks the owner to signal, in order of occurrence */
     enum Kind { NewEnsemble, ServiceDetected, EnsembleLabel, RestartService, DateTime };
     struct Ev { Kind kind; uint32_t id; };
@@ -46,12 +41,10 @@ struct FigEvents {           /* what one FIB asks the owner to signal, in order 
 class FigDb {
 public:
     std::mutex m;
-    uint16_t eid = 0; uint8_t ecc = 0; DabLabel ensLabel; ExtLabel ensExt;
+    uint16_t eid = 0; uint8_t ecc = 0; DabLabel ensLabel;
     std::vector<Service> services;                       /* in order of acceptance, like the reference's vector */
     std::vector<ServiceComponent> components;
     std::vector<Subchannel> subch = std::vector<Subchannel>(64);
-    std::map<uint32_t, ExtLabel> serviceExt;             /* by SId */
-    std::map<std::pair<uint32_t, int>, ExtLabel> compExt;
     dab_date_time_t dateTime; bool timeOffsetReceived = false;
     std::map<uint32_t, int8_t> repeatCount;
     std::chrono::steady_clock::time_point lastDecrement = std::chrono::steady_clock::now();
@@ -59,7 +52,7 @@ public:
     void clear()
     {
         std::lock_guard<std::mutex> l(m);
-        components.clear(); subch.assign(64, Subchannel()); services.clear(); repeatCount.clear(); serviceExt.clear(); compExt.clear();
+        components.clear(); subch.assign(64, Subchannel()); services.clear(); repeatCount.clear();
         lastDecrement = std::chrono::steady_clock::now();
     }
 
@@ -90,18 +83,16 @@ public:
     {
         std::string o; char t[256];
         snprintf(t, sizeof t, "E %u %u %d %u [%s]\n", eid, ecc, (int)ensLabel.charset, ensLabel.fig1_flag, hex(ensLabel.fig1_label).c_str()); o += t;
-        o += extDump("XE 0 0", ensExt);
+        o += extDump("XE 0 0", ensLabel);
         for (const auto& s : services) {
             snprintf(t, sizeof t, "S %u %d %d %d %u [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hex(s.serviceLabel.fig1_label).c_str()); o += t;
-            auto it = serviceExt.find(s.serviceId);
-            if (it != serviceExt.end()) { snprintf(t, sizeof t, "XS %u 0", s.serviceId); o += extDump(t, it->second); }
+            snprintf(t, sizeof t, "XS %u 0", s.serviceId); o += extDump(t, s.serviceLabel);
         }
         for (const auto& s : services) for (const auto& c : components) {       /* grouped per service like getComponents() */
             if (c.SId != s.serviceId) continue;
             snprintf(t, sizeof t, "C %u %d %d %d %d %d %u %d %d %d %d %d %u [%s]\n", c.SId, c.componentNr, c.TMid, c.ASCTy, c.DSCTy, c.subchannelId, c.SCId, c.PS_flag, c.CAflag, c.DGflag,
                      c.packetAddress, (int)c.componentLabel.charset, c.componentLabel.fig1_flag, hex(c.componentLabel.fig1_label).c_str()); o += t;
-            auto it = compExt.find(std::make_pair(c.SId, (int)c.componentNr));
-            if (it != compExt.end()) { snprintf(t, sizeof t, "XC %u %d", c.SId, c.componentNr); o += extDump(t, it->second); }
+            snprintf(t, sizeof t, "XC %u %d", c.SId, c.componentNr); o += extDump(t, c.componentLabel);
         }
         for (const auto& u : subch) {
             if (u.subChId == -1) continue;
@@ -127,12 +118,13 @@ private:
         return v;
     }
     static std::string hex(const std::string& s) { std::string o; char t[4]; for (unsigned char c : s) { snprintf(t, sizeof t, "%02x", c); o += t; } return o; }
-    static std::string extDump(const char* head, const ExtLabel& x)
+    static std::string extDump(const char* head, const DabLabel& x)
     {
         if (x.segments.empty() && x.segment_count == 0) return std::string();
         std::string o = head; char t[64];
-        snprintf(t, sizeof t, " %d %d %d %d", x.toggle ? 1 : 0, x.segment_count, x.rfu, (int)x.charset); o += t;
+        snprintf(t, sizeof t, " %d %d %d %d", x.toggle_flag ? 1 : 0, (int)x.segment_count, x.fig2_rfu ? 1 : 0, (int)x.extended_label_charset); o += t;
         for (const auto& kv : x.segments) { snprintf(t, sizeof t, " %d:", kv.first); o += t; o += hex(std::string(kv.second.begin(), kv.second.end())); }
+        o += " utf8="; o += hex(x.fig2_label());
         return o + "\n";
     }
 
@@ -284,16 +276,16 @@ private:
         }
     }
 
-    void extSegment(ExtLabel& x, const uint8_t* f, int nbytes, bool toggle, int seg, int rfu)
+    void extSegment(DabLabel& x, const uint8_t* f, int nbytes, bool toggle, int seg, int rfu)
     {
-        if (x.toggle != toggle) { x.segments.clear(); x.charset = CharacterSet::Undefined; x.toggle = toggle; }
+        if ((x.toggle_flag != 0) != toggle) { x.segments.clear(); x.extended_label_charset = CharacterSet::Undefined; x.toggle_flag = toggle ? 1 : 0; }
         if (seg == 0) {
             x.segment_count = ((f[0] >> 4) & 7) + 1;
-            x.charset = (f[0] & 0x80) ? CharacterSet::UnicodeUcs2 : CharacterSet::UnicodeUtf8;
+            x.extended_label_charset = (f[0] & 0x80) ? CharacterSet::UnicodeUcs2 : CharacterSet::UnicodeUtf8;
             const int skip = rfu == 0 ? 3 : 1;
             if (nbytes <= skip) return;                /* the reference throws here ("FIG2 label length too short"); the glue ignores the FIG */
             f += skip; nbytes -= skip;
-            x.rfu = rfu;
+            x.fig2_rfu = rfu != 0;
         }
         x.segments[seg] = std::vector<uint8_t>(f, f + nbytes);
     }
@@ -309,15 +301,17 @@ private:
         switch (ext) { case 0: case 1: idlen = 2; break; case 4: idlen = (h[1] & 0x80) ? 5 : 3; break; case 5: idlen = 4; break; default: return; }
         if (len <= 1 + idlen) return;
         const uint8_t* data = h + 1 + idlen; const int n = len - 1 - idlen;
-        if (ext == 0) { if ((uint16_t)(h[1] << 8 | h[2]) == eid) extSegment(ensExt, data, n, toggle, seg, rfu); }
-        else if (ext == 1) { const uint32_t sid = h[1] << 8 | h[2]; if (findService(sid)) extSegment(serviceExt[sid], data, n, toggle, seg, rfu); }
+        if (ext == 0) { if ((uint16_t)(h[1] << 8 | h[2]) == eid) extSegment(ensLabel, data, n, toggle, seg, rfu); }
+        else if (ext == 1) { Service* sv = findService(h[1] << 8 | h[2]); if (sv) extSegment(sv->serviceLabel, data, n, toggle, seg, rfu); }
         else if (ext == 4) {
             const int scids = h[1] & 0x0F;
             const uint32_t sid = (h[1] & 0x80) ? ((uint32_t)h[2] << 24 | (uint32_t)h[3] << 16 | (uint32_t)h[4] << 8 | h[5]) : (uint32_t)(h[2] << 8 | h[3]);
-            if (findComponent(sid, scids)) extSegment(compExt[std::make_pair(sid, scids)], data, n, toggle, seg, rfu);
+            ServiceComponent* c = findComponent(sid, scids);
+            if (c) extSegment(c->componentLabel, data, n, toggle, seg, rfu);
         } else {
             const uint32_t sid = (uint32_t)h[1] << 24 | (uint32_t)h[2] << 16 | (uint32_t)h[3] << 8 | h[4];
-            if (findService(sid)) extSegment(serviceExt[sid], data, n, toggle, seg, rfu);
+            Service* sv = findService(sid);
+            if (sv) extSegment(sv->serviceLabel, data, n, toggle, seg, rfu);
         }
     }
 
