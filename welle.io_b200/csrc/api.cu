@@ -599,13 +599,6 @@ int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
     { int rc_ = check_launch(ctx, "set_slot_kernel"); cudaStreamSynchronize(ctx->stream); return rc_; }
 }
 
-static ViterbiParams fic_viterbi_params(dabb_ctx* ctx, int n_frames, uint8_t* fibs, uint2* dec)
-{
-    ViterbiParams vp{};
-    vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
-    vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
-    return vp;
-}
 
 static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc, cudaStream_t st, uint2* dec)
 {
@@ -943,17 +936,14 @@ int dabb_msc_decode(dabb_ctx* ctx, const dabb_subchannel* sc, const int8_t* soft
     if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
     const int frag = sc->length_cu * 64, nbits = 24 * prof.bitrate, nsteps = nbits + 6, rw = vit_row_words(nsteps), flen = 3 * prof.bitrate;
     if (prof.in_bits > frag) { ctx->err = "protection profile needs more bits than the sub-channel holds"; return DABB_E_ARG; }
-    // de-puncture on the host side of the ABI? no: build the map, expand on the device with a gather, then the common path
+    // build the de-puncturing map, expand on the device with a gather, then the common Viterbi path
     std::vector<int16_t> map((size_t)nsteps * 4);
     build_msc_map(*ctx->host, prof, map.data());
     std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, nbits, w);
-    int16_t* d_map = nullptr; uint32_t* d_w = nullptr; uint32_t* rows = nullptr; int8_t* ring = nullptr; MscSlotState* d_sl = nullptr; int32_t* d_valid = nullptr;
+    int16_t* d_map = nullptr; uint32_t* d_w = nullptr; uint32_t* rows = nullptr;
     CK(cudaMalloc((void**)&d_map, map.size() * 2)); CK(cudaMalloc((void**)&d_w, w.size() * 4)); CK(cudaMalloc((void**)&rows, (size_t)n * rw * 4));
     CK(cudaMemcpy(d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     int rc = ensure_dec(ctx, vit_dec_bytes(n, nsteps));
-    // reuse the generic path: scatter the punctured softbits into mother-code order with a tiny kernel-free trick:
-    // cudaMemcpy of the map is enough because msc_prep_kernel needs ring state; instead expand here with thrust-free code
-    (void)ring; (void)d_sl; (void)d_valid;
     if (!rc) {
         // expand on device: one thread per (cif, step)
         launch_msc_expand(soft, n, frag, d_map, nsteps, rows, rw, ctx->stream);

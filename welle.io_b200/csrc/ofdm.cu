@@ -187,12 +187,11 @@ struct __align__(16) DemodSmem {
 
 // one symbol's samples, already in shared memory at in[0..], -> spectrum in registers (same pass structure as
 // fft2048_from_global); idx0 = frame-relative index of in[0] for the NCO phase
-template <bool DIRECT> __device__ __forceinline__ float2 ld_in(const float2* in, int i) { return DIRECT ? __ldg(in + i) : in[i]; }
 
 // With afc: also accumulates the fine-AFC correlation of this symbol, sum x[i] * conj(x[i - T_u]) over its last 504 samples
 // (ofdm-processor.cpp:436-442): those are the transform inputs n = 1544..2047, which the owning thread has just mixed, so only
 // the guard-interval partner (T_u samples earlier, at in[n - 2048]) is loaded and mixed here.
-template <bool EXACT, bool DIRECT>
+template <bool EXACT>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
                                                   const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc)
 {
@@ -204,7 +203,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
     for (int h = 0; h < 2; h++) {
         float2 x[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) x[c] = ld_in<DIRECT>(in, t + 128 * h + 256 * c);
+        for (int c = 0; c < 8; c++) x[c] = in[t + 128 * h + 256 * c];
         if (nco.mix) {
             int32_t l = h ? sub_mod(lp, nco.d128) : lp;
 #pragma unroll
@@ -213,7 +212,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
                 if (c >= 6 && afc) {
                     const int n = t + 128 * h + 256 * c;
                     if (n >= TU - TG) {
-                        const float2 b = mix_sample(ld_in<DIRECT>(in, n - TU), tb, sub_mod(l, nco.u2048));     // phase of the sample T_u earlier
+                        const float2 b = mix_sample(in[n - TU], tb, sub_mod(l, nco.u2048));     // phase of the sample T_u earlier
                         fc.x += x[c].x * b.x + x[c].y * b.y;
                         fc.y += x[c].y * b.x - x[c].x * b.y;
                     }
@@ -225,7 +224,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
             for (int c = 6; c < 8; c++) {
                 const int n = t + 128 * h + 256 * c;
                 if (n >= TU - TG) {
-                    const float2 b = ld_in<DIRECT>(in, n - TU);
+                    const float2 b = in[n - TU];
                     fc.x += x[c].x * b.x + x[c].y * b.y;
                     fc.y += x[c].y * b.x - x[c].x * b.y;
                 }
@@ -255,7 +254,7 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     passC_ldg<EXACT, false>(v, t, tw_c5);
 }
 
-template <bool EXACT, bool TAP, bool DIRECT>
+template <bool EXACT, bool TAP>
 __global__ void __launch_bounds__(OFDM_THREADS, DEMOD_CTAS_PER_SM)
 ofdm_demod_kernel(DevTables tb, OfdmParams p)
 {
@@ -281,7 +280,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     };
     if (t == 0) { mbar_init(&sm.full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    if (!DIRECT && t == 0) issue(l_first - 1);
+    if (t == 0) issue(l_first - 1);
 
     if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
     const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
@@ -304,12 +303,12 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         const int goff = (l == 0) ? 0 : TG;
         const int shift = (int)((reinterpret_cast<uintptr_t>(src + s0) >> 3) & 1);
         const Nco& nco = l == 0 ? ncoP : ncoS;
-        if (!DIRECT) { mbar_wait(&sm.full, parity); parity ^= 1; }
-        const float2* in = DIRECT ? (src + s0) : (sm.inbuf + shift);
+        mbar_wait(&sm.full, parity); parity ^= 1;
+        const float2* in = sm.inbuf + shift;
         float2 v[16];
-        fft2048_from_smem<EXACT, DIRECT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
+        fft2048_from_smem<EXACT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
         __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
-        if (!DIRECT && t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
+        if (t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(l + 1);
         }
@@ -738,10 +737,9 @@ void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, c
     const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
     const size_t sm = sizeof(DemodSmem) > (size_t)p.smem_floor ? sizeof(DemodSmem) : (size_t)p.smem_floor;
     const bool tap = p.r1 != nullptr;
-#define LAUNCH(E, T, D) do { set_smem(ofdm_demod_kernel<E, T, D>, sm); ofdm_demod_kernel<E, T, D><<<grid, block, sm, st>>>(tb, p); } while (0)
-    static const bool direct = getenv("DABB_OFDM_DIRECT") != nullptr;    // experiment: global -> register loads instead of TMA staging
-    if (fft_mode == 0) { if (tap) LAUNCH(true, true, false); else if (direct) LAUNCH(true, false, true); else LAUNCH(true, false, false); }
-    else { if (tap) LAUNCH(false, true, false); else LAUNCH(false, false, false); }
+#define LAUNCH(E, T) do { set_smem(ofdm_demod_kernel<E, T>, sm); ofdm_demod_kernel<E, T><<<grid, block, sm, st>>>(tb, p); } while (0)
+    if (fft_mode == 0) { if (tap) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (tap) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
 }
 

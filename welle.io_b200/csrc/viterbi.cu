@@ -282,15 +282,6 @@ template <int VIT_STAGES>
 __global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
 viterbi_kernel(ViterbiParams p) { viterbi_cta<VIT_STAGES>(p, blockIdx.x); }
 
-// several independent codeword sets (FIC + one per selected sub-channel slot) in one launch, so that their CTAs share the SMs
-template <int VIT_STAGES>
-__global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
-viterbi_batch_kernel(ViterbiBatch b)
-{
-    int k = 0;
-    while (k + 1 < b.n && (int)blockIdx.x >= b.cta_end[k]) k++;
-    viterbi_cta<VIT_STAGES>(b.p[k], (int)blockIdx.x - (k ? b.cta_end[k - 1] : 0));
-}
 
 // one thread per frame: CRC of the 12 FIBs (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80)
 __global__ void fic_crc_kernel(const uint8_t* __restrict__ fibs, const int32_t* __restrict__ active, int n_frames, int32_t* __restrict__ mask_out)
@@ -383,18 +374,6 @@ void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
     }
 }
 
-void launch_viterbi_batch(ViterbiBatch& b, cudaStream_t st, int stages)
-{
-    int total = 0;
-    for (int k = 0; k < b.n; k++) { total += (b.p[k].n_cw + VIT_THREADS - 1) / VIT_THREADS; b.cta_end[k] = total; b.p[k].one = 1u; }
-    if (!total) return;
-    if (stages == 1) {
-        viterbi_batch_kernel<1><<<total, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(b);
-    } else {
-        cudaFuncSetAttribute(viterbi_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemT<3>));
-        viterbi_batch_kernel<3><<<total, VIT_THREADS, sizeof(VitSmemT<3>), st>>>(b);
-    }
-}
 
 size_t vit_dec_bytes(int n_cw, int nsteps) { return (size_t)((n_cw + VIT_THREADS - 1) / VIT_THREADS) * nsteps * VIT_THREADS * sizeof(uint2); }
 

@@ -42,8 +42,6 @@ struct ViterbiParams {
     uint32_t one;                     // = 1 (set by the launcher; keeps a multiply-add opaque to the assembler, see viterbi_core.cuh)
 };
 
-struct ViterbiBatch { int n; ViterbiParams p[5]; int cta_end[5]; };
-void launch_viterbi_batch(ViterbiBatch& b, cudaStream_t st, int stages = 3);
 
 int vit_row_words(int nsteps);
 size_t vit_dec_bytes(int n_cw, int nsteps);
