@@ -1,0 +1,40 @@
+"""The host glue (welle.io_b200/host: RadioReceiver surface, worker loop, service database, callbacks, .msc dump) end to end on the CPU,
+with a TEST DOUBLE of the C ABI (tests/mock_backend/mock_dab_b200.c: hands out the oracle's frame records) in place of libdab_b200.so.
+The double is compiled into a temporary directory and only this test points the dynamic loader at it; the same flow runs against the real
+GPU library in tests/test_gpu_glue.py."""
+import os
+import subprocess
+
+import numpy as np
+
+import dabtx
+from conftest import ROOT
+
+
+def test_radio_receiver_glue_with_mock_backend(oracle, tmp_path):
+    exe = os.path.join(ROOT, "welle.io_b200", "glue_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "welle.io_b200", "host")])
+    mock = tmp_path / "libdab_b200.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(mock), os.path.join(ROOT, "tests", "mock_backend", "mock_dab_b200.c"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    tx = dabtx.DabTx(seed=0xBEEF)
+    iq = tx.frames(14)
+    f = tmp_path / "in.cf32"
+    iq.tofile(f)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(tmp_path), DABB_MOCK_IQ=str(f))
+    out = subprocess.run([exe, str(f), str(tmp_path / "o"), "12"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    summary = dict(kv.split("=") for kv in out.stdout.split())
+    fibs = np.fromfile(tmp_path / "o.fibs", np.uint8).reshape(-1, 33)
+    msc = np.fromfile(tmp_path / "o.msc", np.uint8)
+    prot = oracle.prot_eep(96, 1, 3)
+    o = oracle.rx_run(iq, prot=prot, start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    # every FIB of every frame reaches onFIBDecodeSuccess, bit for bit, and the service database built from them lists the one service
+    n = min(len(fibs), len(o["fibs"]))
+    assert n >= 12 * 10 and np.array_equal(fibs[:n], o["fibs"][:n]) and fibs[:, 0].all()
+    assert summary["selected"] == "1" and int(summary["services"]) == 1 and int(summary["syncs"]) == 1
+    # playSingleProgramme (from inside the 12th FIB callback) selected the sub-channel FIG 0/1 + 0/2 describe: the dump holds the logical frames
+    m = min(len(msc), len(o["msc"]))
+    assert m >= 288 * 20 and np.array_equal(msc[:m], o["msc"][:m])
+    assert int(summary["logical_frames"]) == len(msc) // 288
