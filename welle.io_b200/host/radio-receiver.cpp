@@ -168,6 +168,11 @@ struct RadioReceiver::Impl {
                  * without a null start over two frames further on */
                 if (acq_need < 5 * TF) acq_need += TF;
                 else { pos += 2 * TF; acq_need = 3 * TF; dabb_stream_reset(ctx, 0, 1, pos); }
+            } else {
+                /* DABB_FRAME_NEED_SAMPLES cannot happen (the loop above always supplies the samples a frame needs); if the library and the
+                 * glue ever disagree about that number, stop instead of spinning */
+                rci.onMessage(message_level_t::Error, "B200 backend", "frame needs more samples than the glue supplied");
+                failed = true; break;
             }
         }
         if (failed) { running = false; rci.onInputFailure(); }
