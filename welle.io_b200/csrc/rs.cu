@@ -332,8 +332,7 @@ rs_superframes_kernel(uint8_t* sfs, int sf_len, int32_t* info, const uint8_t* gf
 void launch_superframe(const SuperframeParams& p, cudaStream_t st)
 {
     const size_t smem = 2 * (size_t)p.window_pitch;
-    static size_t configured = 0;
-    if (smem > configured) { cudaFuncSetAttribute(superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(superframe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     // per device: no caching across contexts
     superframe_kernel<<<p.n_streams, SF_THREADS, smem, st>>>(p);
 }
 
