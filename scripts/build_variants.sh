@@ -1,0 +1,22 @@
+#!/bin/bash
+# Builds experimental variants of libdab_b200.so (compile-time switches) next to the repo root as gpurun_exp_<name>.so (git-ignored; they
+# travel to the GPU box with the snapshot).  Run on the CPU box, then on the GPU:   bash scripts/gpu_variants.sh
+#   pairs     -DDABB_DEMAP_PAIRS           two carriers per packed reciprocal chain in the demap   (round 1: -1 % on ofdm_demod_kernel)
+#   cta6      -DDEMOD_CTAS_PER_SM=6        80 registers (spills) - only useful together with a smaller shared-memory footprint
+#   vit64     -DVIT_THREADS_N=64           Viterbi CTAs of 64 codewords                              (round 1: no change)
+#   nof32x2   -DDABB_NO_F32X2              scalar fp32 arithmetic (the pre-packed baseline)
+set -eu
+cd "$(dirname "$0")/../welle.io_b200/csrc"
+make -s
+FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-ffp-contract=off"
+build() {   # name, source, macro
+    nvcc $FLAGS $3 -c $2.cu -o build/$2_$1.o
+    objs=""
+    for o in api ofdm viterbi rs tables; do if [ $o = $2 ]; then objs="$objs build/$2_$1.o"; else objs="$objs build/$o.o"; fi; done
+    nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../gpurun_exp_$1.so $objs -lcudart
+    echo "built gpurun_exp_$1.so"
+}
+build pairs ofdm -DDABB_DEMAP_PAIRS
+build cta6 ofdm -DDEMOD_CTAS_PER_SM=6
+build vit64 viterbi -DVIT_THREADS_N=64
+build nof32x2 ofdm -DDABB_NO_F32X2
