@@ -547,6 +547,7 @@ struct FibRecorder : RadioControllerInterface {
     const uint16_t* eid = nullptr;
 };
 std::string hexs(const std::string& s) { std::string o; char t[4]; for (unsigned char c : s) { snprintf(t, sizeof t, "%02x", c); o += t; } return o; }
+std::string short_hex(const DabLabel& l) { for (unsigned char c : l.fig1_label) if (c >= 0x7B || c < 0x20 || c == 0x24 || c == 0x5C || c == 0x5E || c == 0x60) return "-"; return hexs(l.fig1_shortlabel_utf8()); }
 std::string ext_dump(const char* head, const DabLabel& l)
 {
     if (l.segments.empty() && l.segment_count == 0) return std::string();
@@ -570,11 +571,12 @@ extern "C" int ref_fib_dump(const uint8_t* fibs, int n, char* out, int cap)
     }
     std::string o = rec.log; char t[256];
     const DabLabel el = fp.getEnsembleLabel();
-    snprintf(t, sizeof t, "E %u %u %d %u [%s]\n", fp.getEnsembleId(), fp.getEnsembleEcc(), (int)el.charset, el.fig1_flag, hexs(el.fig1_label).c_str()); o += t;
+    snprintf(t, sizeof t, "E %u %u %d %u [%s] [%s]\n", fp.getEnsembleId(), fp.getEnsembleEcc(), (int)el.charset, el.fig1_flag, hexs(el.fig1_label).c_str(), short_hex(el).c_str()); o += t;
     o += ext_dump("XE 0 0", el);
     const auto services = fp.getServiceList();
     for (const auto& s : services) {
-        snprintf(t, sizeof t, "S %u %d %d %d %u [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hexs(s.serviceLabel.fig1_label).c_str()); o += t;
+        snprintf(t, sizeof t, "S %u %d %d %d %u [%s] [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hexs(s.serviceLabel.fig1_label).c_str(),
+                 short_hex(s.serviceLabel).c_str()); o += t;
         snprintf(t, sizeof t, "XS %u 0", s.serviceId); o += ext_dump(t, s.serviceLabel);
     }
     for (const auto& s : services) for (const auto& c : fp.getComponents(s)) {

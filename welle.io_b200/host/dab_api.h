@@ -52,6 +52,13 @@ struct DabLabel {
     /* the EBU Latin -> UTF-8 table is a UI concern and not part of this backend: bytes >= 0x80 (and the few EBU code points below
      * 0x80 that differ from ASCII) are returned as they are */
     std::string fig1_label_utf8() const { return fig1_label; }
+    /* the abbreviated label: the characters whose bit (MSB = first character) is set in the 16-bit flag field (EN 300 401 5.2.2.3) */
+    std::string fig1_shortlabel_utf8() const
+    {
+        std::string o;
+        for (size_t i = 0; i < fig1_label.size() && i < 16; i++) if (fig1_flag & (0x8000u >> i)) o += fig1_label[i];
+        return o;
+    }
 
     /* extended label from FIG 2 segments (UTF-8 or UCS-2), same fields as the reference (backend/dab-constants.h:88-118) */
     std::map<int, std::vector<uint8_t>> segments;

@@ -82,10 +82,11 @@ public:
     std::string dump() const
     {
         std::string o; char t[256];
-        snprintf(t, sizeof t, "E %u %u %d %u [%s]\n", eid, ecc, (int)ensLabel.charset, ensLabel.fig1_flag, hex(ensLabel.fig1_label).c_str()); o += t;
+        snprintf(t, sizeof t, "E %u %u %d %u [%s] [%s]\n", eid, ecc, (int)ensLabel.charset, ensLabel.fig1_flag, hex(ensLabel.fig1_label).c_str(), shortHex(ensLabel).c_str()); o += t;
         o += extDump("XE 0 0", ensLabel);
         for (const auto& s : services) {
-            snprintf(t, sizeof t, "S %u %d %d %d %u [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hex(s.serviceLabel.fig1_label).c_str()); o += t;
+            snprintf(t, sizeof t, "S %u %d %d %d %u [%s] [%s]\n", s.serviceId, s.language, s.programType, (int)s.serviceLabel.charset, s.serviceLabel.fig1_flag, hex(s.serviceLabel.fig1_label).c_str(),
+                     shortHex(s.serviceLabel).c_str()); o += t;
             snprintf(t, sizeof t, "XS %u 0", s.serviceId); o += extDump(t, s.serviceLabel);
         }
         for (const auto& s : services) for (const auto& c : components) {       /* grouped per service like getComponents() */
@@ -117,6 +118,8 @@ private:
         }
         return v;
     }
+    /* short label, only for labels whose characters are plain ASCII (the EBU Latin -> UTF-8 conversion is not part of this backend) */
+    static std::string shortHex(const DabLabel& l) { for (unsigned char c : l.fig1_label) if (c >= 0x7B || c < 0x20 || c == 0x24 || c == 0x5C || c == 0x5E || c == 0x60) return "-"; return hex(l.fig1_shortlabel_utf8()); }
     static std::string hex(const std::string& s) { std::string o; char t[4]; for (unsigned char c : s) { snprintf(t, sizeof t, "%02x", c); o += t; } return o; }
     static std::string extDump(const char* head, const DabLabel& x)
     {
