@@ -233,7 +233,6 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--coresident", action="store_true")
     ap.add_argument("--cfo-hz", type=float, default=50.0, help="carrier offset of the secondary 'oscillator active' measurement (0 = skip); must keep the 5-frame ring periodic (multiples of 1/0.48 s)")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -293,7 +292,7 @@ def main():
     torch.cuda.synchronize()
     log(f"input ready: {S} streams x {BUF_LEN} samples")
 
-    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU, coresident=a.coresident)
+    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
     ctx.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
     ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)
 

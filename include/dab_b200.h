@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DABB_ABI_VERSION 2
+#define DABB_ABI_VERSION 3
 
 enum {
     DABB_OK = 0,
@@ -46,6 +46,10 @@ typedef struct dabb_ctx dabb_ctx;
  * factorisation, separate multiply/add roundings); DABB_FFT_FMA lets the compiler contract to FMA
  * (<= 1e-6 relative difference, faster). */
 enum { DABB_FFT_EXACT = 0, DABB_FFT_FMA = 1 };
+/* Oscillator arithmetic: DABB_NCO_EXACT reproduces every entry of the reference's 2 048 000-entry table bit for bit (verified
+ * exhaustively at dabb_create); DABB_NCO_FAST evaluates the same phase with fp32 sincospi (each oscillator sample within ~1e-6 of
+ * the table value: soft-decision intermediates within 1e-4 relative, decoded FIC/MSC bytes unchanged in the tests). */
+enum { DABB_NCO_EXACT = 0, DABB_NCO_FAST = 1 };
 
 /* RadioReceiverOptions::fftPlacementMethod / freqsyncMethod (backend/radio-receiver-options.h:35-64).  0 is the reference's
  * default in both enums (the reference's own enumerator values differ: see INTEGRATION.md for the mapping). */
@@ -65,7 +69,9 @@ typedef struct {
     int32_t ofdm_groups;        /* CTAs per frame in the OFDM kernel (divisor of 75), 0 -> chosen from n_streams */
     int32_t fft_placement;      /* DABB_PLACEMENT_* (PhaseReference::findIndex variant) */
     int32_t freqsync_method;    /* DABB_FREQSYNC_* (OFDMProcessor::processPRS variant) */
-    int32_t reserved[4];
+    int32_t nco_mode;           /* DABB_NCO_*: arithmetic of the frequency-correcting oscillator (ofdm-processor.cpp:92-94,211-214) */
+    int32_t ofdm_tail_split;    /* 0: automatic (large batches cut their last frames into short CTAs), -1: off */
+    int32_t reserved[2];
 } dabb_config;
 
 /* replaces: RadioReceiver::setReceiverOptions (backend/radio-receiver.cpp:119-124): takes effect from the next frame */

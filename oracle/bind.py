@@ -200,7 +200,7 @@ class Oracle:
         n = self.lib.orc_rx_run(rx, _p(iq), C.c_long(len(iq)), _p(fibs), C.c_long(12 * nfr), C.byref(nf_), _p(msc), C.c_long(len(msc)), C.byref(nm_),
                                 _p(rs), C.c_long(4 * nfr), C.byref(nr_), fi, C.c_long(nfr), _p(soft) if want_soft else None, C.c_long(want_soft))
         self.lib.orc_rx_free(rx)
-        info = [dict(start_index=fi[i].start_index, fine=fi[i].fine, coarse=fi[i].coarse, pos=fi[i].frame_pos) for i in range(n)]
+        info = [dict(start_index=fi[i].start_index, fine=fi[i].fine, coarse=fi[i].coarse, pos=fi[i].frame_pos, snr_raw=fi[i].snr_raw) for i in range(n)]
         out = dict(frames=n, fibs=fibs[:33 * nf_.value].reshape(-1, 33), msc=msc[:nm_.value], rs=rs[:2 * nr_.value].reshape(-1, 2), info=info)
         if want_soft:
             out["soft"] = soft.reshape(want_soft, 75, 3072)[:min(n, want_soft)]

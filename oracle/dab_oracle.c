@@ -413,11 +413,17 @@ static void demap_symbol(const cf* X, cf* ref, int8_t* soft, float* r1s)
     }
 }
 
-void orc_ofdm_demod_frame(const float* prs, const float* syms, int8_t* soft, float* r1s)
+int orc_snr(const float* spec);
+void orc_ofdm_demod_frame2(const float* prs, const float* syms, int8_t* soft, float* r1s, int* snr);
+void orc_ofdm_demod_frame(const float* prs, const float* syms, int8_t* soft, float* r1s) { orc_ofdm_demod_frame2(prs, syms, soft, r1s, NULL); }
+
+/* also returns OfdmDecoder::get_snr(fft_buffer, 1) of the phase reference symbol's spectrum (ofdm-decoder.cpp:144-160) */
+void orc_ofdm_demod_frame2(const float* prs, const float* syms, int8_t* soft, float* r1s, int* snr)
 {
     ensure_tables();
     cf ref[ORC_TU], X[ORC_TU];
     orc_fft(ORC_TU, prs, (float*)ref, 0);
+    if (snr) *snr = orc_snr((const float*)ref);
     for (int l = 1; l < ORC_L; l++) {
         orc_fft(ORC_TU, syms + 2 * ((size_t)(l - 1) * ORC_TS + ORC_TG), (float*)X, 0);
         demap_symbol(X, ref, soft + (size_t)(l - 1) * 2 * ORC_K, r1s ? r1s + (size_t)(l - 1) * 2 * ORC_K : NULL);
@@ -1000,7 +1006,8 @@ long orc_rx_run(orc_rx_t* r, const float* iq, long nsamples,
             }
         }
         /* ---- decoder thread work for this frame (ofdm-decoder.cpp:93-130) ---- */
-        orc_ofdm_demod_frame((const float*)prsbuf, (const float*)syms, soft, NULL);
+        int snr_raw = 0;
+        orc_ofdm_demod_frame2((const float*)prsbuf, (const float*)syms, soft, NULL, &snr_raw);
         if (soft_tap && nf < soft_cap_frames) memcpy(soft_tap + (size_t)nf * 75 * 3072, soft, 75 * 3072);
         {
             uint8_t fb[12 * 256], ok[12];
@@ -1032,7 +1039,7 @@ long orc_rx_run(orc_rx_t* r, const float* iq, long nsamples,
         }
         /* ---- back on the OFDM thread ---- */
         r->fine = (int16_t)((double)r->fine + 0.1 * (double)atan2f(fc.i, fc.r) / M_PI * (ORC_CARRIER_DIFF / 2));
-        if (finfo && nf < finfo_cap) { finfo[nf].start_index = start; finfo[nf].fine = r->fine; finfo[nf].coarse = r->coarse; finfo[nf].snr_raw = 0; finfo[nf].frame_pos = fpos; }
+        if (finfo && nf < finfo_cap) { finfo[nf].start_index = start; finfo[nf].fine = r->fine; finfo[nf].coarse = r->coarse; finfo[nf].snr_raw = snr_raw; finfo[nf].frame_pos = fpos; }
         nf++; r->nframes++;
         if (!rx_get(r, &src, nullsym, ORC_TNULL, r->coarse + r->fine)) goto done;
         if (r->fine > ORC_CARRIER_DIFF / 2) { r->coarse += ORC_CARRIER_DIFF; r->fine -= ORC_CARRIER_DIFF; }

@@ -24,7 +24,7 @@ def test_exports_match_header():
     for f in fns:
         assert hasattr(lib, f), f"{f} declared in include/dab_b200.h but not exported"
     assert sorted(pkg.EXPORTS) == fns
-    assert lib.dabb_abi_version() == 2
+    assert lib.dabb_abi_version() == 3
 
 
 def test_struct_sizes():

@@ -38,3 +38,36 @@ def test_radio_receiver_glue(oracle, tmp_path):
     # one impulse response, one set of (L-1) K / 96 constellation points and one null symbol per decoded frame
     nfr = len(fibs) // 12
     assert int(summary["cirs"]) == int(summary["consts"]) == int(summary["nulls"]) == nfr and summary["tapsizes"] == "1"
+
+
+def test_batch_decode_on_gpu(oracle, tmp_path):
+    """welle.io_b200/batch_decode (native multi-file driver over the C ABI + the service database) on the real library: three
+    recordings of different length, start offset and sub-channel protection decoded in lock-step; every .fic / .msc dump equals the
+    oracle's for that recording (the same flow runs on the test double in tests/test_glue_mock.py)."""
+    exe = os.path.join(ROOT, "welle.io_b200", "batch_decode")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "welle.io_b200", "host")])
+    specs = [dict(seed=0x11, n=12, kw={}, pad=0), dict(seed=0x22, n=9, kw=dict(bitrate=64, level=2), pad=5000), dict(seed=0x33, n=14, kw={}, pad=777)]
+    files, sigs = [], []
+    for k, sp in enumerate(specs):
+        tx = dabtx.DabTx(seed=sp["seed"], **sp["kw"])
+        iq = np.concatenate([np.zeros(sp["pad"], np.complex64), tx.frames(sp["n"])])
+        f = tmp_path / f"rec{k}.iq"
+        iq.tofile(f); files.append(str(f)); sigs.append(iq)
+    outdir = tmp_path / "out"; outdir.mkdir()
+    run = subprocess.run([exe, "--out", str(outdir)] + files, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    lines = run.stdout.strip().splitlines()
+    assert len(lines) == 3
+    for k, sp in enumerate(specs):
+        fibs = np.fromfile(outdir / f"rec{k}.iq.fic", np.uint8).reshape(-1, 33)
+        msc = np.fromfile(outdir / f"rec{k}.iq.msc", np.uint8)
+        br = sp["kw"].get("bitrate", 96); lv = sp["kw"].get("level", 3)
+        prot = oracle.prot_eep(br, 1, lv)
+        o_fic = oracle.rx_run(sigs[k], disable_coarse=True)
+        n = min(len(fibs), len(o_fic["fibs"]))
+        assert n >= 12 * (sp["n"] - 3) and np.array_equal(fibs[:n], o_fic["fibs"][:n]), k
+        o = oracle.rx_run(sigs[k], prot=prot, start_cu=0, len_cu=dabtx.eep_cu(br, True, lv), select_after_frames=1, disable_coarse=True)
+        m = min(len(msc), len(o["msc"]))
+        assert m >= 3 * br * 8 and np.array_equal(msc[:m], o["msc"][:m]), k
+        assert f"bitrate={br}" in lines[k] and "service=0x" in lines[k]

@@ -268,3 +268,43 @@ def test_closed_loop_multipath_offset_noise(oracle, ref, tmp_path):
     assert k >= 288 * 10 and np.array_equal(m["msc"][:k], e["msc"][:k])
     r = min(len(m["rs"]), len(e["rs"]))
     assert r >= 2 and np.array_equal(m["rs"][:r], e["rs"][:r])
+
+
+def test_snr_estimate(oracle, ref, tmp_path):
+    """OfdmDecoder::get_snr (ofdm-decoder.cpp:240-265) through the only tap the reference has for it: onSNR, the value
+    snr = 0.7 snr + 0.3 get_snr(PRS spectrum) reported after every 11th frame (:144-160).  Replaying that recursion over the oracle's
+    per-frame values must give the reference's floats."""
+    tx = dabtx.DabTx(seed=0x5A)
+    s = tx.frames(36)
+    sp = float(np.mean(np.abs(s[3000:190000]) ** 2))
+    iq = s.copy()
+    for k, db in enumerate((24.0, 9.0, 16.0, 6.0, 12.0, 20.0)):          # the noise level changes every six frames
+        seg = slice(6 * k * TF, 6 * (k + 1) * TF)
+        iq[seg] = dabtx.add_awgn(s[seg], db, seed=30 + k, signal_power=sp)
+    e = ref.e2e(iq, disable_coarse=True, select_at_fib=24, dump_path=str(tmp_path / "snr.msc"))
+    m = oracle.rx_run(iq, disable_coarse=True)
+    raw = [i["snr_raw"] for i in m["info"]]
+    assert len(set(raw)) >= 4 and all(0 <= r <= 40 for r in raw), raw
+    snr, count, rep = np.float32(0), 0, []
+    for r in raw:
+        snr = np.float32(0.7 * float(snr) + 0.3 * r)
+        count += 1
+        if count > 10:
+            rep.append(snr); count = 0
+    k = min(len(rep), len(e["snr"]))
+    assert k >= 2 and np.array_equal(np.array(rep[:k], np.float32), e["snr"][:k]), (rep, e["snr"])
+
+
+def test_reacquisition_after_gap(oracle, ref, tmp_path):
+    """a recording with a hole (signal, 1.3 frames of near-silence, signal at an unrelated timing): SyncOnPhase fails, the null search
+    runs again from the running signal level (ofdm-processor.cpp:166,215,347-350) - FIBs like the reference's over the whole run"""
+    tx = dabtx.DabTx(seed=0x6B)
+    s = tx.frames(22)
+    a, b = s[:9 * TF + 40000], s[11 * TF - 777:]
+    iq = np.concatenate([a, np.full(int(1.3 * TF), 1e-5 + 0j, np.complex64), b]).astype(np.complex64)
+    e = ref.e2e(iq, disable_coarse=True, select_at_fib=1 << 30, dump_path=str(tmp_path / "gap.msc"))
+    m = oracle.rx_run(iq, disable_coarse=True)
+    n = min(len(m["fibs"]), len(e["fibs"]))
+    assert n >= 12 * 14 and np.array_equal(m["fibs"][:n], e["fibs"][:n])
+    ok = m["fibs"][:n, 0]
+    assert ok[:12 * 6].all() and ok[-24:].all() and not ok.all()          # locked, lost, locked again

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -57,13 +58,13 @@ struct dabb_ctx {
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
     int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
-    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr;
-    int8_t* d_soft = nullptr; uint32_t* d_fic_rows = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
+    int8_t* d_soft = nullptr; uint2* d_fic_steptab = nullptr; uint32_t* d_fic_stage_off = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
     dabb_frame_result* d_results = nullptr;
     // per slot
     struct Slot {
-        bool configured = false; ProtProfile prof{}; int nsteps = 0, nbits = 0, row_words = 0, flen = 0;
-        int16_t* d_map = nullptr; uint32_t* d_prbs_words = nullptr; uint32_t* d_rows = nullptr; int32_t* d_valid = nullptr;
+        bool configured = false; ProtProfile prof{}; int nsteps = 0, nbits = 0, frag_pitch = 0, flen = 0;
+        uint2* d_steptab = nullptr; uint32_t* d_stage_off = nullptr; uint32_t* d_prbs_words = nullptr; int8_t* d_frag = nullptr; int32_t* d_valid = nullptr;
         uint8_t* d_logical = nullptr; uint2* d_dec = nullptr; int8_t* d_ring = nullptr; uint8_t* d_window = nullptr; uint8_t* d_sf = nullptr; int32_t* d_info = nullptr;
     } slot[DABB_MAX_SUBCH];
     uint32_t* d_fic_prbs_words = nullptr;
@@ -71,7 +72,7 @@ struct dabb_ctx {
     float2* d_iq_stage = nullptr; size_t iq_stage_samples = 0; uint8_t* d_raw_stage = nullptr; size_t raw_stage_bytes = 0;
     // pinned host staging for results
     dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
-    int groups = 1;
+    int groups = 1; int fc_pitch = 1; int tail_frames = 0; int nco_fast = 0;
     const int32_t** d_info_tab = nullptr;
     // optional per-kernel timing: one event after every launch, durations = differences of consecutive events
     bool prof = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_name; size_t prof_used = 0;
@@ -167,16 +168,21 @@ __global__ void acquire_kernel(StreamState* st, const float2* iq, int64_t stride
         return true;
     };
     float l1;
-    int started = z.started;
-    if (!started) {
+    // Progress is kept: the state is written back at every point from which the search can be resumed exactly (after the warm-up and
+    // at the start of every attempt), so a buffer that ends in the middle of an attempt costs only that attempt, and eight failed
+    // attempts (no signal) end the call with the position advanced - the reference's notSynced loop keeps running the same way
+    // (ofdm-processor.cpp:253-323).
+    auto checkpoint = [&]() { z.started = 1; z.pos = pos + buf_start[s]; z.local_phase = lp; z.slevel = sl; st[s] = z; };
+    if (!z.started) {
         sl = 0.f;
-        for (int i = 0; i < TF / 2; i++) if (!get(0, l1)) return;   // not enough samples: leave the state untouched
-        started = 1;
+        for (int i = 0; i < TF / 2; i++) if (!get(0, l1)) return;   // not enough samples for the warm-up: state untouched
+        checkpoint();
     }
     const int32_t phase = z.coarse + z.fine;
     // local ring of the last 64 envelope values is enough for the 50-tap moving sum
     float env[64];
     for (int attempt = 0; attempt < 8; attempt++) {
+        checkpoint();
         int idx = 0; float cur = 0.f;
         for (int i = 0; i < 50; i++) { if (!get(0, l1)) return; env[idx & 63] = l1; cur = __fadd_rn(cur, l1); idx++; }
         int counter = 0; bool fail = false;
@@ -196,9 +202,7 @@ __global__ void acquire_kernel(StreamState* st, const float2* iq, int64_t stride
         z.acquired = 1;
         break;
     }
-    if (!z.acquired) return;
-    z.started = started; z.pos = pos + buf_start[s]; z.local_phase = lp; z.slevel = sl;
-    st[s] = z;
+    checkpoint();      // acquired: tracking starts here; not acquired: the next call continues the search from here
 }
 
 __global__ void plan_kernel(StreamState* st, StepScratch* scr, const int64_t* buf_start, int64_t buf_len, int S,
@@ -244,7 +248,7 @@ __global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_
     // coarse corrector (ofdm-processor.cpp:397-409): find_index_kernel evaluated processPRS where the FIC ratio asked for it
     if (coarse_corr) {
         const int corr = coarse_corr[s];
-        if (corr != 0 && corr != 100) { z.coarse += corr * 1000; if (abs(z.coarse) > 35000) z.coarse = 0; }
+        if (corr != 100) { z.coarse += corr * 1000; if (abs(z.coarse) > 35000) z.coarse = 0; }     // 100: not evaluated / no estimate (:404-408)
     }
     const int32_t p2 = z.coarse + z.fine;
     // phase applied to the first data-symbol sample = lp after 2048+idx samples, minus p2; expressed at index 2048
@@ -258,7 +262,7 @@ __global__ void post_sync_kernel(StreamState* st, StepScratch* scr, const int32_
 
 // lane A, right after the OFDM kernel: the part of OFDMProcessor::run that feeds the next frame's synchronisation
 // (fine corrector update :450-451, consumed samples, NCO phase, corrector wrap :478-486)
-__global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int groups, const float2* fc_part)
+__global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int groups /* partial sums per frame */, const float2* fc_part, const float* lvl_part)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -281,6 +285,16 @@ __global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int gro
         z.pos += (int64_t)TU + idx + 75 * (int64_t)TS + TNULL;
         if (z.fine > 500) { z.coarse += 1000; z.fine -= 1000; }
         else if (z.fine < -500) { z.coarse -= 1000; z.fine += 1000; }
+        // sLevel (ofdm-processor.cpp:166,215) is an IIR over EVERY sample read: exact while a stream searches (acquire_kernel), and
+        // while it tracks it follows the same recursion on a sub-sample (one magnitude per symbol and thread of the OFDM kernel,
+        // decayed per symbol) - only a re-acquisition after a sync loss ever reads it
+        if (lvl_part) {
+            float est = 0.f;
+            for (int g = 0; g < groups; g++) est += lvl_part[(int64_t)s * groups + g];
+            const float ln1ma = -1.000005e-5f;          // ln(1 - 1e-5)
+            const float n_frame = (float)(TU + idx + 75 * TS + TNULL);
+            z.slevel = z.slevel * expf(n_frame * ln1ma) + est * (1.0f - expf((float)TS * ln1ma)) * expf((float)TNULL * ln1ma);
+        }
         z.nframes++;
         c.r_fx = fx; c.r_fy = fy;
         st[s] = z;
@@ -421,6 +435,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     ctx->max_cu = cfg->max_subch_cu > 0 ? cfg->max_subch_cu : 144;
     ctx->groups = cfg->ofdm_groups > 0 ? cfg->ofdm_groups : (ctx->S >= 1024 ? 1 : (ctx->S >= 64 ? 5 : 25));
     if (75 % ctx->groups) ctx->groups = 1;
+    ctx->nco_fast = cfg->nco_mode == DABB_NCO_FAST;
     auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
@@ -429,7 +444,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     {
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lane B gets the higher priority: its CTAs take the SM resources lane A leaves free
         if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
-        ctx->ofdm_smem_floor = cfg->reserved[0] == 2 ? 50 * 1024 : 0;   // experimental co-residency cap (measured slower: off by default)
+        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 50 * 1024 : 0;   // experimental co-residency cap (measured slower: off by default)
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
@@ -440,6 +455,8 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     build_host_tables(*ctx->host);
     const int S = ctx->S;
     int rc = 0;
+    ctx->tail_frames = (cfg->ofdm_tail_split == 0 && ctx->groups == 1) ? ofdm_tail_frames(S) : 0;
+    ctx->fc_pitch = ctx->tail_frames ? 15 : ctx->groups;
     // tables
     float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
     if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
@@ -479,13 +496,19 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, 768, w);
         if ((rc = dalloc(ctx, &ctx->d_fic_prbs_words, w.size()))) return fail(rc);
         cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
+        // expansion tables of the decoder kernel for the FIC puncturing (fic-handler.cpp:144-191)
+        std::vector<uint2> steps; std::vector<uint32_t> soff;
+        build_vit_tables(ctx->host->fic_map, 774, steps, soff);
+        if ((rc = dalloc(ctx, &ctx->d_fic_steptab, steps.size())) || (rc = dalloc(ctx, &ctx->d_fic_stage_off, soff.size()))) return fail(rc);
+        cudaMemcpy(ctx->d_fic_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_fic_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice);
     }
     ctx->ring_pitch = ctx->max_cu * 64;
     if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fic_ratio, S)) || (rc = dalloc(ctx, &ctx->d_coarse, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
         (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_prs, 2 * (size_t)S)) ||
         (rc = dalloc(ctx, &ctx->d_nco_sync, 4 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_nco_frame, 8 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_active, 2 * (size_t)S)) ||
-        (rc = dalloc(ctx, &ctx->d_index, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_snr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fc, 2 * (size_t)S * ctx->groups)) ||
-        (rc = dalloc(ctx, &ctx->d_soft, 2 * (size_t)S * DABB_SOFT_PER_FRAME, false)) || (rc = dalloc(ctx, &ctx->d_fic_rows, (size_t)S * 4 * vit_row_words(774), false)) ||
+        (rc = dalloc(ctx, &ctx->d_index, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_snr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fc, 2 * (size_t)S * ctx->fc_pitch)) || (rc = dalloc(ctx, &ctx->d_lvl, 2 * (size_t)S * ctx->fc_pitch)) ||
+        (rc = dalloc(ctx, &ctx->d_soft, 2 * (size_t)S * DABB_SOFT_PER_FRAME + VIT_FRAG_SLACK, false)) ||
         (rc = dalloc(ctx, &ctx->d_fibs, (size_t)S * 12 * 32)) || (rc = dalloc(ctx, &ctx->d_crc, S)) || (rc = dalloc(ctx, &ctx->d_results, S)) ||
         (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)))
         return fail(rc);
@@ -564,18 +587,22 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
         sl.configured = false;
     }
     if (!sl.configured) {
-        sl.prof = prof; sl.nbits = 24 * prof.bitrate; sl.nsteps = sl.nbits + 6; sl.row_words = vit_row_words(sl.nsteps); sl.flen = 3 * prof.bitrate;
+        sl.prof = prof; sl.nbits = 24 * prof.bitrate; sl.nsteps = sl.nbits + 6; sl.frag_pitch = ctx->ring_pitch; sl.flen = 3 * prof.bitrate;
         std::vector<int16_t> map((size_t)sl.nsteps * 4);
         build_msc_map(*ctx->host, prof, map.data());
+        std::vector<uint2> steps; std::vector<uint32_t> soff;
+        build_vit_tables(map.data(), sl.nsteps, steps, soff);
         std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, sl.nbits, w);
         const int flen_pad = (sl.flen + 15) & ~15;
-        if ((rc = dalloc(ctx, &sl.d_map, map.size())) || (rc = dalloc(ctx, &sl.d_prbs_words, w.size())) || (rc = dalloc(ctx, &sl.d_rows, (size_t)S * 4 * sl.row_words, false)) ||
+        if ((rc = dalloc(ctx, &sl.d_steptab, steps.size())) || (rc = dalloc(ctx, &sl.d_stage_off, soff.size())) || (rc = dalloc(ctx, &sl.d_prbs_words, w.size())) ||
+            (rc = dalloc(ctx, &sl.d_frag, (size_t)S * 4 * sl.frag_pitch + VIT_FRAG_SLACK)) ||
             (rc = dalloc(ctx, &sl.d_valid, (size_t)S * 4)) || (rc = dalloc(ctx, &sl.d_logical, (size_t)S * 4 * flen_pad)) ||
             (rc = dalloc(ctx, &sl.d_window, (size_t)S * 5 * flen_pad)) || (rc = dalloc(ctx, &sl.d_sf, (size_t)S * 5 * flen_pad)) ||
             (rc = dalloc(ctx, &sl.d_info, (size_t)S * 16)))
             return rc;
         if (!sl.d_ring && (rc = dalloc(ctx, &sl.d_ring, (size_t)S * MSC_RING * ctx->ring_pitch))) return rc;
-        CK(cudaMemcpyAsync(sl.d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(sl.d_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(sl.d_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(sl.d_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         { void* q = nullptr; if (cudaMalloc(&q, vit_dec_bytes(S * 4, sl.nsteps)) != cudaSuccess) { ctx->err = "cudaMalloc(slot decisions)"; return DABB_E_NOMEM; } ctx->allocs.push_back(q); sl.d_dec = (uint2*)q; }
@@ -603,10 +630,11 @@ int dabb_remove_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
 static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint8_t* fibs, int32_t* crc, cudaStream_t st, uint2* dec)
 {
     int rc;
-    launch_fic_prep(ctx->dev, soft, soft_stride, active, n_frames, ctx->d_fic_rows, st);
-    if ((rc = check_launch(ctx, "fic_prep_kernel"))) return rc;
+    // FIC codeword (frame f, block b) = softbits [2304 b, 2304 b + 2304) of the frame's first three symbols (fic-handler.cpp:111-127):
+    // the decoder kernel reads them where the OFDM kernel wrote them and de-punctures on the fly
     ViterbiParams vp{};
-    vp.rows = ctx->d_fic_rows; vp.row_words = vit_row_words(774); vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
+    vp.frag = soft; vp.cw_div = 4; vp.outer_stride = soft_stride; vp.inner_stride = 2304; vp.steptab = ctx->d_fic_steptab; vp.stage_off = ctx->d_fic_stage_off;
+    vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
     vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
     launch_viterbi(vp, st, ctx->vit_stages_now);
     if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
@@ -632,7 +660,7 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
     int32_t* d_nco_sync = ctx->d_nco_sync + (size_t)par * 2 * S; int32_t* d_nco_frame = ctx->d_nco_frame + (size_t)par * 4 * S;
     int32_t* d_active = ctx->d_active + (size_t)par * S; int32_t* d_index = ctx->d_index + (size_t)par * S; int32_t* d_snr = ctx->d_snr + (size_t)par * S;
-    float2* d_fc = ctx->d_fc + (size_t)par * S * ctx->groups;
+    float2* d_fc = ctx->d_fc + (size_t)par * S * ctx->fc_pitch; float* d_lvl = ctx->d_lvl + (size_t)par * S * ctx->fc_pitch;
     int8_t* d_soft = ctx->d_soft + (size_t)par * S * DABB_SOFT_PER_FRAME;
 
     const float2* iq = reinterpret_cast<const float2*>(io->iq);
@@ -691,12 +719,13 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
     post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, ctx->disable_coarse ? nullptr : ctx->d_coarse, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
-    op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.level = d_lvl; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    op.n_full = S - ctx->tail_frames; op.tail_groups = ctx->tail_frames ? 15 : 1; op.fc_pitch = ctx->fc_pitch; op.nco_fast = ctx->nco_fast;
     // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
     op.smem_floor = serial ? 0 : ctx->ofdm_smem_floor;
     launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, A);
     if ((rc = check_launch(ctx, "ofdm_demod_kernel"))) return rc;
-    advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->groups, d_fc);
+    advance_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, S, ctx->fc_pitch, d_fc, d_lvl);
     if ((rc = check_launch(ctx, "advance_kernel"))) return rc;
     if (ctx->d_null) {
         null_tap_kernel<<<S, 256, 0, A>>>(scr, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, ctx->d_null);
@@ -719,11 +748,12 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         MscCollectParams cp{}; cp.soft = d_soft; cp.soft_stride = DABB_SOFT_PER_FRAME; cp.active = d_active; cp.slots = ctx->d_slots; cp.n_slots = ctx->n_slots; cp.slot = k; cp.ring = sl.d_ring; cp.ring_pitch = ctx->ring_pitch;
         launch_msc_collect(cp, S, B);
         if ((rc = check_launch(ctx, "msc_collect_kernel"))) return rc;
-        MscPrepParams pp{}; pp.active = d_active; pp.slots = ctx->d_slots; pp.n_slots = ctx->n_slots; pp.slot = k; pp.ring = sl.d_ring; pp.ring_pitch = ctx->ring_pitch; pp.map = sl.d_map; pp.nsteps = sl.nsteps;
-        pp.rows = sl.d_rows; pp.row_words = sl.row_words; pp.valid = sl.d_valid;
-        launch_msc_prep(pp, S, B);
-        if ((rc = check_launch(ctx, "msc_prep_kernel"))) return rc;
-        ViterbiParams vp{}; vp.rows = sl.d_rows; vp.row_words = sl.row_words; vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
+        MscPrepParams pp{}; pp.active = d_active; pp.slots = ctx->d_slots; pp.n_slots = ctx->n_slots; pp.slot = k; pp.ring = sl.d_ring; pp.ring_pitch = ctx->ring_pitch;
+        pp.frag_out = sl.d_frag; pp.frag_pitch = sl.frag_pitch; pp.valid = sl.d_valid;
+        launch_msc_gather(pp, S, B);
+        if ((rc = check_launch(ctx, "msc_gather_kernel"))) return rc;
+        ViterbiParams vp{}; vp.frag = sl.d_frag; vp.cw_div = 1; vp.outer_stride = sl.frag_pitch; vp.inner_stride = 0; vp.steptab = sl.d_steptab; vp.stage_off = sl.d_stage_off;
+        vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
         launch_viterbi(vp, B, ctx->vit_stages_now);
         if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
@@ -827,7 +857,7 @@ int dabb_ofdm_demod(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_
     sync_all(ctx);
     OfdmParams op{}; op.iq = reinterpret_cast<const float2*>(iq); op.stride = stride; op.prs_start = prs_start; op.active = nullptr; op.soft = soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = reinterpret_cast<float2*>(r1); op.freqcorr = reinterpret_cast<float2*>(fc); op.snr = nullptr; op.n_frames = n;
-    op.groups = (fc || n >= 1024) ? 1 : (n >= 64 ? 5 : 25); op.sym_per_cta = 75 / op.groups;
+    op.groups = (fc || n >= 1024) ? 1 : (n >= 64 ? 5 : 25); op.sym_per_cta = 75 / op.groups; op.n_full = n; op.tail_groups = 1; op.fc_pitch = op.groups; op.nco_fast = ctx->nco_fast;
     int32_t* nco4 = nullptr;
     if (nco) {
         // expand {lp applied to PRS sample 0, Hz} to the 4-entry form of the pipeline (same increment for PRS and symbols)
@@ -886,28 +916,53 @@ int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt)
     return DABB_OK;
 }
 
+// stage-level helper: the decoder kernel on n codewords of `frag` punctured softbits each (device, any alignment / values): the input
+// is copied into a padded 16-byte pitched buffer with -128 mapped to -127 (same symbol after the reference's clamp)
+static int run_stage_viterbi(dabb_ctx* ctx, const int8_t* soft, int n_cw, int64_t in_stride, int frag, const int16_t* map, int nsteps, int nbits,
+                             const uint32_t* d_prbs_words, uint8_t* out, int64_t out_stride)
+{
+    std::vector<uint2> steps; std::vector<uint32_t> soff;
+    build_vit_tables(map, nsteps, steps, soff);
+    if ((int)soff.back() > frag) { ctx->err = "de-puncturing map consumes more softbits than provided"; return DABB_E_ARG; }
+    const int pitch = (frag + 15) & ~15;
+    uint2* d_steps = nullptr; uint32_t* d_soff = nullptr; int8_t* tmp = nullptr;
+    CK(cudaMalloc((void**)&d_steps, steps.size() * sizeof(uint2))); CK(cudaMalloc((void**)&d_soff, soff.size() * 4));
+    CK(cudaMalloc((void**)&tmp, (size_t)n_cw * pitch + VIT_FRAG_SLACK));
+    CK(cudaMemcpyAsync(d_steps, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_soff, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(tmp, 0, (size_t)n_cw * pitch + VIT_FRAG_SLACK, ctx->stream));
+    int rc = 0;
+    if (pitch == frag && in_stride == frag) { launch_clamp_copy(soft, tmp, (int64_t)n_cw * frag, ctx->stream); rc = check_launch(ctx, "clamp_copy_kernel"); }
+    else {
+        CK(cudaMemcpy2DAsync(tmp, pitch, soft, (size_t)in_stride, frag, n_cw, cudaMemcpyDeviceToDevice, ctx->stream));
+        launch_clamp_copy(tmp, tmp, (int64_t)n_cw * pitch, ctx->stream); rc = check_launch(ctx, "clamp_copy_kernel");
+    }
+    if (!rc) rc = ensure_dec(ctx, vit_dec_bytes(n_cw, nsteps));
+    if (!rc) {
+        ViterbiParams vp{}; vp.frag = tmp; vp.cw_div = 1; vp.outer_stride = pitch; vp.inner_stride = 0; vp.steptab = d_steps; vp.stage_off = d_soff;
+        vp.n_cw = n_cw; vp.nsteps = nsteps; vp.nbits = nbits; vp.dec = ctx->d_dec; vp.out = out; vp.out_stride = out_stride; vp.prbs_words = d_prbs_words; vp.valid = nullptr;
+        launch_viterbi(vp, ctx->stream);
+        rc = check_launch(ctx, "viterbi_kernel");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_steps); cudaFree(d_soff); cudaFree(tmp);
+    return rc;
+}
+
 int dabb_viterbi(dabb_ctx* ctx, const int8_t* soft, int32_t n_cw, int32_t nbits, uint8_t* bits_out)
 {
     if (!ctx || !soft || !bits_out || n_cw < 1 || nbits < 32 || (nbits % 32) || ((nbits + 6) % 6)) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
-    const int nsteps = nbits + 6, rw = vit_row_words(nsteps), ob = nbits / 8;
-    uint32_t* rows = nullptr; uint8_t* bytes = nullptr;
-    CK(cudaMalloc((void**)&rows, (size_t)n_cw * rw * 4));
+    const int nsteps = nbits + 6, ob = nbits / 8;
+    uint8_t* bytes = nullptr;
     CK(cudaMalloc((void**)&bytes, (size_t)n_cw * ob));
-    int rc = ensure_dec(ctx, vit_dec_bytes(n_cw, nsteps));
-    if (!rc) {
-        launch_sym_rows_from_soft(soft, n_cw, nsteps, rows, ctx->stream);
-        rc = check_launch(ctx, "sym_rows_from_soft_kernel");
-    }
-    if (!rc) {
-        ViterbiParams vp{}; vp.rows = rows; vp.row_words = rw; vp.n_cw = n_cw; vp.nsteps = nsteps; vp.nbits = nbits; vp.dec = ctx->d_dec; vp.out = bytes; vp.out_stride = ob; vp.prbs_words = nullptr; vp.valid = nullptr;
-        launch_viterbi(vp, ctx->stream);
-        rc = check_launch(ctx, "viterbi_kernel");
-    }
+    std::vector<int16_t> map((size_t)nsteps * 4);
+    std::fill(map.begin(), map.end(), (int16_t)0);                      // >= 0 = present: nothing punctured, the caller's zeros are softbit 0
+    int rc = run_stage_viterbi(ctx, soft, n_cw, (int64_t)nsteps * 4, nsteps * 4, map.data(), nsteps, nbits, nullptr, bytes, ob);
     if (!rc) { launch_unpack_bits(bytes, ob, n_cw, nbits, bits_out, ctx->stream); rc = check_launch(ctx, "unpack_bits_kernel"); }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(rows); cudaFree(bytes);
+    cudaFree(bytes);
     return rc;
 }
 
@@ -916,14 +971,10 @@ int dabb_fic_decode(dabb_ctx* ctx, const int8_t* soft, int32_t n_frames, uint8_t
     if (!ctx || !soft || !fib_out || !crc_mask_out || n_frames < 1) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
-    uint32_t* rows = nullptr;
-    uint32_t* save = ctx->d_fic_rows;
-    if (n_frames > ctx->S) { CK(cudaMalloc((void**)&rows, (size_t)n_frames * 4 * vit_row_words(774) * 4)); ctx->d_fic_rows = rows; }
-    int rc = ensure_dec(ctx, vit_dec_bytes(n_frames * 4, 774));
-    if (!rc) rc = run_fic(ctx, soft, 9216, nullptr, n_frames, fib_out, crc_mask_out, ctx->stream, ctx->d_dec);
+    // codeword (f, b) = softbits [9216 f + 2304 b, +2304)
+    int rc = run_stage_viterbi(ctx, soft, n_frames * 4, 2304, 2304, ctx->host->fic_map, 774, 768, ctx->d_fic_prbs_words, fib_out, 96);
+    if (!rc) { launch_fic_crc(fib_out, nullptr, n_frames, crc_mask_out, ctx->stream); rc = check_launch(ctx, "fic_crc_kernel"); }
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_fic_rows = save;
-    if (rows) cudaFree(rows);
     return rc;
 }
 
@@ -934,28 +985,18 @@ int dabb_msc_decode(dabb_ctx* ctx, const dabb_subchannel* sc, const int8_t* soft
     sync_all(ctx);
     ProtProfile prof;
     if (make_prot_profile(sc->bitrate, sc->short_form, sc->uep_level, sc->eep_profile_a, sc->eep_level, prof) < 0) { ctx->err = "unsupported protection profile"; return DABB_E_UNSUPPORTED; }
-    const int frag = sc->length_cu * 64, nbits = 24 * prof.bitrate, nsteps = nbits + 6, rw = vit_row_words(nsteps), flen = 3 * prof.bitrate;
+    const int frag = sc->length_cu * 64, nbits = 24 * prof.bitrate, nsteps = nbits + 6, flen = 3 * prof.bitrate;
     if (prof.in_bits > frag) { ctx->err = "protection profile needs more bits than the sub-channel holds"; return DABB_E_ARG; }
-    // build the de-puncturing map, expand on the device with a gather, then the common Viterbi path
     std::vector<int16_t> map((size_t)nsteps * 4);
     build_msc_map(*ctx->host, prof, map.data());
     std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, nbits, w);
-    int16_t* d_map = nullptr; uint32_t* d_w = nullptr; uint32_t* rows = nullptr;
-    CK(cudaMalloc((void**)&d_map, map.size() * 2)); CK(cudaMalloc((void**)&d_w, w.size() * 4)); CK(cudaMalloc((void**)&rows, (size_t)n * rw * 4));
-    CK(cudaMemcpy(d_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
-    int rc = ensure_dec(ctx, vit_dec_bytes(n, nsteps));
-    if (!rc) {
-        // expand on device: one thread per (cif, step)
-        launch_msc_expand(soft, n, frag, d_map, nsteps, rows, rw, ctx->stream);
-        rc = check_launch(ctx, "msc_expand_kernel");
-    }
-    if (!rc) {
-        ViterbiParams vp{}; vp.rows = rows; vp.row_words = rw; vp.n_cw = n; vp.nsteps = nsteps; vp.nbits = nbits; vp.dec = ctx->d_dec; vp.out = bytes_out; vp.out_stride = flen; vp.prbs_words = d_w; vp.valid = nullptr;
-        launch_viterbi(vp, ctx->stream);
-        rc = check_launch(ctx, "viterbi_kernel");
-    }
+    uint32_t* d_w = nullptr;
+    CK(cudaMalloc((void**)&d_w, w.size() * 4));
+    CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    // output rows are 3*bitrate bytes (a multiple of 4)
+    int rc = run_stage_viterbi(ctx, soft, n, frag, frag, map.data(), nsteps, nbits, d_w, bytes_out, flen);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_map); cudaFree(d_w); cudaFree(rows);
+    cudaFree(d_w);
     return rc;
 }
 

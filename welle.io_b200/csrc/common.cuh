@@ -34,9 +34,13 @@ struct OfdmParams {
     const int32_t* active;                       // [n] or nullptr: 0 = skip frame
     int8_t* soft; int64_t soft_stride;           // per frame stride in bytes (>= 75*3072)
     float2* r1;                                  // optional tap [n][75][1536]
-    float2* freqcorr;                            // optional [n][groups] partial CP correlation sums
+    float2* freqcorr;                            // optional [n][fc_pitch] partial CP correlation sums
+    float* level;                                // optional [n][fc_pitch] partial signal-level estimates (see advance_kernel in api.cu)
     int32_t* snr;                                // optional [n] get_snr value of the PRS
     int n_frames; int groups; int sym_per_cta;   // groups * sym_per_cta == 75
+    int n_full; int tail_groups;                 // frames >= n_full are cut into tail_groups CTAs each (tail_groups divides 75; 1 / 0 = off)
+    int fc_pitch;                                // freqcorr entries per frame (>= groups, tail_groups); 0 -> the larger of the two
+    int nco_fast;                                // DABB_NCO_FAST: fp32 oscillator (tolerance mode)
     int smem_floor;                              // request at least this much dynamic shared memory (caps CTAs/SM so that other kernels fit beside it)
 };
 
@@ -47,7 +51,7 @@ struct SyncParams {
     const int32_t* active;
     int32_t* index_out; float* cir_out; int n;
     // coarse frequency corrector (OFDMProcessor::processPRS, PatternOfZeros): evaluated for streams whose FIC success
-    // counter is below 5 (ofdm-processor.cpp:397); result = carrier offset, or 0 when not evaluated
+    // counter is below 5 (ofdm-processor.cpp:397); result = carrier offset, or 100 when not evaluated / no estimate
     const int32_t* fic_ratio; int32_t* coarse_out;
     int placement;      // DABB_PLACEMENT_*: 0 ThresholdBeforePeak, 1 StrongestPeak, 2 EarliestPeakWithBinning
     int freqsync;       // DABB_FREQSYNC_*: 0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS
@@ -55,6 +59,7 @@ struct SyncParams {
 
 int ofdm_init_constants();     // per-device constants of ofdm.cu (call once after cudaSetDevice)
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
+int ofdm_tail_frames(int n_frames);
 void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st);
 

@@ -79,6 +79,17 @@ __device__ __forceinline__ float2 mix_sample(float2 v, const DevTables& tb, int3
     return cmul_<true>(v, osc_value(tb, lp));   // std::complex product, separately rounded
 }
 
+// ---- tolerance-mode oscillator (DABB_NCO_FAST): fp32 sincospi of the exact integer phase.  osc(m) = e^{j 2 pi m / 2 048 000}
+// = (cospi, sinpi)(m / 1 024 000); m < 2^21 is exact in fp32, the quotient is rounded once (<= 6e-8 relative -> <= 4e-7 rad), sincospif
+// adds ~1e-7: every oscillator sample is within ~1e-6 of the reference's table value (north_star: soft intermediates within 1e-4).
+__device__ __forceinline__ float2 osc_fast(int32_t m)
+{
+    float s, c;
+    sincospif(__fmul_rn((float)m, 1.0f / 1024000.0f), &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ float2 cmul_fast(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
+
 __device__ __forceinline__ float block_sum(float v, float* red, int t)
 {
     // fixed-order reduction: lane tree, then the four warp results added in warp order
@@ -170,6 +181,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// (1 - 1e-5)^2552: what the reference's level tracker sLevel = 1e-5 |v|_1 + (1 - 1e-5) sLevel (ofdm-processor.cpp:166,215) forgets per symbol
+constexpr float LEVEL_DECAY_SYM = 0.97480279f;
 #ifndef DEMOD_CTAS_PER_SM
 #define DEMOD_CTAS_PER_SM 5
 #endif
@@ -181,6 +194,7 @@ struct __align__(16) DemodSmem {
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
     uint16_t sbuf[1536 + 128];        // (re | im << 8) per logical carrier: one 16-bit scatter store per carrier
+    float2 rtab[2][16];              // DABB_NCO_FAST: e^{-j theta((128 h + 256 c) Hz)} for the PRS / the data symbols
     float red[16];
     uint64_t full;
 };
@@ -191,10 +205,42 @@ struct __align__(16) DemodSmem {
 // With afc: also accumulates the fine-AFC correlation of this symbol, sum x[i] * conj(x[i - T_u]) over its last 504 samples
 // (ofdm-processor.cpp:436-442): those are the transform inputs n = 1544..2047, which the owning thread has just mixed, so only
 // the guard-interval partner (T_u samples earlier, at in[n - 2048]) is loaded and mixed here.
-template <bool EXACT>
+template <bool EXACT, bool FASTNCO>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
-                                                  const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc)
+                                                  const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc, const float2* rtab, float& l1_first)
 {
+    // l1_first: |re| + |im| of the thread's first (mixed) sample, the sub-sampled input of the running signal level (see advance_kernel)
+    if (FASTNCO && nco.mix) {
+        // sample n = t + 128 h + 256 c gets osc(lp - (128 h + 256 c) Hz) = osc(lp) * rtab[8 h + c]; the guard-interval correlation is
+        // taken on the raw samples: mixing multiplies every term x[i] conj(x[i - T_u]) by the same e^{-j theta(2048 Hz)}, applied
+        // once to the frame's sum at the end of the kernel
+        const float2 o0 = osc_fast(mod_rate64((int64_t)nco.lp0 - (idx0 + t) * (int64_t)nco.ph));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float2 x[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[c] = in[t + 128 * h + 256 * c];
+            if (afc) {
+#pragma unroll
+                for (int c = 6; c < 8; c++) {
+                    const int n = t + 128 * h + 256 * c;
+                    if (n >= TU - TG) {
+                        const float2 b = in[n - TU];
+                        fc.x += x[c].x * b.x + x[c].y * b.y;
+                        fc.y += x[c].y * b.x - x[c].x * b.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[c] = cmul_fast(x[c], cmul_fast(o0, rtab[8 * h + c]));
+            if (h == 0) l1_first = fabsf(x[0].x) + fabsf(x[0].y);
+            float2 y[8];
+            passA_block<EXACT, false>(x, y, sm.tw);
+#pragma unroll
+            for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
+        }
+        return;
+    }
     // one 8-point block at a time (load, oscillator, radix-2 + radix-4, store): keeps 8 instead of 16 inputs live while the
     // oscillator's double-precision temporaries are
     int32_t lp = 0;
@@ -230,6 +276,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
                 }
             }
         }
+        if (h == 0) l1_first = fabsf(x[0].x) + fabsf(x[0].y);
         float2 y[8];
         passA_block<EXACT, false>(x, y, sm.tw);
 #pragma unroll
@@ -254,18 +301,22 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     passC_ldg<EXACT, false>(v, t, tw_c5);
 }
 
-template <bool EXACT, bool TAP>
+template <bool EXACT, bool TAP, bool FASTNCO>
 __global__ void __launch_bounds__(OFDM_THREADS, DEMOD_CTAS_PER_SM)
 ofdm_demod_kernel(DevTables tb, OfdmParams p)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     DemodSmem& sm = *reinterpret_cast<DemodSmem*>(smraw);
     const int t = threadIdx.x;
-    const int f = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
+    // the first n_full frames are walked by `groups` CTAs each; the remaining (tail) frames are cut into tail_groups short CTAs, which
+    // are dispatched last and fill the SM slots the long CTAs free one by one at the end of the launch
+    int f, g, spc, ng;
+    if ((int)blockIdx.x < p.n_full * p.groups) { f = blockIdx.x / p.groups; g = blockIdx.x % p.groups; spc = p.sym_per_cta; ng = p.groups; }
+    else { const int r = blockIdx.x - p.n_full * p.groups; f = p.n_full + r / p.tail_groups; g = r % p.tail_groups; spc = 75 / p.tail_groups; ng = p.tail_groups; }
     if (p.active && !p.active[f]) return;
 
     const float2* src = p.iq + (int64_t)f * p.stride + p.prs_start[f];
-    const int l_first = 1 + g * p.sym_per_cta, l_last = l_first + p.sym_per_cta;   // data symbols [l_first, l_last)
+    const int l_first = 1 + g * spc, l_last = l_first + spc;   // data symbols [l_first, l_last)
 
     // sample range of symbol l relative to the first useful PRS sample: the PRS is [0,2048); symbol l >= 1 (guard first)
     // starts at 2048 + (l-1)*2552, its FFT window 504 samples later (ofdm-decoder.cpp:178-180)
@@ -287,6 +338,11 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
     const Nco ncoP = make_nco(p.nco ? p.nco[4 * f] : 0, p.nco ? p.nco[4 * f + 1] : 0);
     const Nco ncoS = make_nco(p.nco ? p.nco[4 * f + 2] : 0, p.nco ? p.nco[4 * f + 3] : 0);
+    if (FASTNCO && t < 32) {
+        const Nco& n = (t >> 4) ? ncoS : ncoP;
+        const int k = t & 15;
+        sm.rtab[t >> 4][k] = osc_fast(mod_rate64(-(int64_t)(128 * (k >> 3) + 256 * (k & 7)) * n.ph));
+    }
     const XIdx xi = make_xidx(t);
     // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
     int sidx[NSLOT];
@@ -296,6 +352,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
 
     float2 prev[NSLOT];
     float2 fc = make_float2(0.f, 0.f);
+    float lvl = 0.f;                                  // decayed sum of one sample magnitude per symbol and thread (signal level estimate)
     uint32_t parity = 0;
 
     for (int l = l_first - 1; l < l_last; l++) {
@@ -306,7 +363,9 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         mbar_wait(&sm.full, parity); parity ^= 1;
         const float2* in = sm.inbuf + shift;
         float2 v[16];
-        fft2048_from_smem<EXACT>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc);
+        float l1s;
+        fft2048_from_smem<EXACT, FASTNCO>(in + goff, s0 + goff, v, sm, t, xi, tw_c5, tb, nco, l >= l_first, fc, sm.rtab[l == 0 ? 0 : 1], l1s);
+        if (l >= l_first || l == 0) lvl = fmaf(lvl, LEVEL_DECAY_SYM, l1s);
         __syncthreads();                       // (1) inbuf fully consumed, pass-A results in xbuf
         if (t == 0 && l + 1 < l_last) {        // prefetch the next symbol while passes B, C and the demap run
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -385,7 +444,17 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     }
     if (p.freqcorr) {
         const float sx = block_sum(fc.x, sm.red, t), sy = block_sum(fc.y, sm.red, t);
-        if (t == 0) p.freqcorr[(int64_t)f * p.groups + g] = make_float2(sx, sy);
+        float2 sum = make_float2(sx, sy);
+        if (FASTNCO && ncoS.mix) sum = cmul_fast(sum, osc_fast(ncoS.u2048));      // x[i] conj(x[i - T_u]) of the mixed samples
+        if (t == 0) p.freqcorr[(int64_t)f * p.fc_pitch + g] = sum;
+        if (g == 0 && t > 0 && t < p.fc_pitch - ng + 1) p.freqcorr[(int64_t)f * p.fc_pitch + ng - 1 + t] = make_float2(0.f, 0.f);   // unused partial slots
+    }
+    if (p.level) {
+        // this CTA's share of the frame's level estimate, referred to the end of symbol 75: mean over the 128 sampled positions, decayed
+        // by the symbols that follow this CTA's last one
+        const float s = block_sum(lvl, sm.red, t);
+        if (t == 0) p.level[(int64_t)f * p.fc_pitch + g] = s * (1.0f / 128.0f) * powf(LEVEL_DECAY_SYM, (float)(76 - l_last));
+        if (g == 0 && t > 0 && t < p.fc_pitch - ng + 1) p.level[(int64_t)f * p.fc_pitch + ng - 1 + t] = 0.f;
     }
 }
 
@@ -686,7 +755,7 @@ find_index_kernel(DevTables tb, SyncParams p)
     }
     if (t == 0) p.index_out[f] = result;
     if (!p.coarse_out) return;
-    if (t == 0) p.coarse_out[f] = 0;
+    if (t == 0) p.coarse_out[f] = 100;          // 100 = not evaluated (OFDMProcessor::processPRS returns 100 for "no estimate" too)
     if (result < 0 || p.fic_ratio[f] * 10 >= 50) return;      // CTA-uniform
     coarse_estimate<EXACT>(tb, sm, src, result, nco, xi, t, p.freqsync, &p.coarse_out[f]);
 }
@@ -732,15 +801,37 @@ int ofdm_init_constants()
 #endif
 }
 
-void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st)
+void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p_in, int fft_mode, cudaStream_t st)
 {
-    const dim3 grid(p.n_frames * p.groups), block(OFDM_THREADS);
+    OfdmParams p = p_in;
+    if (p.tail_groups < 1 || 75 % p.tail_groups) { p.tail_groups = 1; }
+    if (p.n_full < 0 || p.n_full > p.n_frames || p.tail_groups == 1) p.n_full = p.n_frames;
+    if (p.fc_pitch < 1) p.fc_pitch = p.groups > p.tail_groups ? p.groups : p.tail_groups;
+    const dim3 grid(p.n_full * p.groups + (p.n_frames - p.n_full) * p.tail_groups), block(OFDM_THREADS);
     const size_t sm = sizeof(DemodSmem) > (size_t)p.smem_floor ? sizeof(DemodSmem) : (size_t)p.smem_floor;
-    const bool tap = p.r1 != nullptr;
-#define LAUNCH(E, T) do { set_smem(ofdm_demod_kernel<E, T>, sm); ofdm_demod_kernel<E, T><<<grid, block, sm, st>>>(tb, p); } while (0)
-    if (fft_mode == 0) { if (tap) LAUNCH(true, true); else LAUNCH(true, false); }
-    else { if (tap) LAUNCH(false, true); else LAUNCH(false, false); }
+    const bool tap = p.r1 != nullptr, fast = p.nco_fast != 0 && p.nco != nullptr;
+#define LAUNCH(E, T, F) do { set_smem(ofdm_demod_kernel<E, T, F>, sm); ofdm_demod_kernel<E, T, F><<<grid, block, sm, st>>>(tb, p); } while (0)
+#define LAUNCH_F(E, T) do { if (fast) LAUNCH(E, T, true); else LAUNCH(E, T, false); } while (0)
+    if (fft_mode == 0) { if (tap) LAUNCH_F(true, true); else LAUNCH_F(true, false); }
+    else { if (tap) LAUNCH_F(false, true); else LAUNCH_F(false, false); }
+#undef LAUNCH_F
 #undef LAUNCH
+}
+
+// how many frames of a launch of n frames (one CTA per frame) to cut into short CTAs: about half a residency's worth, so that the
+// short CTAs fill the slots the long ones leave as they finish (0 when the launch is too small for that to matter)
+int ofdm_tail_frames(int n_frames)
+{
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        set_smem(ofdm_demod_kernel<true, false, false>, sizeof(DemodSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ofdm_demod_kernel<true, false, false>, OFDM_THREADS, sizeof(DemodSmem));
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    if (n_frames < 2 * resident) return 0;
+    return resident / 2;
 }
 
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st)

@@ -1,41 +1,30 @@
 // viterbi.cu — batched K=7 rate-1/4 Viterbi for FIC and MSC codewords on sm_100a, plus the de-puncturing /
 // time-de-interleaving kernels that feed it.
 //
-//   fic_prep_kernel      FicHandler::processFicBlock/processFicInput de-puncturing (fic-handler.cpp:111-191)
 //   msc_collect_kernel   MscHandler::processMscBlock CIF slicing (msc-handler.cpp:129-158) into a residue-major ring
-//   msc_prep_kernel      DabAudio::run time de-interleaver (dab-audio.cpp:113-149) + EEP/UEP de-puncturing
-//                        (eep-protection.cpp:115-152, uep-protection.cpp:169-239)
-//   viterbi_kernel       Viterbi::deconvolve (viterbi.cpp:227-339) + energy de-dispersal (energy_dispersal.h:35-54,
+//   msc_gather_kernel    DabAudio::run time de-interleaver (dab-audio.cpp:113-149): the punctured fragment of one CIF, contiguous
+//   viterbi_kernel       de-puncturing (fic-handler.cpp:144-191, eep-protection.cpp:115-152, uep-protection.cpp:169-239) +
+//                        Viterbi::deconvolve (viterbi.cpp:227-339) + energy de-dispersal (energy_dispersal.h:35-54,
 //                        fic-handler.cpp:199-201) + MSB-first byte pack (decoder_adapter.cpp:57-67)
 //   fic_crc_kernel       check_CRC_bits per FIB (MathHelper.h:53-80)
 //
-// viterbi_kernel: one codeword per thread, 64 path metrics packed 2x16 bit in 32 registers (viterbi_core.cuh), the
-// de-punctured symbols of 24 trellis steps per thread are staged into shared memory with cp.async.bulk (TMA, one
-// 128-byte copy per thread and stage, completion on an mbarrier, 3-stage ring), decision words go to HBM/L2 as
-// 8 bytes per step per codeword and are read back by the same thread for the traceback.
-// Issue-slot bound (integer ACS); HBM traffic is ~4+16 bytes per trellis step.
+// viterbi_kernel: one codeword per thread, 64 path metrics packed 2x16 bit in 32 registers (viterbi_core.cuh).  The kernel reads
+// the PUNCTURED softbits (FIC: straight from the OFDM kernel's output; MSC: the gathered fragment): per 24 trellis steps every
+// thread stages the 16-byte aligned 128 bytes that hold its next <= 96 softbits into shared memory with cp.async.bulk (TMA,
+// completion on an mbarrier, 3-stage ring) and expands them itself - the puncturing pattern is the same for every codeword of a
+// launch, so the byte selector / mask / window-advance flag of each step come from one small table (build_vit_tables) and the
+// expansion of a step is PRMT + LOP3 + IADD.  Decision words go to HBM/L2 as 8 bytes per step per codeword and are read back by
+// the same thread for the traceback.  Issue-slot bound (integer ACS).
 #include "common.cuh"
 #include "viterbi_core.cuh"
 #include "viterbi.cuh"
+#include <vector>
 
 namespace dabb {
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint32_t sym4(uint32_t w)   // four int8 softbits -> four clamp(s+127, 0, 255) symbols
-{
-    return __vsubus4(w ^ 0x80808080u, 0x01010101u);
-}
-
-// one trellis step: four map entries (index into the punctured softbits or -1 = punctured -> softbit 0) -> four symbols
-__device__ __forceinline__ uint32_t gather_sym4(const int8_t* seg, uint2 m)
-{
-    const int i0 = (int16_t)(m.x & 0xFFFF), i1 = (int16_t)(m.x >> 16), i2 = (int16_t)(m.y & 0xFFFF), i3 = (int16_t)(m.y >> 16);
-    const uint32_t b0 = i0 >= 0 ? (uint8_t)seg[i0] : 0u, b1 = i1 >= 0 ? (uint8_t)seg[i1] : 0u, b2 = i2 >= 0 ? (uint8_t)seg[i2] : 0u, b3 = i3 >= 0 ? (uint8_t)seg[i3] : 0u;
-    return sym4(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -66,45 +55,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // ------------------------------------------------------------------------------------------------ prep kernels
-// generic: soft int8 [n][nsteps*4] -> symbol rows
-__global__ void sym_rows_from_soft_kernel(const int8_t* __restrict__ soft, int n_cw, int nsteps, uint32_t* __restrict__ rows, int row_words)
-{
-    const int groups = row_words / 8;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)n_cw * groups) return;
-    const int cw = (int)(idx / groups), g = (int)(idx % groups);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(soft + (int64_t)cw * nsteps * 4);
-    uint32_t* dst = rows + (int64_t)cw * row_words + 8 * g;
-#pragma unroll
-    for (int s = 0; s < 6; s++) { const int st = 6 * g + s; dst[s] = st < nsteps ? sym4(src[st]) : 0x7F7F7F7Fu; }
-    dst[6] = 0; dst[7] = 0;
-}
-
-// FIC: codeword (frame f, block b) takes softbits [2304 b, 2304 b + 2304) of the frame's first three symbols
-__global__ void __launch_bounds__(128)
-fic_prep_kernel(const int8_t* __restrict__ soft, int64_t soft_stride, const int32_t* __restrict__ active,
-                const int16_t* __restrict__ fic_map, uint32_t* __restrict__ rows, int row_words)
-{
-    __shared__ __align__(16) int8_t seg[2304];
-    const int cw = blockIdx.x, f = cw >> 2, b = cw & 3, t = threadIdx.x;
-    if (active && !active[f]) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(soft + (int64_t)f * soft_stride + 2304 * b);
-    for (int i = t; i < 576; i += 128) reinterpret_cast<uint32_t*>(seg)[i] = src[i];
-    __syncthreads();
-    uint32_t* dst = rows + (int64_t)cw * row_words;
-    const int groups = row_words / 8;
-    const uint2* map2 = reinterpret_cast<const uint2*>(fic_map);     // four int16 indices per trellis step
-    for (int w = t; w < groups * 8; w += 128) {
-        const int g = w >> 3, s = w & 7, st = 6 * g + s;
-        uint32_t v = 0;
-        if (s < 6) {
-            v = 0x7F7F7F7Fu;
-            if (st < 774) v = gather_sym4(seg, map2[st]);
-        }
-        dst[w] = v;
-    }
-}
-
 // MSC collect: copy the sub-channel's slice of each of this frame's 4 CIFs into the de-interleaver ring, residue-major:
 // ring[(stream*slots + slot)][cif mod 20][r][j] = softbit (start_cu*64 + r + 16 j) of that CIF.
 // One thread per capacity unit (64 softbits = 4 values of j for each of the 16 residues): four 16-byte loads, a 4x4 byte
@@ -137,20 +87,13 @@ msc_collect_kernel(MscCollectParams p)
     }
 }
 
-// MSC prep: one CTA per (stream, CIF c).  Copies the 16 residue rows of the time-de-interleaved fragment
+// MSC gather: one CTA per (stream, CIF c).  Copies the 16 residue rows of the time-de-interleaved fragment
 // (out[i] = CIF[n - (16 - map[i & 15])][i], dab-audio.cpp:113-143) from the ring into shared memory, still residue-major
-// (row r at word stride `sw`, odd so that the 16 rows start in different banks), and writes the de-punctured symbol row:
-// softbit i of the fragment sits at (i & 15) * 4 sw + (i >> 4).
+// (row r at word stride `sw`, odd so that the 16 rows start in different banks), and writes the fragment in natural order
+// (softbit i of the fragment sits at (i & 15) * 4 sw + (i >> 4) in shared memory) as one 4-byte store per thread and word.
 __constant__ int c_deint_delay[16] = {16, 8, 12, 4, 14, 6, 10, 2, 15, 7, 11, 3, 13, 5, 9, 1};   // 16 - map[r]
-__device__ __forceinline__ uint32_t gather_sym4_rm(const int8_t* seg, uint2 m, int sb)
-{
-    const int i0 = (int16_t)(m.x & 0xFFFF), i1 = (int16_t)(m.x >> 16), i2 = (int16_t)(m.y & 0xFFFF), i3 = (int16_t)(m.y >> 16);
-    const uint32_t b0 = i0 >= 0 ? (uint8_t)seg[(i0 & 15) * sb + (i0 >> 4)] : 0u, b1 = i1 >= 0 ? (uint8_t)seg[(i1 & 15) * sb + (i1 >> 4)] : 0u;
-    const uint32_t b2 = i2 >= 0 ? (uint8_t)seg[(i2 & 15) * sb + (i2 >> 4)] : 0u, b3 = i3 >= 0 ? (uint8_t)seg[(i3 & 15) * sb + (i3 >> 4)] : 0u;
-    return sym4(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
-}
 __global__ void __launch_bounds__(128)
-msc_prep_kernel(MscPrepParams p)
+msc_gather_kernel(MscPrepParams p)
 {
     extern __shared__ __align__(16) int8_t frag_s[];
     const int s = blockIdx.x / 4, c = blockIdx.x % 4, t = threadIdx.x;
@@ -171,21 +114,22 @@ msc_prep_kernel(MscPrepParams p)
         for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
     }
     __syncthreads();
-    const int cw = s * 4 + c;
-    uint32_t* dst = p.rows + (int64_t)cw * p.row_words;
-    const int groups = p.row_words / 8, nsteps = p.nsteps, sb = 4 * sw;
-    const uint2* map2 = reinterpret_cast<const uint2*>(p.map);
-    // thread t always handles word q = t & 7 of a group (128 is a multiple of 8): lanes with q >= 6 only write the padding
-    const int q = t & 7;
-    const uint32_t fill = q < 6 ? 0x7F7F7F7Fu : 0u;
-#pragma unroll 4
-    for (int w = t; w < groups * 8; w += 128) {
-        const int stp = 6 * (w >> 3) + q;
-        uint32_t v = fill;
-        if (q < 6 && stp < nsteps) v = gather_sym4_rm(frag_s, __ldg(map2 + stp), sb);
-        dst[w] = v;
+    const int cw = s * 4 + c, sb = 4 * sw;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.frag_out + (int64_t)cw * p.frag_pitch);
+    const uint8_t* fs = reinterpret_cast<const uint8_t*>(frag_s);
+    for (int q = t; q < frag / 4; q += 128) {
+        const uint8_t* b = fs + (4 * (q & 3)) * sb + (q >> 2);      // bytes i = 4q .. 4q+3: residues 4 (q & 3) + k, column q >> 2
+        dst[q] = (uint32_t)b[0] | ((uint32_t)b[sb] << 8) | ((uint32_t)b[2 * sb] << 16) | ((uint32_t)b[3 * sb] << 24);
     }
     if (t == 0 && p.valid) p.valid[cw] = 1;
+}
+
+// stage-level API helper: copy with -128 -> -127 (both are symbol 0 after the reference's clamp, viterbi.cpp:232-237), so that the
+// decoder kernel may form symbols without a saturating subtract
+__global__ void clamp_copy_kernel(const int8_t* src, int8_t* dst, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int8_t v = src[i]; dst[i] = v == -128 ? (int8_t)-127 : v; }
 }
 
 // ------------------------------------------------------------------------------------------------ the decoder
@@ -194,9 +138,9 @@ msc_prep_kernel(MscPrepParams p)
 #endif
 constexpr int VIT_THREADS = VIT_THREADS_N;     // codewords per CTA
 constexpr int VIT_MIN_CTAS = 512 / VIT_THREADS;   // 512 threads of 128 registers per SM
-constexpr int VIT_STAGES_MAX = 3;
-constexpr int VIT_ROW_PITCH = 144;      // 128 B of symbols + 16 B pad: 16-byte reads of 8 consecutive rows hit 32 distinct banks
+constexpr int VIT_ROW_PITCH = 144;      // 128 B of softbits + 16 B pad (rows stay 16-byte aligned for the bulk copies)
 constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
+constexpr int VIT_STAGE_STEPS = 24;     // trellis steps per stage: at most 96 punctured softbits + 15 bytes of alignment slack < 128
 
 template <int VIT_STAGES> struct __align__(16) VitSmemT {
     unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];
@@ -213,18 +157,20 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
     const int t = threadIdx.x;
     const int cw = block * VIT_THREADS + t;
     const bool have = cw < p.n_cw;
-    const int groups = p.nsteps / 6;                 // 6 steps per 32-byte group, 4 groups per 128-byte stage
+    const int groups = p.nsteps / 6;                 // 6 steps per group, 4 groups per stage
     const int nstages = (groups + 3) / 4;
-    const unsigned char* row = reinterpret_cast<const unsigned char*>(p.rows + (int64_t)(have ? cw : 0) * p.row_words);
+    const int cwc = have ? cw : 0;
+    const unsigned char* frag = reinterpret_cast<const unsigned char*>(p.frag) + (int64_t)(cwc / p.cw_div) * p.outer_stride + (int64_t)(cwc % p.cw_div) * p.inner_stride;
 
     if (t == 0) { for (int s = 0; s < VIT_STAGES; s++) mbar_init(&sm.full[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    // prologue: fill the ring
-    for (int s = 0; s < VIT_STAGES && s < nstages; s++) {
-        if (t == 0) mbar_expect_tx(&sm.full[s], VIT_THREADS * 128);
-        bulk_g2s(&sm.stage[s][t * VIT_ROW_PITCH], row + (int64_t)s * 128, 128, &sm.full[s]);
-    }
+    // stage s needs the softbits [stage_off[s], stage_off[s+1]) of the fragment: copy the 16-byte aligned 128 bytes that cover them
+    auto issue = [&](int s, int buf) {
+        if (t == 0) mbar_expect_tx(&sm.full[buf], VIT_THREADS * 128);
+        bulk_g2s(&sm.stage[buf][t * VIT_ROW_PITCH], frag + (__ldg(p.stage_off + s) & ~15u), 128, &sm.full[buf]);
+    };
+    for (int s = 0; s < VIT_STAGES && s < nstages; s++) issue(s, s);
 
     uint32_t Q[32];
     vit_init(Q);
@@ -234,13 +180,23 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
         const int buf = s % VIT_STAGES;
         mbar_wait(&sm.full[buf], (s / VIT_STAGES) & 1);
         vit_normalize(Q);
-        const uint4* my = reinterpret_cast<const uint4*>(&sm.stage[buf][t * VIT_ROW_PITCH]);
+        // 8-byte window (w0, w1) over the thread's row; everything about the window but its content is the same for all threads
+        const uint32_t* my = reinterpret_cast<const uint32_t*>(&sm.stage[buf][t * VIT_ROW_PITCH]);
+        int nx = (int)((__ldg(p.stage_off + s) & 15u) >> 2);
+        uint32_t w0 = my[nx], w1 = my[nx + 1];
+        nx += 2;
 #pragma unroll 1
         for (int gq = 0; gq < 4; gq++) {
             const int g = 4 * s + gq;
             if (g >= groups) break;
-            const uint4 a = my[2 * gq], b = my[2 * gq + 1];
-            const uint32_t w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+            uint32_t w[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const uint2 e = __ldg(p.steptab + 6 * g + k);           // {byte selector | advance << 16, byte mask}
+                // present softbits -> symbol s + 127 = (s ^ 0x80) - 1 (softbits are >= -127), punctured -> 127 (viterbi.cpp:232-237)
+                w[k] = ((__byte_perm(w0, w1, e.x) & e.y) ^ 0x80808080u) - 0x01010101u;
+                if (e.x & 0x10000u) { w0 = w1; w1 = my[nx]; nx++; }       // warp-uniform
+            }
             uint32_t d[12];
             vit_six_steps(Q, w, d, p.one);
             if (have) {
@@ -249,32 +205,47 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
             }
         }
         __syncthreads();   // every thread is done with this buffer's phase before it is re-armed
-        if (s + VIT_STAGES < nstages) {
-            if (t == 0) mbar_expect_tx(&sm.full[buf], VIT_THREADS * 128);
-            bulk_g2s(&sm.stage[buf][t * VIT_ROW_PITCH], row + (int64_t)(s + VIT_STAGES) * 128, 128, &sm.full[buf]);
-        }
+        if (s + VIT_STAGES < nstages) issue(s + VIT_STAGES, buf);
     }
     if (!have) return;
     if (p.valid && !p.valid[cw]) return;
-    // traceback from state 0, skipping the 6 tail steps (viterbi.cpp:313-339); bit t of the output is MSB-first in byte t/8
-    uint32_t state = 0, acc = 0;
+    // Traceback from state 0, skipping the 6 tail steps (viterbi.cpp:313-339).  The decoded bit of a step enters the state at bit 5
+    // and moves down one position per step, so after six steps the state IS the six decoded bits, earliest first from bit 5: the
+    // output is assembled six bits at a time.  96 steps (nbits is a multiple of 96) give three output words; the decision words are
+    // read in batches of 24 independent loads (their addresses do not depend on the path).
+    uint32_t state = 0;
     uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
     const uint32_t* prbs = p.prbs_words;
-    // the decision words are read back in blocks of 16 independent loads (their addresses do not depend on the path),
-    // so the serial state recursion runs from registers; nbits is a multiple of 32
-    for (int tb = p.nbits - 16; tb >= 0; tb -= 16) {
-        uint2 d[16];
+    for (int tb = p.nbits - 96; tb >= 0; tb -= 96) {
+        uint32_t acc[3] = {0, 0, 0};     // big-endian bit string of the times tb .. tb+95: acc[2] = tb .. tb+31 (time tb at bit 31)
 #pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = dec[(int64_t)(tb + k + 6) * VIT_THREADS];
+        for (int q = 3; q >= 0; q--) {
+            uint2 d[24];
 #pragma unroll
-        for (int k = 15; k >= 0; k--) {
-            const int tt = tb + k;
-            const uint32_t word = (state & 32) ? d[k].y : d[k].x;
-            const uint32_t bit = (word >> (state & 31)) & 1u;
-            state = (state >> 1) | (bit << 5);
-            acc |= bit << (8 * ((tt >> 3) & 3) + 7 - (tt & 7));
+            for (int k = 0; k < 24; k++) d[k] = dec[(int64_t)(tb + 24 * q + k + 6) * VIT_THREADS];
+#pragma unroll
+            for (int h = 3; h >= 0; h--) {
+#pragma unroll
+                for (int k = 5; k >= 0; k--) {
+                    const uint2 dd = d[6 * h + k];
+                    const uint32_t word = (state & 32u) ? dd.y : dd.x;
+                    // bit (state & 31) of the word rotated to bit 5
+                    const uint32_t rot = __funnelshift_r(word, word, state - 5u);
+                    state = (rot & 32u) | (state >> 1);
+                }
+                // state = bits of the times T .. T+5 (T = tb + 24 q + 6 h) from bit 5 down; position of time T+5 counted from the end
+                const int lo = 96 - (24 * q + 6 * h + 6);        // bit offset of time T+5 in the 96-bit string (0 = time tb+95)
+                acc[lo >> 5] |= state << (lo & 31);
+                if ((lo & 31) > 26) acc[(lo >> 5) + 1] |= state >> (32 - (lo & 31));
+            }
         }
-        if ((tb & 31) == 0) { out[tb >> 5] = prbs ? acc ^ prbs[tb >> 5] : acc; acc = 0; }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            // acc[2 - j] holds the times tb + 32 j .. tb + 32 j + 31, first time at bit 31; memory order is byte (time / 8) first
+            const uint32_t v = __byte_perm(acc[2 - j], 0, 0x0123);
+            const int wi = (tb >> 5) + j;
+            out[wi] = prbs ? v ^ prbs[wi] : v;
+        }
     }
 }
 
@@ -314,52 +285,42 @@ __global__ void unpack_bits_kernel(const uint8_t* __restrict__ bytes, int64_t st
     bits[idx] = (bytes[(int64_t)cw * stride + (b >> 3)] >> (7 - (b & 7))) & 1;
 }
 
-// stage-level API helper: punctured softbits [n][frag] -> symbol rows (EEP/UEP de-puncturing only)
-__global__ void msc_expand_kernel(const int8_t* __restrict__ soft, int n, int frag, const int16_t* __restrict__ map, int nsteps, uint32_t* __restrict__ rows, int row_words)
-{
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)n * row_words) return;
-    const int cw = (int)(idx / row_words), w = (int)(idx % row_words), g = w >> 3, q = w & 7, stp = 6 * g + q;
-    uint32_t v = 0;
-    if (q < 6) {
-        v = 0x7F7F7F7Fu;
-        if (stp < nsteps) {
-            uint32_t packed = 0;
-            for (int k = 0; k < 4; k++) { const int m = map[4 * stp + k]; const int sb = m >= 0 ? soft[(int64_t)cw * frag + m] : 0; packed |= vit_sym(sb) << (8 * k); }
-            v = packed;
-        }
-    }
-    rows[idx] = v;
-}
-
 } // namespace
 
-void launch_msc_expand(const int8_t* soft, int n, int frag, const int16_t* map, int nsteps, uint32_t* rows, int row_words, cudaStream_t st)
+// Per-profile expansion tables of the decoder kernel from a de-puncturing map (4 entries per trellis step: index into the punctured
+// softbits, consecutive, or -1).  steps[t] = {PRMT selector over the 8-byte window | advance flag << 16, byte mask};
+// stage_off[s] = index of the first softbit consumed by stage s (24 steps), stage_off[nstages] = total.
+void build_vit_tables(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off)
 {
-    const int64_t total = (int64_t)n * row_words;
-    msc_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(soft, n, frag, map, nsteps, rows, row_words);
+    steps.assign(nsteps, make_uint2(0, 0));
+    stage_off.clear();
+    int cursor = 0, pos = 0;
+    for (int t = 0; t < nsteps; t++) {
+        if (t % VIT_STAGE_STEPS == 0) { stage_off.push_back((uint32_t)cursor); pos = cursor & 3; }
+        uint32_t sel = 0, mask = 0; int n = 0;
+        for (int k = 0; k < 4; k++) {
+            const int m = map[4 * t + k];
+            if (m >= 0) { sel |= (uint32_t)(pos + n) << (4 * k); mask |= 0xFFu << (8 * k); n++; cursor++; }
+        }
+        pos += n;
+        uint32_t adv = 0;
+        if (pos >= 4) { pos -= 4; adv = 1; }
+        steps[t] = make_uint2(sel | (adv << 16), mask);
+    }
+    stage_off.push_back((uint32_t)cursor);
 }
 
-int vit_row_words(int nsteps) { const int groups = nsteps / 6; return ((groups + 3) / 4) * 4 * 8; }
-
-void launch_sym_rows_from_soft(const int8_t* soft, int n_cw, int nsteps, uint32_t* rows, cudaStream_t st)
+void launch_clamp_copy(const int8_t* src, int8_t* dst, int64_t n, cudaStream_t st)
 {
-    const int rw = vit_row_words(nsteps);
-    const int64_t total = (int64_t)n_cw * (rw / 8);
-    sym_rows_from_soft_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(soft, n_cw, nsteps, rows, rw);
-}
-
-void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint32_t* rows, cudaStream_t st)
-{
-    fic_prep_kernel<<<n_frames * 4, 128, 0, st>>>(soft, soft_stride, active, tb.fic_map, rows, vit_row_words(774));
+    clamp_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
 }
 
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st) { msc_collect_kernel<<<n_streams * 4, 128, 0, st>>>(p); }
-void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st)
+void launch_msc_gather(const MscPrepParams& p, int n_streams, cudaStream_t st)
 {
     const int smem = p.ring_pitch + 64;      // 16 residue rows, each padded to an odd word count
-    if (smem > 48 * 1024) cudaFuncSetAttribute(msc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    msc_prep_kernel<<<n_streams * 4, 128, smem, st>>>(p);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(msc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    msc_gather_kernel<<<n_streams * 4, 128, smem, st>>>(p);
 }
 
 void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)

@@ -1,6 +1,7 @@
 // viterbi.cuh — parameter blocks and launchers of viterbi.cu / rs.cu
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace dabb {
 
@@ -27,13 +28,16 @@ struct MscCollectParams {
 struct MscPrepParams {
     const int32_t* active; const MscSlotState* slots; int n_slots; int slot;
     const int8_t* ring; int ring_pitch;
-    const int16_t* map; int nsteps;
-    uint32_t* rows; int row_words;
+    int8_t* frag_out; int frag_pitch; // [n_streams*4][frag_pitch] time-de-interleaved punctured fragments (pitch: multiple of 16)
     int32_t* valid;                   // [n_streams*4] set to 1 for every codeword produced
 };
 
 struct ViterbiParams {
-    const uint32_t* rows; int row_words;
+    // punctured softbits of codeword cw at frag + (cw / cw_div) * outer_stride + (cw % cw_div) * inner_stride (16-byte aligned, readable
+    // up to 160 bytes past the codeword's last softbit); values >= -127
+    const int8_t* frag; int cw_div; int64_t outer_stride, inner_stride;
+    const uint2* steptab;             // [nsteps] per-step expansion entries (build_vit_tables)
+    const uint32_t* stage_off;        // [nstages + 1]
     int n_cw, nsteps, nbits;
     uint2* dec;                       // [(n_cw+127)/128][nsteps][128]
     uint8_t* out; int64_t out_stride; // packed bytes, multiple of 4
@@ -43,13 +47,12 @@ struct ViterbiParams {
 };
 
 
-int vit_row_words(int nsteps);
 size_t vit_dec_bytes(int n_cw, int nsteps);
-void launch_sym_rows_from_soft(const int8_t* soft, int n_cw, int nsteps, uint32_t* rows, cudaStream_t st);
-void launch_fic_prep(const DevTables& tb, const int8_t* soft, int64_t soft_stride, const int32_t* active, int n_frames, uint32_t* rows, cudaStream_t st);
+constexpr int VIT_FRAG_SLACK = 160;   // bytes the decoder kernel may read past a codeword's last softbit
+void build_vit_tables(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off);
+void launch_clamp_copy(const int8_t* src, int8_t* dst, int64_t n, cudaStream_t st);
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st);
-void launch_msc_prep(const MscPrepParams& p, int n_streams, cudaStream_t st);
-void launch_msc_expand(const int8_t* soft, int n, int frag, const int16_t* map, int nsteps, uint32_t* rows, int row_words, cudaStream_t st);
+void launch_msc_gather(const MscPrepParams& p, int n_streams, cudaStream_t st);
 void launch_viterbi(const ViterbiParams& p, cudaStream_t st, int stages = 3);
 void launch_fic_crc(const uint8_t* fibs, const int32_t* active, int n_frames, int32_t* mask_out, cudaStream_t st);
 void launch_unpack_bits(const uint8_t* bytes, int64_t stride, int n_cw, int nbits, uint8_t* bits, cudaStream_t st);

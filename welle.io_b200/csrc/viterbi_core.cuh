@@ -81,62 +81,89 @@ VIT_HD void vit_metrics(uint32_t w, uint32_t E[8])
     for (int p = 0; p < 8; p++) E[p] = a[p & 1] + b[(p >> 1) & 1] + c[(p >> 2) & 1];
 }
 
+// The eight packed branch-metric words of one step for a layout whose SIMD partner differs by pattern DELTA:
+// MC[p] = E[p] | E[p ^ DELTA] << 16.  Built directly in packed form: with A = s0 + s3, B = s1, C = s2 (one dot-product
+// instruction each) the pair (x, x) or (x, max - x) is one multiply-add, its complement (max, max) - pair one subtract, and
+// MC[p] = PA[p & 1] + PB[(p >> 1) & 1] + PC[p >> 2] (no carry between the halves: every sum is <= 1020).
+template <int DELTA> VIT_HD void vit_mc(uint32_t w, uint32_t (&MC)[8])
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t A = __dp4a(w, 0x01000001u, 0u), B = __dp4a(w, 0x00000100u, 0u), C = __dp4a(w, 0x00010000u, 0u);
+#else
+    const uint32_t A = (w & 0xFF) + (w >> 24), B = (w >> 8) & 0xFF, C = (w >> 16) & 0xFF;
+#endif
+    // (x, x) = x * 0x10001;  (x, max - x) = x * (1 - 65536) + (max << 16)   (mod 2^32)
+    const uint32_t PA0 = (DELTA & 1) ? A * 0xFFFF0001u + (510u << 16) : A * 0x00010001u;
+    const uint32_t PB0 = (DELTA & 2) ? B * 0xFFFF0001u + (255u << 16) : B * 0x00010001u;
+    const uint32_t PC0 = (DELTA & 4) ? C * 0xFFFF0001u + (255u << 16) : C * 0x00010001u;
+    const uint32_t PA[2] = {PA0, 0x01FE01FEu - PA0}, PB[2] = {PB0, 0x00FF00FFu - PB0}, PC[2] = {PC0, 0x00FF00FFu - PC0};
+    uint32_t AB[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) AB[q] = PA[q & 1] + PB[q >> 1];
+#pragma unroll
+    for (int p = 0; p < 8; p++) MC[p] = AB[p & 3] + PC[p >> 2];
+}
+
 // One ACS step from layout L_B to L_{(B+1)%6}.  Q: 32 packed metric registers; dlo/dhi: decision bits of new states
 // 0..31 / 32..63.
-template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t (&E)[8], uint32_t& dlo, uint32_t& dhi, const uint32_t one)
+template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32_t& dlo, uint32_t& dhi, const uint32_t one)
 {
     (void)one;
     uint32_t N[32];
     // decision bits are OR-ed into four partial words per half (short dependency chains, no branches)
-    uint32_t pl_[4] = {0, 0, 0, 0}, ph_[4] = {0, 0, 0, 0};
+    uint32_t acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // [0..3]: new states 0..31, [4..7]: new states 32..63
+    // VIT_MIN(dst, a, b, nl, nh): dst = per-half signed minimum of (a, b); decision bit of new state nl (low half) / nh (high half)
+    // is set when b wins strictly ((a - b) > 0: ties keep the a = old[i] branch, viterbi.cpp:263-275).
 #if defined(__CUDA_ARCH__)
-    // forced predication (the compiler otherwise turns some of these into divergent branches).  The bit is ADDED with a
-    // predicated multiply-add (`@!p mad.lo acc = bit * 1 + acc`; every bit is set at most once, so add == or): that is an
-    // IMAD on the FMA pipe, which balances the ALU pipe where the packed min/add instructions already run at half rate.
-    // `one` is the value 1 passed through a kernel parameter so that the assembler cannot fold the multiply away.
-#define VIT_OR_IF_NOT(acc, pred_le, bitconst) asm("{\n.reg .pred q;\nsetp.eq.u32 q, %1, 0;\n@q mad.lo.u32 %0, %2, %3, %0;\n}" : "+r"(acc) : "r"((uint32_t)(pred_le)), "r"((uint32_t)(bitconst)), "r"(one))
+    // One asm statement per packed minimum: the two predicates VIMNMX.S16x2 produces are consumed by predicated multiply-adds
+    // inside the same statement, so they never become general registers (passing them through C++ bools made the compiler
+    // materialise every predicate with SEL / LOP3 / P2R: 276 instead of ~190 instructions per trellis step).  The bit is ADDED
+    // with `@p mad.lo acc = bit * 1 + acc` (every bit is set at most once, so add == or): an IMAD on the FMA pipe, which balances
+    // the ALU pipe where the packed minimum runs.  `one` is the value 1 passed through a kernel parameter so that the assembler
+    // cannot fold the multiply away.
+#define VIT_ACC(n) acc_[(((n) >> 5) << 2) | (((n) >> 3) & 3)]
+#define VIT_MIN(dst, a, b, nl, nh) \
+    asm("{\n.reg .pred pu, pv;\n.reg .u16 r0, r1, r2, r3;\n.reg .b32 m;\n" \
+        "min.s16x2 m, %3, %4;\nmov.b32 {r0, r1}, m;\nmov.b32 {r2, r3}, %3;\n" \
+        "setp.eq.s16 pv, r0, r2;\nsetp.eq.s16 pu, r1, r3;\n" \
+        "@!pv mad.lo.u32 %1, %5, %6, %1;\n@!pu mad.lo.u32 %2, %5, %7, %2;\nmov.b32 %0, m;\n}" \
+        : "=r"(dst), "+r"(VIT_ACC(nl)), "+r"(VIT_ACC(nh)) \
+        : "r"(a), "r"(b), "r"(one), "r"(1u << ((nl) & 31)), "r"(1u << ((nh) & 31)))
 #else
-#define VIT_OR_IF_NOT(acc, pred_le, bitconst) do { if (!(pred_le)) (acc) |= (bitconst); } while (0)
+#define VIT_ACC(n) acc_[(((n) >> 5) << 2) | (((n) >> 3) & 3)]
+#define VIT_MIN(dst, a, b, nl, nh) do { bool ph__, pl__; dst = vibmin16(a, b, ph__, pl__); \
+        if (!pl__) VIT_ACC(nl) |= 1u << ((nl) & 31); if (!ph__) VIT_ACC(nh) |= 1u << ((nh) & 31); } while (0)
 #endif
-#define VIT_SETBIT(pred_le, n) do { if ((n) < 32) VIT_OR_IF_NOT(pl_[((n) >> 3) & 3], pred_le, 1u << ((n) & 31)); else VIT_OR_IF_NOT(ph_[((n) >> 3) & 3], pred_le, 1u << ((n) & 31)); } while (0)
     if constexpr (B < 5) {
         constexpr int delta = vit_pat(1 << B);   // pattern change when butterfly bit B flips
         uint32_t MC[8];
-#pragma unroll
-        for (int p = 0; p < 8; p++) MC[p] = E[p] | (E[p ^ delta] << 16);
+        vit_mc<delta>(w, MC);
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int ilo = vit_insert_zero(j, B);            // butterfly with bit B = 0; its SIMD partner is ilo + (1<<B)
             const int ra = vit_remove_bit(ilo, B), rb = vit_remove_bit(ilo + 32, B);
             const int p = vit_pat(ilo);
             const uint32_t m0 = Q[ra] + MC[p], m1 = Q[rb] + MC[p ^ 7], m2 = Q[ra] + MC[p ^ 7], m3 = Q[rb] + MC[p];
-            bool ph, pl;
             const int ne = 2 * ilo, nehi = ne + (2 << B);     // new states in the low / high half of the even result
-            N[vit_remove_bit(ne, B + 1)] = vibmin16(m0, m1, ph, pl);
-            VIT_SETBIT(pl, ne); VIT_SETBIT(ph, nehi);
-            N[vit_remove_bit(ne + 1, B + 1)] = vibmin16(m2, m3, ph, pl);
-            VIT_SETBIT(pl, ne + 1); VIT_SETBIT(ph, nehi + 1);
+            VIT_MIN(N[vit_remove_bit(ne, B + 1)], m0, m1, ne, nehi);
+            VIT_MIN(N[vit_remove_bit(ne + 1, B + 1)], m2, m3, ne + 1, nehi + 1);
         }
     } else {
         // L_5: register i = (old[i], old[i+32]); result register i = (new[2i], new[2i+1]) = layout L_0
         uint32_t XC[8];
-#pragma unroll
-        for (int p = 0; p < 8; p++) XC[p] = E[p] | (E[p ^ 7] << 16);
+        vit_mc<7>(w, XC);
 #pragma unroll
         for (int i = 0; i < 32; i++) {
             const int p = vit_pat(i);
             const uint32_t x = dup_lo(Q[i]) + XC[p];        // (old[i] + m,        old[i] + 1020 - m)
             const uint32_t y = dup_hi(Q[i]) + XC[p ^ 7];    // (old[i+32] + 1020-m, old[i+32] + m)
-            bool ph, pl;
-            N[i] = vibmin16(x, y, ph, pl);
-            const int ne = 2 * i;
-            VIT_SETBIT(pl, ne); VIT_SETBIT(ph, ne + 1);
+            VIT_MIN(N[i], x, y, 2 * i, 2 * i + 1);
         }
     }
-#undef VIT_SETBIT
-#undef VIT_OR_IF_NOT
-    dlo = (pl_[0] | pl_[1]) | (pl_[2] | pl_[3]);
-    dhi = (ph_[0] | ph_[1]) | (ph_[2] | ph_[3]);
+#undef VIT_MIN
+#undef VIT_ACC
+    dlo = (acc_[0] | acc_[1]) | (acc_[2] | acc_[3]);
+    dhi = (acc_[4] | acc_[5]) | (acc_[6] | acc_[7]);
 #pragma unroll
     for (int r = 0; r < 32; r++) Q[r] = N[r];
 }
@@ -165,13 +192,12 @@ VIT_HD void vit_normalize(uint32_t (&Q)[32])
 // six steps: words w[0..5] hold the symbols, dec[2*s], dec[2*s+1] receive the decision words
 VIT_HD void vit_six_steps(uint32_t (&Q)[32], const uint32_t w[6], uint32_t dec[12], const uint32_t one = 1u)
 {
-    uint32_t E[8];
-    vit_metrics(w[0], E); vit_acs<0>(Q, E, dec[0], dec[1], one);
-    vit_metrics(w[1], E); vit_acs<1>(Q, E, dec[2], dec[3], one);
-    vit_metrics(w[2], E); vit_acs<2>(Q, E, dec[4], dec[5], one);
-    vit_metrics(w[3], E); vit_acs<3>(Q, E, dec[6], dec[7], one);
-    vit_metrics(w[4], E); vit_acs<4>(Q, E, dec[8], dec[9], one);
-    vit_metrics(w[5], E); vit_acs<5>(Q, E, dec[10], dec[11], one);
+    vit_acs<0>(Q, w[0], dec[0], dec[1], one);
+    vit_acs<1>(Q, w[1], dec[2], dec[3], one);
+    vit_acs<2>(Q, w[2], dec[4], dec[5], one);
+    vit_acs<3>(Q, w[3], dec[6], dec[7], one);
+    vit_acs<4>(Q, w[4], dec[8], dec[9], one);
+    vit_acs<5>(Q, w[5], dec[10], dec[11], one);
 }
 
 // soft bit (int8, 0 = punctured) -> decoder symbol clamp(s + 127, 0, 255)  (viterbi.cpp:232-237)

@@ -15,6 +15,7 @@ L, K, TU, TS, TG, TNULL, TF = 76, 1536, 2048, 2552, 504, 2656, 196608
 SOFT_PER_FRAME = 75 * 3072
 MAX_SUBCH = 4
 FFT_EXACT, FFT_FMA = 0, 1
+NCO_EXACT, NCO_FAST = 0, 1
 IQ_CF32, IQ_U8, IQ_S8, IQ_S16LE, IQ_S16BE = 0, 1, 2, 3, 4
 FRAME_DECODED, FRAME_NEED_SAMPLES, FRAME_NO_SYNC, FRAME_ACQUIRING = 0, 1, 2, 3
 
@@ -27,7 +28,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_streams", C.c_int32), ("transmission_mode", C.c_int32),
                 ("fft_mode", C.c_int32), ("disable_coarse", C.c_int32), ("keep_taps", C.c_int32), ("n_subch_slots", C.c_int32),
                 ("max_subch_cu", C.c_int32), ("ofdm_groups", C.c_int32), ("fft_placement", C.c_int32), ("freqsync_method", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("nco_mode", C.c_int32), ("ofdm_tail_split", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Options(C.Structure):
@@ -148,7 +149,7 @@ class DevBuf:
 
 class Context:
     def __init__(self, n_streams=1, device=0, fft_mode=FFT_EXACT, disable_coarse=True, keep_taps=False, n_subch_slots=1,
-                 max_subch_cu=0, ofdm_groups=0, coresident=False, fft_placement=0, freqsync_method=0):
+                 max_subch_cu=0, ofdm_groups=0, fft_placement=0, freqsync_method=0, nco_mode=NCO_EXACT, ofdm_tail_split=0):
         self.lib = load_library()
         cfg = Config()
         cfg.abi_version = self.lib.dabb_abi_version()
@@ -156,7 +157,7 @@ class Context:
         cfg.fft_mode, cfg.disable_coarse, cfg.keep_taps = fft_mode, int(disable_coarse), int(keep_taps)
         cfg.n_subch_slots, cfg.max_subch_cu, cfg.ofdm_groups = n_subch_slots, max_subch_cu, ofdm_groups
         cfg.fft_placement, cfg.freqsync_method = int(fft_placement), int(freqsync_method)
-        cfg.reserved[0] = 2 if coresident else 0      # 2: cap the OFDM kernel at 4 CTAs/SM so that lane-B CTAs fit beside it (experimental)
+        cfg.nco_mode, cfg.ofdm_tail_split = int(nco_mode), int(ofdm_tail_split)
         h = C.c_void_p()
         rc = self.lib.dabb_create(C.byref(cfg), C.byref(h))
         if rc != 0:
