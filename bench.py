@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tail-split", action="store_true", help="A/B: do not cut the last frames of the OFDM launch into short CTAs")
     ap.add_argument("--cfo-hz", type=float, default=50.0, help="carrier offset of the secondary 'oscillator active' measurement (0 = skip); must keep the 5-frame ring periodic (multiples of 1/0.48 s)")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -292,7 +293,7 @@ def main():
     torch.cuda.synchronize()
     log(f"input ready: {S} streams x {BUF_LEN} samples")
 
-    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
+    ctx = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU, ofdm_tail_split=-1 if a.no_tail_split else 0)
     ctx.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
     ext = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)
 
@@ -315,6 +316,7 @@ def main():
     e0.record(ext)
     for _ in range(a.steps):
         ctx.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(call), BUF_LEN); call += 1
+    ctx.join_lanes()       # the FIC / MSC / RS lane of the last steps runs on other streams: the closing event waits for it
     e1.record(ext)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -482,34 +484,37 @@ def main():
                 blk[..., 0] = re; blk[..., 1] = im
                 del re, im
             torch.cuda.synchronize()
-            ctx2 = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU)
-            ctx2.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
-            ext2 = torch.cuda.ExternalStream(ctx2.cuda_stream(), device=dev)
-            c2 = 0
-            for _ in range(a.warmup):
-                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
-            ctx2.sync()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(ext2)
-            for _ in range(a.steps):
-                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
-            g1.record(ext2); torch.cuda.synchronize()
-            ms2 = g0.elapsed_time(g1)
-            ctx2.profile(True)
-            for _ in range(a.steps):
-                ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
-            ctx2.sync(); ctx2.profile(False)
-            pr2 = ctx2.profile_read()
-            o2 = ctx2.process(buf, BUF_LEN, buf_start_for(c2), BUF_LEN, msc_stride=3 * BITRATE); c2 += 1
-            r2 = o2["results"]
-            k2 = pr2["ofdm_demod_kernel"]["ms"] / pr2["ofdm_demod_kernel"]["n"]
-            with_nco = {"cfo_hz": a.cfo_hz, "value": S * a.steps / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / a.steps, "ofdm_ms_per_launch": k2,
-                        "ofdm_frac": S * OFDM_BYTES_PER_FRAME / (k2 * 1e-3) / 1e9 / hbm_peak,
-                        "frames_decoded": int((r2["status"] == 0).sum()), "fib_crc_ok": int(sum(bin(int(m)).count("1") for m in r2["fib_crc_mask"])),
-                        "fine_corr_median_hz": float(np.median(r2["fine_corr"])),
-                        "oscillator_on_the_fly": int(ctx2.get_info(0)), "oscillator_table_mismatches": int(ctx2.get_info(1)),
-                        "note": "same workload with a carrier offset: the numerically controlled oscillator (reference: 2 048 000-entry table lookup + complex multiply per sample; here evaluated on the fly after an exhaustive comparison with that table) is active for every stream"}
-            ctx2.close()
+            with_nco = {}
+            for mode_name, mode in (("exact", pkg.NCO_EXACT), ("fast", pkg.NCO_FAST)):
+                ctx2 = pkg.Context(n_streams=S, device=local, fft_mode=a.fft_mode, disable_coarse=True, n_subch_slots=1, max_subch_cu=SUBCH_CU, nco_mode=mode)
+                ctx2.select_subchannel(0, SUBCH_CU, BITRATE, eep_profile_a=True, eep_level=3, dabplus=True)
+                ext2 = torch.cuda.ExternalStream(ctx2.cuda_stream(), device=dev)
+                c2 = 0
+                for _ in range(a.warmup):
+                    ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+                ctx2.sync()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(ext2)
+                for _ in range(a.steps):
+                    ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+                ctx2.join_lanes()
+                g1.record(ext2); torch.cuda.synchronize()
+                ms2 = g0.elapsed_time(g1)
+                ctx2.profile(True)
+                for _ in range(a.steps):
+                    ctx2.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(c2), BUF_LEN); c2 += 1
+                ctx2.sync(); ctx2.profile(False)
+                pr2 = ctx2.profile_read()
+                o2 = ctx2.process(buf, BUF_LEN, buf_start_for(c2), BUF_LEN, msc_stride=3 * BITRATE); c2 += 1
+                r2 = o2["results"]
+                k2 = pr2["ofdm_demod_kernel"]["ms"] / pr2["ofdm_demod_kernel"]["n"]
+                with_nco[mode_name] = {"cfo_hz": a.cfo_hz, "nco_mode": mode_name, "value": S * a.steps / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / a.steps, "ofdm_ms_per_launch": k2,
+                            "ofdm_frac": S * OFDM_BYTES_PER_FRAME / (k2 * 1e-3) / 1e9 / hbm_peak,
+                            "frames_decoded": int((r2["status"] == 0).sum()), "fib_crc_ok": int(sum(bin(int(m)).count("1") for m in r2["fib_crc_mask"])),
+                            "fine_corr_median_hz": float(np.median(r2["fine_corr"])),
+                            "oscillator_on_the_fly": int(ctx2.get_info(0)), "oscillator_table_mismatches": int(ctx2.get_info(1)),
+                            "note": "same workload with a carrier offset: the numerically controlled oscillator (reference: 2 048 000-entry table lookup + complex multiply per sample; here evaluated on the fly after an exhaustive comparison with that table) is active for every stream"}
+                ctx2.close()
         except Exception as e:  # noqa
             with_nco = {"error": repr(e)}
     roofline["oscillator_active"] = with_nco

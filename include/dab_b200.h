@@ -168,6 +168,9 @@ int dabb_process(dabb_ctx* ctx, const dabb_io* io);
 /* asynchronous form for benchmarking with device-resident inputs: enqueue only, no host copies */
 int dabb_process_async(dabb_ctx* ctx, const dabb_io* io);
 int dabb_sync(dabb_ctx* ctx);
+/* makes the context's main stream (dabb_cuda_stream) wait for everything enqueued so far on the library's other streams, so that an
+ * event recorded on it afterwards marks the completion of all work of the preceding dabb_process_async calls (timing) */
+int dabb_join_lanes(dabb_ctx* ctx);
 void* dabb_cuda_stream(dabb_ctx* ctx);              /* cudaStream_t of the context */
 int64_t dabb_kernel_launches(const dabb_ctx* ctx);  /* number of CUDA kernels this context has launched */
 

@@ -555,6 +555,15 @@ void* dabb_cuda_stream(dabb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullpt
 int64_t dabb_kernel_launches(const dabb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int dabb_sync(dabb_ctx* ctx) { if (!ctx) return DABB_E_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->streamB)); CK(cudaStreamSynchronize(ctx->stream2)); if (ctx->prof) prof_collect(ctx); return 0; }
 
+int dabb_join_lanes(dabb_ctx* ctx)
+{
+    if (!ctx) return DABB_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->prof || !ctx->evB_valid[ctx->last_parity]) return DABB_OK;       // serial mode: everything is on the main stream already
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evB[ctx->last_parity], 0));       // lane B's last record follows the FIC stream's join
+    return DABB_OK;
+}
+
 int dabb_stream_reset(dabb_ctx* ctx, int32_t first, int32_t count, int64_t pos)
 {
     if (!ctx || first < 0 || count < 0 || first + count > ctx->S) return DABB_E_ARG;

@@ -69,7 +69,7 @@ class IO(C.Structure):
 
 
 EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_get_info", "dabb_select_subchannel",
-           "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_cuda_stream", "dabb_kernel_launches",
+           "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_join_lanes", "dabb_cuda_stream", "dabb_kernel_launches",
            "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_find_index_ex", "dabb_coarse_estimate", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
            "dabb_rs_superframes", "dabb_dev_alloc", "dabb_dev_free", "dabb_memcpy_h2d", "dabb_memcpy_d2h"]
 
@@ -195,6 +195,9 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.dabb_sync(self.h))
+
+    def join_lanes(self):
+        self._ck(self.lib.dabb_join_lanes(self.h))
 
     def profile(self, enable):
         self._ck(self.lib.dabb_profile(self.h, int(enable)))
