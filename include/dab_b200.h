@@ -135,7 +135,9 @@ typedef struct {
     int64_t next_pos;       /* logical sample position where the next frame's T_u read starts */
     float   freq_corr_re, freq_corr_im;    /* FreqCorr accumulator (ofdm-processor.cpp:435-442) */
     float   slevel;
-    int32_t reserved[3];
+    int32_t acq_failed;     /* null searches that failed inside this call (each one re-enters OFDMProcessor::run's notSynced state,
+                               ofdm-processor.cpp:253-323: what RadioReceiver::restart(doScan) counts for onSignalPresence) */
+    int32_t reserved[2];
 } dabb_frame_result;
 
 enum { DABB_FRAME_DECODED = 0, DABB_FRAME_NEED_SAMPLES = 1, DABB_FRAME_NO_SYNC = 2, DABB_FRAME_ACQUIRING = 3 };

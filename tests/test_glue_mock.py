@@ -74,3 +74,43 @@ def test_batch_decode_with_mock_backend(oracle, tmp_path):
         m = min(len(msc), len(o["msc"]))
         assert m >= 3 * br * 8 and np.array_equal(msc[:m], o["msc"][:m]), k
         assert f"bitrate={br}" in lines[k] and "service=0x" in lines[k]
+
+
+def _rawfile_exe():
+    import pytest
+    exe = os.path.join(ROOT, "oracle", "_ref", "rawfile_test")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "welle.io_b200", "host")])
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "rawfile"])
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/rawfile_test not built (needs /root/reference)")
+    return exe
+
+
+def test_stock_crawfile_drives_the_glue_with_mock_backend(oracle, tmp_path):
+    """The lower boundary with the reference's OWN input class: the unmodified src/input/raw_file.cpp (+ raw_file.h, virtual_input.h,
+    various/ringbuffer.h), compiled against the glue's headers and linked with libwelle_b200_host.so (oracle/Makefile: rawfile), feeds
+    RadioReceiver through CRAWFile(throttle=false, rewind=false) exactly like welle-cli.cpp:514-516,612-664: FIB dump and .msc dump equal
+    the oracle's (which is pinned to the reference's own RadioReceiver on the same file)."""
+    exe = _rawfile_exe()
+    mock = tmp_path / "libdab_b200.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(mock), os.path.join(ROOT, "tests", "mock_backend", "mock_dab_b200.c"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    tx = dabtx.DabTx(seed=0xC0DE)
+    iq = tx.frames(14)
+    f = tmp_path / "rec.cf32.iq"
+    iq.tofile(f)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(tmp_path), DABB_MOCK_IQ=str(f))
+    out = subprocess.run([exe, str(f), str(tmp_path / "o"), "12"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    summary = dict(kv.split("=") for kv in out.stdout.split())
+    fibs = np.fromfile(tmp_path / "o.fibs", np.uint8).reshape(-1, 33)
+    msc = np.fromfile(tmp_path / "o.msc", np.uint8)
+    o = oracle.rx_run(iq, prot=oracle.prot_eep(96, 1, 3), start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    n = min(len(fibs), len(o["fibs"]))
+    assert n >= 12 * 10 and np.array_equal(fibs[:n], o["fibs"][:n]) and fibs[:, 0].all()
+    assert summary["selected"] == "1" and int(summary["services"]) == 1 and int(summary["syncs"]) == 1
+    m = min(len(msc), len(o["msc"]))
+    assert m >= 288 * 20 and np.array_equal(msc[:m], o["msc"][:m])
+    # getReceiverStats().timeLastFCT0Frame is served (set when the ensemble was cleared at restart / by FIG 0/0 with CIF count 0)
+    assert 0.0 <= float(summary["fct0_age_s"]) < 120.0

@@ -71,3 +71,51 @@ def test_batch_decode_on_gpu(oracle, tmp_path):
         m = min(len(msc), len(o["msc"]))
         assert m >= 3 * br * 8 and np.array_equal(msc[:m], o["msc"][:m]), k
         assert f"bitrate={br}" in lines[k] and "service=0x" in lines[k]
+
+
+@pytest.mark.parametrize("fmt", ["cf32", "u8"])
+def test_stock_crawfile_drives_the_glue_on_gpu(oracle, tmp_path, fmt):
+    """the reference's own CRAWFile (unmodified raw_file.cpp compiled against the glue, oracle/Makefile: rawfile) feeding the B200
+    backend like welle-cli does: FIB and .msc dumps equal the oracle's on the same recording (cf32 and the RTL-SDR style u8 format,
+    which CRAWFile converts on the host before the glue sees it)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "rawfile_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/rawfile_test not built (needs /root/reference at build time)")
+    tx = dabtx.DabTx(seed=0xC0DE)
+    iq = tx.frames(16)
+    if fmt == "cf32":
+        f = tmp_path / "rec.cf32.iq"; iq.tofile(f); ref_sig = iq
+    else:
+        inter = np.stack([iq.real, iq.imag], axis=-1)
+        u8 = np.clip(np.round(inter * 2.0 * 128.0 + 128.0), 0, 255).astype(np.uint8)
+        f = tmp_path / "rec.u8.iq"; u8.tofile(f)
+        ref_sig = ((u8.astype(np.float32) - 128.0) / 128.0).view(np.complex64).reshape(-1)
+    out = subprocess.run([exe, str(f), str(tmp_path / "o"), "12"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    summary = dict(kv.split("=") for kv in out.stdout.split())
+    fibs = np.fromfile(tmp_path / "o.fibs", np.uint8).reshape(-1, 33)
+    msc = np.fromfile(tmp_path / "o.msc", np.uint8)
+    o = oracle.rx_run(ref_sig, prot=oracle.prot_eep(96, 1, 3), start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    n = min(len(fibs), len(o["fibs"]))
+    assert n >= 12 * 12 and np.array_equal(fibs[:n], o["fibs"][:n]) and fibs[:n, 0].all()
+    m = min(len(msc), len(o["msc"]))
+    assert m >= 288 * 24 and np.array_equal(msc[:m], o["msc"][:m])
+    assert summary["selected"] == "1" and int(summary["services"]) == 1 and int(summary["superframes"]) >= 3
+    print(f"stock CRAWFile -> glue -> GPU ({fmt}): {summary}")
+
+
+def test_scan_reports_signal_presence(tmp_path):
+    """RadioReceiver::restart(doScan = true): onSignalPresence(true) once SyncOnPhase succeeds on a DAB signal, onSignalPresence(false)
+    after the sixth entry into the unsynchronised state on noise (ofdm-processor.cpp:258-262,351-355)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "rawfile_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/rawfile_test not built (needs /root/reference at build time)")
+    sig = dabtx.DabTx(seed=0x5CA).frames(8)
+    f1 = tmp_path / "sig.cf32.iq"; sig.tofile(f1)
+    rng = np.random.default_rng(5)
+    noise = ((rng.standard_normal(8 * 196608) + 1j * rng.standard_normal(8 * 196608)) * 0.05).astype(np.complex64)
+    f2 = tmp_path / "noise.cf32.iq"; noise.tofile(f2)
+    s1 = dict(kv.split("=") for kv in subprocess.run([exe, str(f1), str(tmp_path / "a"), "12", "1", "1"], capture_output=True, text=True, timeout=600).stdout.split())
+    s2 = dict(kv.split("=") for kv in subprocess.run([exe, str(f2), str(tmp_path / "b"), "12", "1", "1"], capture_output=True, text=True, timeout=600).stdout.split())
+    assert s1["presence_true"] == "1" and s1["presence_false"] == "0" and int(s1["ok"]) > 0
+    assert s2["presence_true"] == "0" and s2["presence_false"] == "1" and int(s2["fibs"]) == 0

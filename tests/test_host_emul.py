@@ -49,3 +49,49 @@ def test_oscillator_on_the_fly_equals_table_for_every_index():
     patched = C.c_int()
     assert lib.emul_osc_mismatches(C.byref(patched)) == 0
     assert patched.value == 3
+
+
+def test_decoder_kernel_emulation_depuncture_and_traceback(oracle):
+    """one thread of the decoder kernel (expansion tables from a de-puncturing map, 8-byte window expansion, packed ACS, 24-step
+    traceback, MSB-first packing) on the CPU from the shared header code: FIC puncturing, EEP-A/B and UEP profiles, no puncturing -
+    output bytes equal to oracle de-puncture + Viterbi + pack"""
+    so = os.path.join(HERE, "libemuld.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "emul_vitdec.cpp")])
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(21)
+    pc = oracle.pcodes()
+
+    def mapping(blocks, nbits):
+        m = []
+        for L, PI in blocks:
+            m += [1 if pc[PI - 1][i & 31] else -1 for i in range(L * 128)]
+        m += [1 if (i & 3) < 2 else -1 for i in range(24)]
+        assert len(m) == 4 * (nbits + 6), (len(m), nbits)
+        return np.array(m, np.int16)
+
+    cases = [("fic", mapping([(21, 16), (3, 15)], 768), 768)]
+    for (br, prof_a, lvl) in ((96, 1, 3), (64, 1, 2), (32, 0, 4), (128, 1, 1), (8, 1, 2)):
+        p = oracle.prot_eep(br, prof_a, lvl)
+        cases.append((f"eep{br}/{prof_a}/{lvl}", mapping([(p.L[k], p.PI[k]) for k in range(p.nblk) if p.L[k]], 24 * br), 24 * br))
+    for (br, lvl) in ((64, 3), (32, 1), (192, 5)):
+        p = oracle.prot_uep(br, lvl)
+        cases.append((f"uep{br}/{lvl}", mapping([(p.L[k], p.PI[k]) for k in range(p.nblk) if p.L[k]], 24 * br), 24 * br))
+    cases.append(("plain", np.zeros(4 * (192 + 6), np.int16), 192))
+    for name, m, nbits in cases:
+        n_in = int((m >= 0).sum())
+        for trial in range(3):
+            bits = rng.integers(0, 2, nbits).astype(np.uint8)
+            enc = oracle.conv_encode(bits).astype(np.float32) * 2 - 1
+            full = np.clip(enc * 40 + rng.standard_normal(len(enc)) * (20 + 30 * trial), -127, 127).astype(np.int8)
+            frag = full[m >= 0]
+            assert len(frag) == n_in
+            depunct = np.zeros(len(m), np.int8); depunct[m >= 0] = frag
+            exp = oracle.pack_bits(oracle.viterbi(depunct, nbits))
+            # place the fragment at a 16-byte aligned address with slack behind it
+            raw = np.zeros(n_in + 16 + 192, np.int8)
+            off = (-raw.ctypes.data) % 16
+            raw[off:off + n_in] = frag
+            raw[off + n_in:off + n_in + 160] = rng.integers(-127, 128, 160)          # whatever follows must not matter
+            out = np.zeros(nbits // 8, np.uint8)
+            rc = lib.emul_vitdec(C.c_void_p(raw.ctypes.data + off), m.ctypes.data_as(C.c_void_p), nbits, None, out.ctypes.data_as(C.c_void_p))
+            assert rc == 0 and np.array_equal(out, exp), (name, trial, int((out != exp).sum()))

@@ -21,7 +21,7 @@ struct StreamState {
     int64_t pos;            // logical sample index of the next sample to read
     int32_t coarse, fine;   // Hz; fine has int16 semantics
     int32_t local_phase;    // localPhase after the last sample read
-    int32_t pad0;
+    int32_t acq_failed;     // failed null searches since the last result record (acquire_kernel counts, advance_kernel hands over)
     int32_t acquired;       // 0: null search needed, 1: tracking
     int32_t started;        // 0: sLevel warm-up (T_F/2 samples) not done yet
     float slevel;
@@ -42,6 +42,7 @@ struct StepScratch {        // per stream, rewritten every step
     int64_t r_next_pos;
     int64_t null_pos;       // logical index of the first sample of the null symbol that follows this frame
     int32_t null_lp, null_ph;   // NCO phase before that sample, and the increment the null is read with
+    int32_t r_acq_failed, pad1;
 };
 
 std::string g_create_error;
@@ -191,14 +192,14 @@ __global__ void acquire_kernel(StreamState* st, const float2* iq, int64_t stride
             env[idx & 63] = l1; cur = __fadd_rn(cur, __fsub_rn(l1, env[(idx - 50) & 63])); idx++;
             if (++counter > TF) { fail = true; break; }
         }
-        if (fail) continue;
+        if (fail) { z.acq_failed++; continue; }
         counter = 0;
         while ((double)__fdiv_rn(cur, 50.f) < __dmul_rn(0.75, (double)sl)) {
             if (!get(phase, l1)) return;
             env[idx & 63] = l1; cur = __fadd_rn(cur, __fsub_rn(l1, env[(idx - 50) & 63])); idx++;
             if (++counter > TNULL + 50) { fail = true; break; }
         }
-        if (fail) continue;
+        if (fail) { z.acq_failed++; continue; }
         z.acquired = 1;
         break;
     }
@@ -269,6 +270,8 @@ __global__ void advance_kernel(StreamState* st, StepScratch* scr, int S, int gro
     StepScratch c = scr[s];
     StreamState z = st[s];
     c.r_start_index = z.start_index; c.r_fx = 0.f; c.r_fy = 0.f;
+    c.r_acq_failed = z.acq_failed;
+    if (z.acq_failed) { z.acq_failed = 0; if (!c.active) st[s].acq_failed = 0; }
     if (c.active) {
         float fx = 0.f, fy = 0.f;      // FreqCorr: partial sums in group order
         for (int g = 0; g < groups; g++) { fx += fc_part[(int64_t)s * groups + g].x; fy += fc_part[(int64_t)s * groups + g].y; }
@@ -353,7 +356,7 @@ __global__ void finalize_kernel(const StepScratch* scr, MscSlotState* slots, int
         }
     }
     r.start_index = c.r_start_index; r.freq_corr_re = c.r_fx; r.freq_corr_im = c.r_fy;
-    r.fine_corr = c.r_fine; r.coarse_corr = c.r_coarse; r.fic_ratio = ratio; r.next_pos = c.r_next_pos; r.slevel = c.r_slevel;
+    r.fine_corr = c.r_fine; r.coarse_corr = c.r_coarse; r.fic_ratio = ratio; r.next_pos = c.r_next_pos; r.slevel = c.r_slevel; r.acq_failed = c.r_acq_failed;
     res[s] = r;
 }
 
@@ -498,7 +501,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_prbs_words, w.data(), w.size() * 4, cudaMemcpyHostToDevice);
         // expansion tables of the decoder kernel for the FIC puncturing (fic-handler.cpp:144-191)
         std::vector<uint2> steps; std::vector<uint32_t> soff;
-        build_vit_tables(ctx->host->fic_map, 774, steps, soff);
+        build_vit_tables_u2(ctx->host->fic_map, 774, steps, soff);
         if ((rc = dalloc(ctx, &ctx->d_fic_steptab, steps.size())) || (rc = dalloc(ctx, &ctx->d_fic_stage_off, soff.size()))) return fail(rc);
         cudaMemcpy(ctx->d_fic_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_fic_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice);
@@ -600,7 +603,7 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
         std::vector<int16_t> map((size_t)sl.nsteps * 4);
         build_msc_map(*ctx->host, prof, map.data());
         std::vector<uint2> steps; std::vector<uint32_t> soff;
-        build_vit_tables(map.data(), sl.nsteps, steps, soff);
+        build_vit_tables_u2(map.data(), sl.nsteps, steps, soff);
         std::vector<uint32_t> w; pack_prbs_words(ctx->host->prbs, sl.nbits, w);
         const int flen_pad = (sl.flen + 15) & ~15;
         if ((rc = dalloc(ctx, &sl.d_steptab, steps.size())) || (rc = dalloc(ctx, &sl.d_stage_off, soff.size())) || (rc = dalloc(ctx, &sl.d_prbs_words, w.size())) ||
@@ -931,7 +934,7 @@ static int run_stage_viterbi(dabb_ctx* ctx, const int8_t* soft, int n_cw, int64_
                              const uint32_t* d_prbs_words, uint8_t* out, int64_t out_stride)
 {
     std::vector<uint2> steps; std::vector<uint32_t> soff;
-    build_vit_tables(map, nsteps, steps, soff);
+    build_vit_tables_u2(map, nsteps, steps, soff);
     if ((int)soff.back() > frag) { ctx->err = "de-puncturing map consumes more softbits than provided"; return DABB_E_ARG; }
     const int pitch = (frag + 15) & ~15;
     uint2* d_steps = nullptr; uint32_t* d_soff = nullptr; int8_t* tmp = nullptr;

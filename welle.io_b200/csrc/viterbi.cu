@@ -140,7 +140,6 @@ constexpr int VIT_THREADS = VIT_THREADS_N;     // codewords per CTA
 constexpr int VIT_MIN_CTAS = 512 / VIT_THREADS;   // 512 threads of 128 registers per SM
 constexpr int VIT_ROW_PITCH = 144;      // 128 B of softbits + 16 B pad (rows stay 16-byte aligned for the bulk copies)
 constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
-constexpr int VIT_STAGE_STEPS = 24;     // trellis steps per stage: at most 96 punctured softbits + 15 bytes of alignment slack < 128
 
 template <int VIT_STAGES> struct __align__(16) VitSmemT {
     unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];
@@ -193,8 +192,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 const uint2 e = __ldg(p.steptab + 6 * g + k);           // {byte selector | advance << 16, byte mask}
-                // present softbits -> symbol s + 127 = (s ^ 0x80) - 1 (softbits are >= -127), punctured -> 127 (viterbi.cpp:232-237)
-                w[k] = ((__byte_perm(w0, w1, e.x) & e.y) ^ 0x80808080u) - 0x01010101u;
+                w[k] = vit_expand_step(w0, w1, e.x, e.y);
                 if (e.x & 0x10000u) { w0 = w1; w1 = my[nx]; nx++; }       // warp-uniform
             }
             uint32_t d[12];
@@ -209,40 +207,22 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
     }
     if (!have) return;
     if (p.valid && !p.valid[cw]) return;
-    // Traceback from state 0, skipping the 6 tail steps (viterbi.cpp:313-339).  The decoded bit of a step enters the state at bit 5
-    // and moves down one position per step, so after six steps the state IS the six decoded bits, earliest first from bit 5: the
-    // output is assembled six bits at a time.  96 steps (nbits is a multiple of 96) give three output words; the decision words are
-    // read in batches of 24 independent loads (their addresses do not depend on the path).
+    // traceback (vit_traceback24): 96 steps (nbits is a multiple of 96) give three output words; the decision words are read in
+    // batches of 24 independent loads (their addresses do not depend on the path)
     uint32_t state = 0;
     uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
     const uint32_t* prbs = p.prbs_words;
     for (int tb = p.nbits - 96; tb >= 0; tb -= 96) {
-        uint32_t acc[3] = {0, 0, 0};     // big-endian bit string of the times tb .. tb+95: acc[2] = tb .. tb+31 (time tb at bit 31)
-#pragma unroll
-        for (int q = 3; q >= 0; q--) {
-            uint2 d[24];
-#pragma unroll
-            for (int k = 0; k < 24; k++) d[k] = dec[(int64_t)(tb + 24 * q + k + 6) * VIT_THREADS];
-#pragma unroll
-            for (int h = 3; h >= 0; h--) {
-#pragma unroll
-                for (int k = 5; k >= 0; k--) {
-                    const uint2 dd = d[6 * h + k];
-                    const uint32_t word = (state & 32u) ? dd.y : dd.x;
-                    // bit (state & 31) of the word rotated to bit 5
-                    const uint32_t rot = __funnelshift_r(word, word, state - 5u);
-                    state = (rot & 32u) | (state >> 1);
-                }
-                // state = bits of the times T .. T+5 (T = tb + 24 q + 6 h) from bit 5 down; position of time T+5 counted from the end
-                const int lo = 96 - (24 * q + 6 * h + 6);        // bit offset of time T+5 in the 96-bit string (0 = time tb+95)
-                acc[lo >> 5] |= state << (lo & 31);
-                if ((lo & 31) > 26) acc[(lo >> 5) + 1] |= state >> (32 - (lo & 31));
-            }
-        }
+        uint32_t acc[3] = {0, 0, 0};
+        vit_u2 d[24];
+#define VIT_TB_QUARTER(Q) do { \
+            _Pragma("unroll") for (int k = 0; k < 24; k++) { const uint2 v = dec[(int64_t)(tb + 24 * (Q) + k + 6) * VIT_THREADS]; d[k].x = v.x; d[k].y = v.y; } \
+            vit_traceback24<(Q)>(state, d, acc); } while (0)
+        VIT_TB_QUARTER(3); VIT_TB_QUARTER(2); VIT_TB_QUARTER(1); VIT_TB_QUARTER(0);
+#undef VIT_TB_QUARTER
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            // acc[2 - j] holds the times tb + 32 j .. tb + 32 j + 31, first time at bit 31; memory order is byte (time / 8) first
-            const uint32_t v = __byte_perm(acc[2 - j], 0, 0x0123);
+            const uint32_t v = vit_pack_be(acc[2 - j]);          // acc[2 - j]: the times tb + 32 j .. tb + 32 j + 31
             const int wi = (tb >> 5) + j;
             out[wi] = prbs ? v ^ prbs[wi] : v;
         }
@@ -287,27 +267,9 @@ __global__ void unpack_bits_kernel(const uint8_t* __restrict__ bytes, int64_t st
 
 } // namespace
 
-// Per-profile expansion tables of the decoder kernel from a de-puncturing map (4 entries per trellis step: index into the punctured
-// softbits, consecutive, or -1).  steps[t] = {PRMT selector over the 8-byte window | advance flag << 16, byte mask};
-// stage_off[s] = index of the first softbit consumed by stage s (24 steps), stage_off[nstages] = total.
-void build_vit_tables(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off)
+void build_vit_tables_u2(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off)
 {
-    steps.assign(nsteps, make_uint2(0, 0));
-    stage_off.clear();
-    int cursor = 0, pos = 0;
-    for (int t = 0; t < nsteps; t++) {
-        if (t % VIT_STAGE_STEPS == 0) { stage_off.push_back((uint32_t)cursor); pos = cursor & 3; }
-        uint32_t sel = 0, mask = 0; int n = 0;
-        for (int k = 0; k < 4; k++) {
-            const int m = map[4 * t + k];
-            if (m >= 0) { sel |= (uint32_t)(pos + n) << (4 * k); mask |= 0xFFu << (8 * k); n++; cursor++; }
-        }
-        pos += n;
-        uint32_t adv = 0;
-        if (pos >= 4) { pos -= 4; adv = 1; }
-        steps[t] = make_uint2(sel | (adv << 16), mask);
-    }
-    stage_off.push_back((uint32_t)cursor);
+    build_vit_tables(map, nsteps, steps, stage_off);     // viterbi_core.cuh
 }
 
 void launch_clamp_copy(const int8_t* src, int8_t* dst, int64_t n, cudaStream_t st)

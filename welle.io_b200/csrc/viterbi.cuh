@@ -49,7 +49,7 @@ struct ViterbiParams {
 
 size_t vit_dec_bytes(int n_cw, int nsteps);
 constexpr int VIT_FRAG_SLACK = 160;   // bytes the decoder kernel may read past a codeword's last softbit
-void build_vit_tables(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off);
+void build_vit_tables_u2(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off);
 void launch_clamp_copy(const int8_t* src, int8_t* dst, int64_t n, cudaStream_t st);
 void launch_msc_collect(const MscCollectParams& p, int n_streams, cudaStream_t st);
 void launch_msc_gather(const MscPrepParams& p, int n_streams, cudaStream_t st);

@@ -111,7 +111,9 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32
     (void)one;
     uint32_t N[32];
     // decision bits are OR-ed into four partial words per half (short dependency chains, no branches)
-    uint32_t acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // [0..3]: new states 0..31, [4..7]: new states 32..63
+    // accumulators: index [0..1] new states 0..31, [2..3] new states 32..63; the low and the high half of one packed minimum use
+    // different arrays (the two read-write operands of one asm statement must be distinct variables)
+    uint32_t accl_[4] = {0, 0, 0, 0}, acch_[4] = {0, 0, 0, 0};
     // VIT_MIN(dst, a, b, nl, nh): dst = per-half signed minimum of (a, b); decision bit of new state nl (low half) / nh (high half)
     // is set when b wins strictly ((a - b) > 0: ties keep the a = old[i] branch, viterbi.cpp:263-275).
 #if defined(__CUDA_ARCH__)
@@ -121,18 +123,18 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32
     // with `@p mad.lo acc = bit * 1 + acc` (every bit is set at most once, so add == or): an IMAD on the FMA pipe, which balances
     // the ALU pipe where the packed minimum runs.  `one` is the value 1 passed through a kernel parameter so that the assembler
     // cannot fold the multiply away.
-#define VIT_ACC(n) acc_[(((n) >> 5) << 2) | (((n) >> 3) & 3)]
+#define VIT_ACCI(n) ((((n) >> 5) << 1) | (((n) >> 4) & 1))
 #define VIT_MIN(dst, a, b, nl, nh) \
     asm("{\n.reg .pred pu, pv;\n.reg .u16 r0, r1, r2, r3;\n.reg .b32 m;\n" \
         "min.s16x2 m, %3, %4;\nmov.b32 {r0, r1}, m;\nmov.b32 {r2, r3}, %3;\n" \
         "setp.eq.s16 pv, r0, r2;\nsetp.eq.s16 pu, r1, r3;\n" \
         "@!pv mad.lo.u32 %1, %5, %6, %1;\n@!pu mad.lo.u32 %2, %5, %7, %2;\nmov.b32 %0, m;\n}" \
-        : "=r"(dst), "+r"(VIT_ACC(nl)), "+r"(VIT_ACC(nh)) \
+        : "=r"(dst), "+r"(accl_[VIT_ACCI(nl)]), "+r"(acch_[VIT_ACCI(nh)]) \
         : "r"(a), "r"(b), "r"(one), "r"(1u << ((nl) & 31)), "r"(1u << ((nh) & 31)))
 #else
-#define VIT_ACC(n) acc_[(((n) >> 5) << 2) | (((n) >> 3) & 3)]
+#define VIT_ACCI(n) ((((n) >> 5) << 1) | (((n) >> 4) & 1))
 #define VIT_MIN(dst, a, b, nl, nh) do { bool ph__, pl__; dst = vibmin16(a, b, ph__, pl__); \
-        if (!pl__) VIT_ACC(nl) |= 1u << ((nl) & 31); if (!ph__) VIT_ACC(nh) |= 1u << ((nh) & 31); } while (0)
+        if (!pl__) accl_[VIT_ACCI(nl)] |= 1u << ((nl) & 31); if (!ph__) acch_[VIT_ACCI(nh)] |= 1u << ((nh) & 31); } while (0)
 #endif
     if constexpr (B < 5) {
         constexpr int delta = vit_pat(1 << B);   // pattern change when butterfly bit B flips
@@ -161,9 +163,9 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32
         }
     }
 #undef VIT_MIN
-#undef VIT_ACC
-    dlo = (acc_[0] | acc_[1]) | (acc_[2] | acc_[3]);
-    dhi = (acc_[4] | acc_[5]) | (acc_[6] | acc_[7]);
+#undef VIT_ACCI
+    dlo = (accl_[0] | accl_[1]) | (acch_[0] | acch_[1]);
+    dhi = (accl_[2] | accl_[3]) | (acch_[2] | acch_[3]);
 #pragma unroll
     for (int r = 0; r < 32; r++) Q[r] = N[r];
 }
@@ -198,6 +200,86 @@ VIT_HD void vit_six_steps(uint32_t (&Q)[32], const uint32_t w[6], uint32_t dec[1
     vit_acs<3>(Q, w[3], dec[6], dec[7], one);
     vit_acs<4>(Q, w[4], dec[8], dec[9], one);
     vit_acs<5>(Q, w[5], dec[10], dec[11], one);
+}
+
+// ---- de-puncturing inside the decoder kernel -------------------------------------------------------------------------------
+// The kernel reads the PUNCTURED softbits of a codeword (consecutive bytes) and expands them itself.  Everything about the expansion
+// but the data is the same for all codewords of a launch: per trellis step a byte selector over an 8-byte window of the stream, a
+// byte mask (punctured positions -> softbit 0) and whether the window moves on by one word afterwards.
+struct vit_u2 { uint32_t x, y; };                  // layout of uint2
+constexpr int VIT_STAGE_STEPS = 24;                // steps per staging unit: <= 96 softbits + 15 bytes of alignment slack < 128
+
+// symbol word of one step: four softbits picked from the window (w0 = lower addresses), punctured -> 0, then s + 127 = (s ^ 0x80) - 1
+// per byte (softbits are >= -127, so no byte borrows): the reference's clamp(s + 127, 0, 255) (viterbi.cpp:232-237)
+VIT_HD uint32_t vit_expand_step(uint32_t w0, uint32_t w1, uint32_t sel, uint32_t mask)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t x = __byte_perm(w0, w1, sel);
+#else
+    const uint64_t win = (uint64_t)w0 | ((uint64_t)w1 << 32);
+    uint32_t x = 0;
+    for (int k = 0; k < 4; k++) x |= (uint32_t)((win >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+#endif
+    return ((x & mask) ^ 0x80808080u) - 0x01010101u;
+}
+
+// Expansion tables from a de-puncturing map (4 entries per trellis step: >= 0 present - the punctured softbits are consumed in
+// order - or < 0 punctured).  steps[t] = {selector | advance flag << 16, mask}; stage_off[s] = index of the first softbit consumed
+// by stage s (VIT_STAGE_STEPS steps; the kernel stages the aligned 128 bytes from there), stage_off[nstages] = total consumed.
+template <class StepVec, class OffVec>
+inline void build_vit_tables(const int16_t* map, int nsteps, StepVec& steps, OffVec& stage_off)
+{
+    steps.clear(); stage_off.clear();
+    int cursor = 0, pos = 0;
+    for (int t = 0; t < nsteps; t++) {
+        if (t % VIT_STAGE_STEPS == 0) { stage_off.push_back((uint32_t)cursor); pos = cursor & 3; }
+        uint32_t sel = 0, mask = 0; int n = 0;
+        for (int k = 0; k < 4; k++)
+            if (map[4 * t + k] >= 0) { sel |= (uint32_t)(pos + n) << (4 * k); mask |= 0xFFu << (8 * k); n++; cursor++; }
+        pos += n;
+        uint32_t adv = 0;
+        if (pos >= 4) { pos -= 4; adv = 1; }
+        typename StepVec::value_type e; e.x = sel | (adv << 16); e.y = mask;
+        steps.push_back(e);
+    }
+    stage_off.push_back((uint32_t)cursor);
+}
+
+// ---- traceback ------------------------------------------------------------------------------------------------------------------
+// From state 0 after the last step, skipping the 6 tail steps (viterbi.cpp:313-339): bit = decision[t + 6][state],
+// state = (state >> 1) | (bit << 5).  The decoded bit enters the state at bit 5 and moves down one position per step, so after six
+// steps the state IS the six decoded bits, earliest first from bit 5: the output is assembled six bits at a time.
+// One call handles 24 steps: d[k] = decision words of the times T0 + k (T0 + 23 first); acc[3] collects a 96-bit big-endian string
+// of the times tb .. tb + 95 (acc[2] bit 31 = time tb); q = which quarter (T0 = tb + 24 q).
+template <int Q24> VIT_HD void vit_traceback24(uint32_t& state, const vit_u2 (&d)[24], uint32_t (&acc)[3])
+{
+#pragma unroll
+    for (int h = 3; h >= 0; h--) {
+#pragma unroll
+        for (int k = 5; k >= 0; k--) {
+            const uint32_t word = (state & 32u) ? d[6 * h + k].y : d[6 * h + k].x;
+#if defined(__CUDA_ARCH__)
+            const uint32_t rot = __funnelshift_r(word, word, state - 5u);       // bit (state & 31) of the word rotated to bit 5
+#else
+            const uint32_t sh = (state - 5u) & 31u;
+            const uint32_t rot = sh ? ((word >> sh) | (word << (32 - sh))) : word;
+#endif
+            state = (rot & 32u) | (state >> 1);
+        }
+        // state = the bits of the times T .. T+5 (T = tb + 24 Q24 + 6 h), time T at bit 5
+        const int lo = 96 - (24 * Q24 + 6 * h + 6);        // offset of time T+5 in the 96-bit string (0 = time tb + 95)
+        acc[lo >> 5] |= state << (lo & 31);
+        if ((lo & 31) > 26) acc[(lo >> 5) + 1] |= state >> (32 - (lo & 31));
+    }
+}
+// the 32 decoded bits of acc (first time at bit 31) -> output word: bit t MSB-first in byte t / 8, bytes in memory order
+VIT_HD uint32_t vit_pack_be(uint32_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, 0, 0x0123);
+#else
+    return (a >> 24) | ((a >> 8) & 0xFF00u) | ((a << 8) & 0xFF0000u) | (a << 24);
+#endif
 }
 
 // soft bit (int8, 0 = punctured) -> decoder symbol clamp(s + 127, 0, 255)  (viterbi.cpp:232-237)

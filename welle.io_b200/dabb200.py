@@ -51,14 +51,14 @@ class FrameResult(C.Structure):
                 ("n_logical", C.c_int32 * MAX_SUBCH), ("n_rs_events", C.c_int32 * MAX_SUBCH), ("rs_uncorr_mask", C.c_int32 * MAX_SUBCH),
                 ("rs_corr", (C.c_int32 * 4) * MAX_SUBCH), ("sf_ready", C.c_int32 * MAX_SUBCH), ("sf_au_count", C.c_int32 * MAX_SUBCH),
                 ("sf_au_crc_mask", C.c_int32 * MAX_SUBCH), ("next_pos", C.c_int64), ("freq_corr_re", C.c_float), ("freq_corr_im", C.c_float),
-                ("slevel", C.c_float), ("reserved", C.c_int32 * 3)]
+                ("slevel", C.c_float), ("acq_failed", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 RESULT_DTYPE = np.dtype([("status", "<i4"), ("start_index", "<i4"), ("fine_corr", "<i4"), ("coarse_corr", "<i4"), ("snr_raw", "<i4"),
                          ("fib_crc_mask", "<i4"), ("fic_ratio", "<i4"), ("n_logical", "<i4", (4,)), ("n_rs_events", "<i4", (4,)),
                          ("rs_uncorr_mask", "<i4", (4,)), ("rs_corr", "<i4", (4, 4)), ("sf_ready", "<i4", (4,)), ("sf_au_count", "<i4", (4,)),
                          ("sf_au_crc_mask", "<i4", (4,)), ("next_pos", "<i8"), ("freq_corr_re", "<f4"), ("freq_corr_im", "<f4"),
-                         ("slevel", "<f4"), ("reserved", "<i4", (3,))], align=True)
+                         ("slevel", "<f4"), ("acq_failed", "<i4"), ("reserved", "<i4", (2,))], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(FrameResult), (RESULT_DTYPE.itemsize, C.sizeof(FrameResult))
 
 

@@ -29,7 +29,7 @@ typedef std::complex<float> complexf;
 typedef int8_t softbit_t;
 #define INPUT_RATE 2048000
 
-enum class CharacterSet { EbuLatin = 0, UnicodeUcs2 = 6, UnicodeUtf8 = 15, Undefined = 16 };
+enum class CharacterSet : uint8_t { EbuLatin = 0x00, UnicodeUcs2 = 0x06, UnicodeUtf8 = 0x0F, Undefined };     /* backend/charsets.h:34-39 */
 enum class TransportMode { Audio = 0, StreamData = 1, FIDC = 2, PacketData = 3 };
 enum class AudioServiceComponentType { DAB, DABPlus, Unknown };
 

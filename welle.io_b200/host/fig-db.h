@@ -48,12 +48,14 @@ public:
     dab_date_time_t dateTime; bool timeOffsetReceived = false;
     std::map<uint32_t, int8_t> repeatCount;
     std::chrono::steady_clock::time_point lastDecrement = std::chrono::steady_clock::now();
+    std::chrono::system_clock::time_point timeLastFCT0Frame = std::chrono::system_clock::now();     /* fib-processor.cpp:141,1272 */
 
     void clear()
     {
         std::lock_guard<std::mutex> l(m);
         components.clear(); subch.assign(64, Subchannel()); services.clear(); repeatCount.clear();
         lastDecrement = std::chrono::steady_clock::now();
+        timeLastFCT0Frame = std::chrono::system_clock::now();
     }
 
     Service* findService(uint32_t sid) { for (auto& s : services) if (s.serviceId == sid) return &s; return nullptr; }
@@ -138,6 +140,8 @@ private:
             case 0: {
                 const uint16_t e = (uint16_t)rd(16, 16);
                 if (e != eid) { eid = e; ev.list.push_back({FigEvents::NewEnsemble, e}); }
+                /* CIF counter low part == 0: every twelve seconds in mode I (fib-processor.cpp:132-142, RadioReceiverStats) */
+                if (rd(40, 8) % 250 == 0) timeLastFCT0Frame = std::chrono::system_clock::now();
                 if (rd(32, 2) != 0) ev.list.push_back({FigEvents::RestartService, 0});
                 break;
             }

@@ -79,8 +79,13 @@ struct RadioReceiver::Impl {
     struct Slot { bool used = false; uint32_t sid = 0; ProgrammeHandlerInterface* handler = nullptr; FILE* dump = nullptr; int bitrate = 0; bool dabplus = false; };
     Slot slots[DABB_MAX_SUBCH];
     std::mutex slotMutex;
-    std::mutex ctxMutex;                    /* serialises dabb_set_options with dabb_process (one submitting thread per handle) */
+    /* The library context is not thread safe (one submitting thread per handle): EVERY dabb_* call on ctx is made under ctxMutex -
+     * the worker's dabb_process / dabb_read_tap as well as the application thread's select / remove / reset / set_options.  Lock order
+     * where both are needed: slotMutex, then ctxMutex. */
+    std::mutex ctxMutex;
     bool synced = false; float snr = 0; int snrCount = 0; long sampleCnt = 0;
+    /* OFDMProcessor::scanMode / attempts (ofdm-processor.cpp:258-262,351-355): set by restart(doScan) */
+    std::atomic<bool> scanMode{false}; int failedSearches = 0;
 
     /* the reference's enumerators (radio-receiver-options.h:35-64) -> DABB_PLACEMENT_* / DABB_FREQSYNC_* (0 = the reference's default) */
     static int placementOf(FFTPlacementMethod m) { return m == FFTPlacementMethod::StrongestPeak ? DABB_PLACEMENT_STRONGEST_PEAK : m == FFTPlacementMethod::EarliestPeakWithBinning ? DABB_PLACEMENT_EARLIEST_PEAK_WITH_BINNING : DABB_PLACEMENT_THRESHOLD_BEFORE_PEAK; }
@@ -118,7 +123,10 @@ struct RadioReceiver::Impl {
                 avail = input.getSamplesToRead();
             }
             if (!running) return false;
-            const int32_t want = (int32_t)std::min<int64_t>(n, std::min<int64_t>(avail, 32768));
+            /* never more than one symbol per call, like the reference (its n is an int16_t: T_u, T_s or T_null samples): CRAWFile
+             * over-reports cf32 availability four times (raw_file.cpp:239-242) and its getSamples waits until the ring really holds
+             * the request, which a large request can never be (256 KiB ring = 32 768 cf32 samples) */
+            const int32_t want = (int32_t)std::min<int64_t>(n, std::min<int64_t>(avail, DABB_TS));
             const int32_t got = input.getSamples(dst, want);
             if (got <= 0) { if (!input.is_ok()) return false; continue; }
             dst += got; n -= got; sampleCnt += got;
@@ -136,8 +144,8 @@ struct RadioReceiver::Impl {
         bool tracking = false;
         dabb_frame_result res; uint8_t fibs[12 * 32];
         std::vector<uint8_t> msc((size_t)DABB_MAX_SUBCH * 4 * 1152), sf((size_t)DABB_MAX_SUBCH * 5760);
-        dabb_stream_reset(ctx, 0, 1, 0);
-        bool failed = false;
+        { std::lock_guard<std::mutex> l(ctxMutex); dabb_stream_reset(ctx, 0, 1, 0); }
+        bool failed = false; failedSearches = 0;
         while (running) {
             /* acquisition needs the sLevel warm-up, the null search and a whole frame: 3 frames; tracking one frame */
             const int64_t need_end = pos + (tracking ? need_track : acq_need);
@@ -154,20 +162,30 @@ struct RadioReceiver::Impl {
             int prc; { std::lock_guard<std::mutex> l(ctxMutex); prc = dabb_process(ctx, &io); }
             if (prc != DABB_OK) { rci.onMessage(message_level_t::Error, "B200 backend", dabb_last_error(ctx)); failed = true; break; }
             pos = res.next_pos;
+            /* every entry into the reference's notSynced state but the first follows a failed null search or a failed SyncOnPhase:
+             * with doScan the sixth entry reports "no signal", the first successful SyncOnPhase "signal" (ofdm-processor.cpp:258-262,351-355) */
+            failedSearches += res.acq_failed + (res.status == DABB_FRAME_NO_SYNC ? 1 : 0);
+            if (scanMode.load() && res.status != DABB_FRAME_DECODED && failedSearches >= 5) { rci.onSignalPresence(false); scanMode = false; failedSearches = 0; }
             if (res.status == DABB_FRAME_DECODED) {
+                if (scanMode.load()) { rci.onSignalPresence(true); scanMode = false; failedSearches = 0; }
                 if (!synced) { synced = true; rci.onSyncChange(true); }
                 tracking = true; acq_need = 3 * TF;
                 dispatch(res, fibs, msc.data(), sf.data());
             } else if (res.status == DABB_FRAME_NO_SYNC) {
                 if (synced) { synced = false; rci.onSyncChange(false); }
                 tracking = false;
+                {   /* the impulse response is handed over after every findIndex, found or not (ofdm-processor.cpp:341-345) */
+                    std::vector<float> cir(DABB_TU);
+                    int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 1, cir.data(), cir.size() * sizeof(float)); }
+                    if (trc == DABB_OK) rci.onNewImpulseResponse(std::move(cir));
+                }
             } else if (res.status == DABB_FRAME_ACQUIRING) {
                 if (synced) { synced = false; rci.onSyncChange(false); }
                 tracking = false;
                 /* the null search did not finish inside the samples at hand: give it one more frame, and after five frames
                  * without a null start over two frames further on */
-                if (acq_need < 5 * TF) acq_need += TF;
-                else { pos += 2 * TF; acq_need = 3 * TF; dabb_stream_reset(ctx, 0, 1, pos); }
+                /* the search keeps its progress (position, level, oscillator phase) between calls: just keep feeding it */
+                acq_need = 3 * TF;
             } else {
                 /* DABB_FRAME_NEED_SAMPLES cannot happen (the loop above always supplies the samples a frame needs); if the library and the
                  * glue ever disagree about that number, stop instead of spinning */
@@ -186,15 +204,18 @@ struct RadioReceiver::Impl {
         if (sampleCnt > INPUT_RATE / 5) { rci.onFrequencyCorrectorChange(r.fine_corr, r.coarse_corr); sampleCnt = 0; }   /* ofdm-processor.cpp:218-223 */
         {
             std::vector<float> cir(DABB_TU);
-            if (dabb_read_tap(ctx, 1, cir.data(), cir.size() * sizeof(float)) == DABB_OK) rci.onNewImpulseResponse(std::move(cir));
+            int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 1, cir.data(), cir.size() * sizeof(float)); }
+            if (trc == DABB_OK) rci.onNewImpulseResponse(std::move(cir));
         }
         {   /* OfdmDecoder hands over r1 of every 96th carrier once per frame (ofdm-decoder.cpp:119-125,216-218) */
             std::vector<DSPCOMPLEX> pts((size_t)(DABB_L - 1) * DABB_K / 96);
-            if (dabb_read_tap(ctx, 2, pts.data(), pts.size() * sizeof(DSPCOMPLEX)) == DABB_OK) rci.onConstellationPoints(std::move(pts));
+            int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 2, pts.data(), pts.size() * sizeof(DSPCOMPLEX)); }
+            if (trc == DABB_OK) rci.onConstellationPoints(std::move(pts));
         }
         {   /* the null symbol that follows the frame, as read with the corrected oscillator (ofdm-processor.cpp:462-469) */
             std::vector<DSPCOMPLEX> nul(DABB_TNULL);
-            if (dabb_read_tap(ctx, 3, nul.data(), nul.size() * sizeof(DSPCOMPLEX)) == DABB_OK) rci.onNewNullSymbol(std::move(nul));
+            int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 3, nul.data(), nul.size() * sizeof(DSPCOMPLEX)); }
+            if (trc == DABB_OK) rci.onNewNullSymbol(std::move(nul));
         }
         for (int f = 0; f < 12; f++) {
             uint8_t bits[256];
@@ -246,6 +267,7 @@ struct RadioReceiver::Impl {
         }
         if (!sub.valid()) return false;
         std::lock_guard<std::mutex> l(slotMutex);
+        std::lock_guard<std::mutex> lc(ctxMutex);          /* the worker may be inside dabb_process: wait for the frame to finish */
         if (unique) for (int k = 0; k < DABB_MAX_SUBCH; k++) if (slots[k].used) { dabb_remove_subchannel(ctx, 0, 1, k); if (slots[k].dump) fclose(slots[k].dump); slots[k] = Slot(); }
         for (int k = 0; k < DABB_MAX_SUBCH; k++) if (slots[k].used && slots[k].sid == srv.serviceId) return true;   /* already decoding (msc-handler.cpp:69-74) */
         int k = 0;
@@ -273,9 +295,9 @@ RadioReceiver::~RadioReceiver() {}
 
 void RadioReceiver::restart(bool doScan)
 {
-    (void)doScan;
     d->stopWorker(); d->closeSlots(); d->db.clear();
-    for (int k = 0; k < DABB_MAX_SUBCH; k++) dabb_remove_subchannel(d->ctx, 0, 1, k);
+    d->scanMode = doScan;                                    /* OFDMProcessor::set_scanMode (radio-receiver.cpp:84) */
+    { std::lock_guard<std::mutex> l(d->ctxMutex); for (int k = 0; k < DABB_MAX_SUBCH; k++) dabb_remove_subchannel(d->ctx, 0, 1, k); }
     d->input.restart();
     d->synced = false; d->running = true;
     d->worker = std::thread(&Impl::run, d.get());
@@ -283,6 +305,7 @@ void RadioReceiver::restart(bool doScan)
 void RadioReceiver::restart_decoder()
 {
     d->closeSlots(); d->db.clear();
+    std::lock_guard<std::mutex> l(d->ctxMutex);
     for (int k = 0; k < DABB_MAX_SUBCH; k++) dabb_remove_subchannel(d->ctx, 0, 1, k);
 }
 void RadioReceiver::stop()
@@ -297,7 +320,7 @@ bool RadioReceiver::removeServiceToDecode(const Service& s)
     std::lock_guard<std::mutex> l(d->slotMutex);
     for (int k = 0; k < DABB_MAX_SUBCH; k++)
         if (d->slots[k].used && d->slots[k].sid == s.serviceId) {
-            dabb_remove_subchannel(d->ctx, 0, 1, k);
+            { std::lock_guard<std::mutex> lc(d->ctxMutex); dabb_remove_subchannel(d->ctx, 0, 1, k); }
             if (d->slots[k].dump) fclose(d->slots[k].dump);
             d->slots[k] = Impl::Slot();
             return true;
@@ -337,7 +360,13 @@ Subchannel RadioReceiver::getSubchannel(const ServiceComponent& sc) const
     return d->db.subch.at(sc.subchannelId);          /* throws std::out_of_range like the reference's vector::at (fib-processor.cpp:1313) */
 }
 DABParams& RadioReceiver::getParams() { return d->params; }
-RadioReceiverStats RadioReceiver::getReceiverStats() const { return RadioReceiverStats(); }
+RadioReceiverStats RadioReceiver::getReceiverStats() const
+{
+    RadioReceiverStats s;
+    std::lock_guard<std::mutex> l(d->db.m);
+    s.timeLastFCT0Frame = d->db.timeLastFCT0Frame;          /* radio-receiver.cpp:225-230 */
+    return s;
+}
 
 /* test hook: feeds n FIBs (32 bytes each) to a fresh service database and writes its text dump (callbacks first) */
 extern "C" int welle_b200_figdb_dump(const uint8_t* fibs, int n, char* out, int cap)
