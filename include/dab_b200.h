@@ -170,6 +170,14 @@ int dabb_process(dabb_ctx* ctx, const dabb_io* io);
 /* asynchronous form for benchmarking with device-resident inputs: enqueue only, no host copies */
 int dabb_process_async(dabb_ctx* ctx, const dabb_io* io);
 int dabb_sync(dabb_ctx* ctx);
+/* Pipelined form of dabb_process for HOST buffers (io->iq_is_host must be 1; pinned memory for full overlap): dabb_submit enqueues the
+ * host->device copy of the step's samples on a copy stream (two device staging slots), the kernels, and the device->host copy of the
+ * results into pinned staging, and returns without waiting; at most two steps may be outstanding (DABB_E_STATE otherwise).
+ * dabb_collect waits for the OLDEST outstanding step and writes its results to the output pointers given at that dabb_submit (they
+ * must stay valid until then; io->iq must stay valid until the step has been collected).  Results come back in submit order; the
+ * copy of step n+1 overlaps the kernels of step n and the read-back of step n-1. */
+int dabb_submit(dabb_ctx* ctx, const dabb_io* io);
+int dabb_collect(dabb_ctx* ctx);
 /* makes the context's main stream (dabb_cuda_stream) wait for everything enqueued so far on the library's other streams, so that an
  * event recorded on it afterwards marks the completion of all work of the preceding dabb_process_async calls (timing) */
 int dabb_join_lanes(dabb_ctx* ctx);

@@ -17,7 +17,12 @@ extern "C" void emul_viterbi(int nbits, const int8_t* soft, uint8_t* out)
     unsigned state = 0;
     for (int t = nbits - 1; t >= 0; t--) {
         const uint64_t d = (uint64_t)dl[t + 6] | ((uint64_t)dh[t + 6] << 32);
-        const unsigned k = (unsigned)(d >> state) & 1u;
+        unsigned pos = 0;
+        switch ((t + 6) % 6) {       // the decision layout of step s is that of vit_acs<s % 6>
+            case 0: pos = vit_dec_pos<0>(state); break; case 1: pos = vit_dec_pos<1>(state); break; case 2: pos = vit_dec_pos<2>(state); break;
+            case 3: pos = vit_dec_pos<3>(state); break; case 4: pos = vit_dec_pos<4>(state); break; default: pos = vit_dec_pos<5>(state); break;
+        }
+        const unsigned k = (unsigned)(d >> pos) & 1u;
         state = (state >> 1) | (k << 5);
         out[t] = (uint8_t)k;
     }

@@ -52,7 +52,7 @@ def test_null_context_is_rejected_everywhere():
     calls = {
         "dabb_stream_reset": (null, 0, 1, C.c_int64(0)), "dabb_set_options": (null, null), "dabb_get_info": (null, 0, null),
         "dabb_select_subchannel": (null, 0, 1, 0, null), "dabb_remove_subchannel": (null, 0, 1, 0),
-        "dabb_process": (null, null), "dabb_process_async": (null, null), "dabb_sync": (null,), "dabb_join_lanes": (null,),
+        "dabb_process": (null, null), "dabb_process_async": (null, null), "dabb_sync": (null,), "dabb_join_lanes": (null,), "dabb_submit": (null, null), "dabb_collect": (null,),
         "dabb_profile": (null, 1), "dabb_profile_read": (null, null, C.c_size_t(0)), "dabb_read_tap": (null, 0, null, C.c_size_t(0)),
         "dabb_ofdm_demod": (null, null, C.c_int64(0), null, 1, null, null, null, null),
         "dabb_find_index": (null, null, C.c_int64(0), null, 1, null, null), "dabb_find_index_ex": (null, null, C.c_int64(0), null, 1, 0, null, null),

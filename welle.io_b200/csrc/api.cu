@@ -71,6 +71,15 @@ struct dabb_ctx {
     uint32_t* d_fic_prbs_words = nullptr;
     std::vector<MscSlotState> h_slots;
     float2* d_iq_stage = nullptr; size_t iq_stage_samples = 0; uint8_t* d_raw_stage = nullptr; size_t raw_stage_bytes = 0;
+    // pipelined host-buffer path (dabb_submit / dabb_collect): copy stream, two device staging slots, two result slots in pinned memory
+    cudaStream_t streamC = nullptr; cudaEvent_t evH2D[2] = {nullptr, nullptr}, evStageFree[2] = {nullptr, nullptr}; bool stageFreeValid[2] = {false, false};
+    void* d_stage2[2] = {nullptr, nullptr}; size_t stage2_bytes[2] = {0, 0};
+    struct Pending {
+        bool used = false; cudaEvent_t done = nullptr; dabb_io io{};
+        dabb_frame_result* h_res = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr; size_t msc_bytes = 0, sf_bytes = 0;
+        int flen[DABB_MAX_SUBCH] = {0, 0, 0, 0}; size_t msc_off[DABB_MAX_SUBCH] = {0, 0, 0, 0}, sf_off[DABB_MAX_SUBCH] = {0, 0, 0, 0};
+    } pend[2];
+    int pend_head = 0, pend_count = 0; int64_t submits = 0;
     // pinned host staging for results
     dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
     int groups = 1; int fc_pitch = 1; int tail_frames = 0; int nco_fast = 0;
@@ -540,6 +549,15 @@ void dabb_destroy(dabb_ctx* ctx)
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
     if (ctx->d_raw_stage) cudaFree(ctx->d_raw_stage);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->d_stage2[i]) cudaFree(ctx->d_stage2[i]);
+        if (ctx->evH2D[i]) cudaEventDestroy(ctx->evH2D[i]);
+        if (ctx->evStageFree[i]) cudaEventDestroy(ctx->evStageFree[i]);
+        auto& p = ctx->pend[i];
+        if (p.done) cudaEventDestroy(p.done);
+        if (p.h_res) cudaFreeHost(p.h_res); if (p.h_fibs) cudaFreeHost(p.h_fibs); if (p.h_msc) cudaFreeHost(p.h_msc); if (p.h_sf) cudaFreeHost(p.h_sf);
+    }
+    if (ctx->streamC) cudaStreamDestroy(ctx->streamC);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->h_fibs) cudaFreeHost(ctx->h_fibs);
     if (ctx->h_msc) cudaFreeHost(ctx->h_msc);
@@ -654,27 +672,15 @@ static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const
     return check_launch(ctx, "fic_crc_kernel");
 }
 
+static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int64_t stride);
+
 int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
 {
     if (!ctx || !io || !io->iq || !io->buf_start) return DABB_E_ARG;
     cudaSetDevice(ctx->device);
     const int S = ctx->S;
     int rc;
-    // Two lanes: A = acquisition, time sync, OFDM demod and the sync-state update of frame n; B = FIC, MSC, RS and the
-    // result record of frame n.  Lane A of frame n+1 only needs lane A of frame n, so B(n) overlaps A(n+1); the per-frame
-    // scratch and the softbits are double buffered by frame parity.  With per-kernel profiling on everything runs
-    // serially on the main stream.
-    const int par = (int)(ctx->step & 1);
-    const bool serial = ctx->prof;
-    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 1;
-    cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
-    StepScratch* scr = ctx->d_scr + (size_t)par * S;
-    int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
-    int32_t* d_nco_sync = ctx->d_nco_sync + (size_t)par * 2 * S; int32_t* d_nco_frame = ctx->d_nco_frame + (size_t)par * 4 * S;
-    int32_t* d_active = ctx->d_active + (size_t)par * S; int32_t* d_index = ctx->d_index + (size_t)par * S; int32_t* d_snr = ctx->d_snr + (size_t)par * S;
-    float2* d_fc = ctx->d_fc + (size_t)par * S * ctx->fc_pitch; float* d_lvl = ctx->d_lvl + (size_t)par * S * ctx->fc_pitch;
-    int8_t* d_soft = ctx->d_soft + (size_t)par * S * DABB_SOFT_PER_FRAME;
-
+    cudaStream_t A = ctx->stream;
     const float2* iq = reinterpret_cast<const float2*>(io->iq);
     int64_t stride = io->stride_samples;
     const int fmt = io->iq_format;
@@ -714,6 +720,29 @@ int dabb_process_async(dabb_ctx* ctx, const dabb_io* io)
         }
         iq = ctx->d_iq_stage; stride = io->buf_len;
     }
+    return enqueue_step(ctx, io, iq, stride);
+}
+
+// one decode step on device-resident cf32 samples (stream s at iq + s * stride)
+static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int64_t stride)
+{
+    const int S = ctx->S;
+    int rc;
+    // Two lanes: A = acquisition, time sync, OFDM demod and the sync-state update of frame n; B = FIC, MSC, RS and the
+    // result record of frame n.  Lane A of frame n+1 only needs lane A of frame n, so B(n) overlaps A(n+1); the per-frame
+    // scratch and the softbits are double buffered by frame parity.  With per-kernel profiling on everything runs
+    // serially on the main stream.
+    const int par = (int)(ctx->step & 1);
+    const bool serial = ctx->prof;
+    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 1;
+    cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
+    StepScratch* scr = ctx->d_scr + (size_t)par * S;
+    int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
+    int32_t* d_nco_sync = ctx->d_nco_sync + (size_t)par * 2 * S; int32_t* d_nco_frame = ctx->d_nco_frame + (size_t)par * 4 * S;
+    int32_t* d_active = ctx->d_active + (size_t)par * S; int32_t* d_index = ctx->d_index + (size_t)par * S; int32_t* d_snr = ctx->d_snr + (size_t)par * S;
+    float2* d_fc = ctx->d_fc + (size_t)par * S * ctx->fc_pitch; float* d_lvl = ctx->d_lvl + (size_t)par * S * ctx->fc_pitch;
+    int8_t* d_soft = ctx->d_soft + (size_t)par * S * DABB_SOFT_PER_FRAME;
+
     // the buffers of this parity were last used by lane B two frames ago
     if (!serial && ctx->evB_valid[par]) CK(cudaStreamWaitEvent(A, ctx->evB[par], 0));
     CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, A));
@@ -813,6 +842,130 @@ int dabb_process(dabb_ctx* ctx, const dabb_io* io)
                             sl.d_sf, (size_t)5 * flen_pad, 5 * sl.flen, S, cudaMemcpyDeviceToHost));
         }
     }
+    return DABB_OK;
+}
+
+// ---- pipelined host-buffer path -------------------------------------------------------------------------------------------------
+// dabb_submit: H2D of the step's samples on a copy stream into one of two device staging slots, the kernels on the lanes, D2H of the
+// results into one of two pinned result slots on lane B - and return.  dabb_collect: wait for the OLDEST outstanding step and hand
+// its results to the pointers given at submit.  With two steps outstanding the copy of step n+1 overlaps the kernels of step n and
+// the result read-back of step n-1.
+static int ensure_pending(dabb_ctx* ctx, dabb_ctx::Pending& p)
+{
+    const int S = ctx->S;
+    if (!p.done) CK(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    if (!p.h_res) CK(cudaHostAlloc((void**)&p.h_res, sizeof(dabb_frame_result) * S, cudaHostAllocDefault));
+    if (!p.h_fibs) CK(cudaHostAlloc((void**)&p.h_fibs, (size_t)S * 12 * 32, cudaHostAllocDefault));
+    size_t msc = 0, sf = 0;
+    for (int k = 0; k < ctx->n_slots; k++) {
+        const auto& sl = ctx->slot[k];
+        p.flen[k] = sl.configured ? sl.flen : 0;
+        if (!sl.configured) continue;
+        const size_t fp = (size_t)((sl.flen + 15) & ~15);
+        p.msc_off[k] = msc; p.sf_off[k] = sf;
+        msc += (size_t)S * 4 * fp; sf += (size_t)S * 5 * fp;
+    }
+    if (msc > p.msc_bytes) { if (p.h_msc) cudaFreeHost(p.h_msc); p.h_msc = nullptr; CK(cudaHostAlloc((void**)&p.h_msc, msc, cudaHostAllocDefault)); p.msc_bytes = msc; }
+    if (sf > p.sf_bytes) { if (p.h_sf) cudaFreeHost(p.h_sf); p.h_sf = nullptr; CK(cudaHostAlloc((void**)&p.h_sf, sf, cudaHostAllocDefault)); p.sf_bytes = sf; }
+    return DABB_OK;
+}
+
+int dabb_submit(dabb_ctx* ctx, const dabb_io* io)
+{
+    if (!ctx || !io || !io->iq || !io->buf_start || !io->iq_is_host) return DABB_E_ARG;
+    if (ctx->prof) { ctx->err = "dabb_submit is not available while per-kernel profiling is on"; return DABB_E_STATE; }
+    if (ctx->pend_count == 2) { ctx->err = "two steps are outstanding: call dabb_collect first"; return DABB_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const int S = ctx->S, fmt = io->iq_format;
+    if (fmt < 0 || fmt > DABB_IQ_S16BE) { ctx->err = "unknown iq_format"; return DABB_E_ARG; }
+    int rc;
+    if (!ctx->streamC) {
+        CK(cudaStreamCreateWithFlags(&ctx->streamC, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->evH2D[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evStageFree[i], cudaEventDisableTiming)); }
+    }
+    const int slot = (int)(ctx->submits & 1);
+    dabb_ctx::Pending& p = ctx->pend[(ctx->pend_head + ctx->pend_count) & 1];
+    if ((rc = ensure_pending(ctx, p))) return rc;
+    cudaStream_t A = ctx->stream, B = ctx->streamB, Cs = ctx->streamC;
+    const size_t bps = fmt == DABB_IQ_CF32 ? 8 : ((fmt == DABB_IQ_U8 || fmt == DABB_IQ_S8) ? 2 : 4);
+    const size_t need = (size_t)S * io->buf_len * bps;
+    if (need > ctx->stage2_bytes[slot]) {
+        sync_all(ctx); cudaStreamSynchronize(Cs);
+        if (ctx->d_stage2[slot]) cudaFree(ctx->d_stage2[slot]);
+        ctx->d_stage2[slot] = nullptr; ctx->stage2_bytes[slot] = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_stage2[slot], need);
+        if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(pipelined staging): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+        ctx->stage2_bytes[slot] = need; ctx->stageFreeValid[slot] = false;
+    }
+    // the staging slot was last read by the step submitted two calls ago
+    if (ctx->stageFreeValid[slot]) CK(cudaStreamWaitEvent(Cs, ctx->evStageFree[slot], 0));
+    CK(cudaMemcpy2DAsync(ctx->d_stage2[slot], (size_t)io->buf_len * bps, io->iq, (size_t)io->stride_samples * bps, (size_t)io->buf_len * bps, S, cudaMemcpyHostToDevice, Cs));
+    CK(cudaEventRecord(ctx->evH2D[slot], Cs));
+    CK(cudaStreamWaitEvent(A, ctx->evH2D[slot], 0));
+    const float2* iq = reinterpret_cast<const float2*>(ctx->d_stage2[slot]);
+    if (fmt != DABB_IQ_CF32) {
+        const size_t ns = (size_t)S * io->buf_len;
+        if (ns > ctx->iq_stage_samples) {
+            sync_all(ctx);
+            if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
+            ctx->d_iq_stage = nullptr; ctx->iq_stage_samples = 0;
+            cudaError_t e = cudaMalloc((void**)&ctx->d_iq_stage, ns * sizeof(float2));
+            if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(iq staging): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
+            ctx->iq_stage_samples = ns;
+        }
+        const dim3 grid((unsigned)((io->buf_len + 255) / 256), (unsigned)S);
+        convert_iq_kernel<<<grid, 256, 0, A>>>(reinterpret_cast<const uint8_t*>(ctx->d_stage2[slot]), io->buf_len, fmt, ctx->d_iq_stage, io->buf_len, io->buf_len, S);
+        if ((rc = check_launch(ctx, "convert_iq_kernel"))) return rc;
+        CK(cudaEventRecord(ctx->evStageFree[slot], A)); ctx->stageFreeValid[slot] = true;       // the raw bytes are consumed
+        iq = ctx->d_iq_stage;
+    }
+    if ((rc = enqueue_step(ctx, io, iq, io->buf_len))) return rc;
+    if (fmt == DABB_IQ_CF32) { CK(cudaEventRecord(ctx->evStageFree[slot], A)); ctx->stageFreeValid[slot] = true; }   // lane A has read the samples
+    // results -> pinned slot, on lane B behind the step's result record
+    if (io->results) CK(cudaMemcpyAsync(p.h_res, ctx->d_results, sizeof(dabb_frame_result) * S, cudaMemcpyDeviceToHost, B));
+    if (io->fibs) CK(cudaMemcpyAsync(p.h_fibs, ctx->d_fibs, (size_t)S * 12 * 32, cudaMemcpyDeviceToHost, B));
+    for (int k = 0; k < ctx->n_slots; k++) {
+        const auto& sl = ctx->slot[k];
+        if (!sl.configured) continue;
+        const size_t fp = (size_t)((sl.flen + 15) & ~15);
+        if (io->msc) {
+            if (io->msc_stride < sl.flen) { ctx->err = "msc_stride smaller than the logical frame"; return DABB_E_ARG; }
+            CK(cudaMemcpyAsync(p.h_msc + p.msc_off[k], sl.d_logical, (size_t)S * 4 * fp, cudaMemcpyDeviceToHost, B));
+        }
+        if (io->sf) {
+            if (io->sf_stride < 5 * sl.flen) { ctx->err = "sf_stride smaller than the superframe"; return DABB_E_ARG; }
+            CK(cudaMemcpyAsync(p.h_sf + p.sf_off[k], sl.d_sf, (size_t)S * 5 * fp, cudaMemcpyDeviceToHost, B));
+        }
+    }
+    CK(cudaEventRecord(p.done, B));
+    p.io = *io; p.used = true;
+    ctx->pend_count++; ctx->submits++;
+    return DABB_OK;
+}
+
+int dabb_collect(dabb_ctx* ctx)
+{
+    if (!ctx) return DABB_E_ARG;
+    if (ctx->pend_count == 0) { ctx->err = "nothing outstanding"; return DABB_E_STATE; }
+    cudaSetDevice(ctx->device);
+    dabb_ctx::Pending& p = ctx->pend[ctx->pend_head];
+    CK(cudaEventSynchronize(p.done));
+    const int S = ctx->S;
+    const dabb_io& io = p.io;
+    if (io.results) memcpy(io.results, p.h_res, sizeof(dabb_frame_result) * S);
+    if (io.fibs) memcpy(io.fibs, p.h_fibs, (size_t)S * 12 * 32);
+    for (int k = 0; k < ctx->n_slots; k++) {
+        const int flen = p.flen[k];
+        if (!flen) continue;
+        const size_t fp = (size_t)((flen + 15) & ~15);
+        if (io.msc)       // pinned rows [S*4][fp] -> caller [S][MAX_SUBCH][4][msc_stride]
+            for (int s = 0; s < S; s++) for (int c = 0; c < 4; c++)
+                memcpy(io.msc + (((size_t)s * DABB_MAX_SUBCH + k) * 4 + c) * io.msc_stride, p.h_msc + p.msc_off[k] + ((size_t)s * 4 + c) * fp, (size_t)flen);
+        if (io.sf)
+            for (int s = 0; s < S; s++) memcpy(io.sf + ((size_t)s * DABB_MAX_SUBCH + k) * io.sf_stride, p.h_sf + p.sf_off[k] + (size_t)s * 5 * fp, (size_t)5 * flen);
+    }
+    p.used = false;
+    ctx->pend_head ^= 1; ctx->pend_count--;
     return DABB_OK;
 }
 

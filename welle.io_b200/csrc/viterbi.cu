@@ -184,17 +184,26 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
         int nx = (int)((__ldg(p.stage_off + s) & 15u) >> 2);
         uint32_t w0 = my[nx], w1 = my[nx + 1];
         nx += 2;
+        // the expansion of group g + 1 (table loads, window loads) is issued before the add-compare-select of group g: independent work
+        // the scheduler interleaves, so that the window's load latency does not sit in front of every six steps
+        auto expand = [&](int g, uint32_t (&wo)[6]) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const uint2 e = __ldg(p.steptab + 6 * g + k);           // {byte selector | advance << 16, byte mask}
+                wo[k] = vit_expand_step(w0, w1, e.x, e.y);
+                if (e.x & 0x10000u) { w0 = w1; w1 = my[nx]; nx++; }       // warp-uniform
+            }
+        };
+        uint32_t wn[6];
+        if (4 * s < groups) expand(4 * s, wn);
 #pragma unroll 1
         for (int gq = 0; gq < 4; gq++) {
             const int g = 4 * s + gq;
             if (g >= groups) break;
             uint32_t w[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const uint2 e = __ldg(p.steptab + 6 * g + k);           // {byte selector | advance << 16, byte mask}
-                w[k] = vit_expand_step(w0, w1, e.x, e.y);
-                if (e.x & 0x10000u) { w0 = w1; w1 = my[nx]; nx++; }       // warp-uniform
-            }
+            for (int k = 0; k < 6; k++) w[k] = wn[k];
+            if (gq < 3 && g + 1 < groups) expand(g + 1, wn);
             uint32_t d[12];
             vit_six_steps(Q, w, d, p.one);
             if (have) {

@@ -71,6 +71,39 @@ VIT_HD uint32_t vminu16x2(uint32_t a, uint32_t b)
 #endif
 }
 
+// per-half signed 16-bit minimum (SASS: VIMNMX.S16x2)
+VIT_HD uint32_t vmin16(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r; asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#else
+    bool ph, pl; return vibmin16(a, b, ph, pl);
+#endif
+}
+// bytes (sign(t1 bit 15), sign(t2 bit 15), sign(t1 bit 31), sign(t2 bit 31)) as 0x00 / 0xFF: PRMT in sign-replicating mode
+VIT_HD uint32_t vit_signbytes(uint32_t t1, uint32_t t2)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;        // generic prmt: selector nibble = byte index 0..7 of {t2, t1} | 8 = replicate that byte's sign bit
+    asm("prmt.b32 %0, %1, %2, 0xFBD9;" : "=r"(r) : "r"(t1), "r"(t2));
+    return r;
+#else
+    return ((t1 >> 15) & 1u ? 0xFFu : 0u) | ((t2 >> 15) & 1u ? 0xFF00u : 0u) | ((t1 >> 31) ? 0xFF0000u : 0u) | ((t2 >> 31) ? 0xFF000000u : 0u);
+#endif
+}
+// where vit_acs<B> stores the decision of NEW state n: bit position 0..63 in the step's decision pair (x = bits 0..31, y = 32..63)
+template <int B> VIT_HD uint32_t vit_dec_pos(uint32_t n)
+{
+    if constexpr (B < 5) {
+        const uint32_t h = n >> 1;                                                    // butterfly index with its bit B = lane bit 1
+        const uint32_t j = ((h >> (B + 1)) << B) | (h & ((1u << B) - 1u));           // ... removed: group 0..15
+        return (j & 7u) | ((n & 1u) << 3) | (((n >> (B + 1)) & 1u) << 4) | ((j >> 3) << 5);
+    } else {
+        const uint32_t g = n >> 2;                                                    // lanes: 4g, 4g + 2, 4g + 1, 4g + 3
+        return (g & 7u) | (((n >> 1) & 1u) << 3) | ((n & 1u) << 4) | ((g >> 3) << 5);
+    }
+}
+
 // branch metrics for the eight patterns from one step's four symbols (bytes s0..s3 of w, each 0..255)
 VIT_HD void vit_metrics(uint32_t w, uint32_t E[8])
 {
@@ -110,32 +143,17 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32
 {
     (void)one;
     uint32_t N[32];
-    // decision bits are OR-ed into four partial words per half (short dependency chains, no branches)
-    // accumulators: index [0..1] new states 0..31, [2..3] new states 32..63; the low and the high half of one packed minimum use
-    // different arrays (the two read-write operands of one asm statement must be distinct variables)
-    uint32_t accl_[4] = {0, 0, 0, 0}, acch_[4] = {0, 0, 0, 0};
-    // VIT_MIN(dst, a, b, nl, nh): dst = per-half signed minimum of (a, b); decision bit of new state nl (low half) / nh (high half)
-    // is set when b wins strictly ((a - b) > 0: ties keep the a = old[i] branch, viterbi.cpp:263-275).
-#if defined(__CUDA_ARCH__)
-    // One asm statement per packed minimum: the two predicates VIMNMX.S16x2 produces are consumed by predicated multiply-adds
-    // inside the same statement, so they never become general registers (passing them through C++ bools made the compiler
-    // materialise every predicate with SEL / LOP3 / P2R: 276 instead of ~190 instructions per trellis step).  The bit is ADDED
-    // with `@p mad.lo acc = bit * 1 + acc` (every bit is set at most once, so add == or): an IMAD on the FMA pipe, which balances
-    // the ALU pipe where the packed minimum runs.  `one` is the value 1 passed through a kernel parameter so that the assembler
-    // cannot fold the multiply away.
-#define VIT_ACCI(n) ((((n) >> 5) << 1) | (((n) >> 4) & 1))
-#define VIT_MIN(dst, a, b, nl, nh) \
-    asm("{\n.reg .pred pu, pv;\n.reg .u16 r0, r1, r2, r3;\n.reg .b32 m;\n" \
-        "min.s16x2 m, %3, %4;\nmov.b32 {r0, r1}, m;\nmov.b32 {r2, r3}, %3;\n" \
-        "setp.eq.s16 pv, r0, r2;\nsetp.eq.s16 pu, r1, r3;\n" \
-        "@!pv mad.lo.u32 %1, %5, %6, %1;\n@!pu mad.lo.u32 %2, %5, %7, %2;\nmov.b32 %0, m;\n}" \
-        : "=r"(dst), "+r"(accl_[VIT_ACCI(nl)]), "+r"(acch_[VIT_ACCI(nh)]) \
-        : "r"(a), "r"(b), "r"(one), "r"(1u << ((nl) & 31)), "r"(1u << ((nh) & 31)))
-#else
-#define VIT_ACCI(n) ((((n) >> 5) << 1) | (((n) >> 4) & 1))
-#define VIT_MIN(dst, a, b, nl, nh) do { bool ph__, pl__; dst = vibmin16(a, b, ph__, pl__); \
-        if (!pl__) accl_[VIT_ACCI(nl)] |= 1u << ((nl) & 31); if (!ph__) acch_[VIT_ACCI(nh)] |= 1u << ((nh) & 31); } while (0)
-#endif
+    // Decisions without predicates.  For a packed pair (a, b) of candidate metrics (every half in [0, 0x7FFF]) t = a + 0x7FFF7FFF - b has
+    // bit 15 / 31 set exactly where b wins strictly ((a - b) > 0: ties keep the a = old[i] branch, viterbi.cpp:263-275) and no carry
+    // crosses the halves.  One PRMT in sign-replicating mode turns the two sign bits of two such words into four 0x00 / 0xFF bytes, one
+    // LOP3 masks them to bit g of every byte and ORs them into the step's decision word: 2 instructions per packed minimum like the
+    // predicated form (VIMNMX with two predicate outputs + two predicated adds), but nothing competes for the seven predicate registers
+    // (that form made the scheduler park predicates in general registers: ~45 extra instructions per step).
+    // Decision layout of a step: group g (0..15) = the two packed minima that share their input registers, byte lane l (0..3) as listed
+    // below; decision bit at word g >> 3, bit 8 l + (g & 7) (vit_dec_pos<B> is the inverse map for the traceback).
+    uint32_t W[2] = {0u, 0u};
+#define VIT_T(a, b) ((a) + 0x7FFF7FFFu - (b))
+#define VIT_PUT(g, t1, t2) do { W[(g) >> 3] |= vit_signbytes(t1, t2) & (0x01010101u << ((g) & 7)); } while (0)
     if constexpr (B < 5) {
         constexpr int delta = vit_pat(1 << B);   // pattern change when butterfly bit B flips
         uint32_t MC[8];
@@ -146,26 +164,32 @@ template <int B> VIT_HD void vit_acs(uint32_t (&Q)[32], const uint32_t w, uint32
             const int ra = vit_remove_bit(ilo, B), rb = vit_remove_bit(ilo + 32, B);
             const int p = vit_pat(ilo);
             const uint32_t m0 = Q[ra] + MC[p], m1 = Q[rb] + MC[p ^ 7], m2 = Q[ra] + MC[p ^ 7], m3 = Q[rb] + MC[p];
-            const int ne = 2 * ilo, nehi = ne + (2 << B);     // new states in the low / high half of the even result
-            VIT_MIN(N[vit_remove_bit(ne, B + 1)], m0, m1, ne, nehi);
-            VIT_MIN(N[vit_remove_bit(ne + 1, B + 1)], m2, m3, ne + 1, nehi + 1);
+            const int ne = 2 * ilo;                           // new states: (ne, ne + (2 << B)) from (m0, m1), (ne + 1, ne + 1 + (2 << B)) from (m2, m3)
+            N[vit_remove_bit(ne, B + 1)] = vmin16(m0, m1);
+            N[vit_remove_bit(ne + 1, B + 1)] = vmin16(m2, m3);
+            VIT_PUT(j, VIT_T(m0, m1), VIT_T(m2, m3));         // lanes: ne, ne + 1, ne + (2 << B), ne + 1 + (2 << B)
         }
     } else {
         // L_5: register i = (old[i], old[i+32]); result register i = (new[2i], new[2i+1]) = layout L_0
         uint32_t XC[8];
         vit_mc<7>(w, XC);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const int p = vit_pat(i);
-            const uint32_t x = dup_lo(Q[i]) + XC[p];        // (old[i] + m,        old[i] + 1020 - m)
-            const uint32_t y = dup_hi(Q[i]) + XC[p ^ 7];    // (old[i+32] + 1020-m, old[i+32] + m)
-            VIT_MIN(N[i], x, y, 2 * i, 2 * i + 1);
+        for (int g = 0; g < 16; g++) {
+            uint32_t t[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = 2 * g + h, p = vit_pat(i);
+                const uint32_t x = dup_lo(Q[i]) + XC[p];        // (old[i] + m,        old[i] + 1020 - m)
+                const uint32_t y = dup_hi(Q[i]) + XC[p ^ 7];    // (old[i+32] + 1020-m, old[i+32] + m)
+                N[i] = vmin16(x, y);                            // (new[2i], new[2i+1])
+                t[h] = VIT_T(x, y);
+            }
+            VIT_PUT(g, t[0], t[1]);                             // lanes: 4g, 4g + 2, 4g + 1, 4g + 3
         }
     }
-#undef VIT_MIN
-#undef VIT_ACCI
-    dlo = (accl_[0] | accl_[1]) | (acch_[0] | acch_[1]);
-    dhi = (accl_[2] | accl_[3]) | (acch_[2] | acch_[3]);
+#undef VIT_PUT
+#undef VIT_T
+    dlo = W[0]; dhi = W[1];
 #pragma unroll
     for (int r = 0; r < 32; r++) Q[r] = N[r];
 }
@@ -251,21 +275,26 @@ inline void build_vit_tables(const int16_t* map, int nsteps, StepVec& steps, Off
 // steps the state IS the six decoded bits, earliest first from bit 5: the output is assembled six bits at a time.
 // One call handles 24 steps: d[k] = decision words of the times T0 + k (T0 + 23 first); acc[3] collects a 96-bit big-endian string
 // of the times tb .. tb + 95 (acc[2] bit 31 = time tb); q = which quarter (T0 = tb + 24 q).
+template <int PH> VIT_HD void vit_tb_step(uint32_t& state, const vit_u2& d)
+{
+    // decision of the state reached by step PH (mod 6) of a six-step group: forward step s used vit_acs<s % 6>
+    const uint32_t pos = vit_dec_pos<PH>(state);
+    const uint32_t word = (pos & 32u) ? d.y : d.x;
+#if defined(__CUDA_ARCH__)
+    const uint32_t rot = __funnelshift_r(word, word, pos - 5u);       // bit (pos & 31) of the word rotated to bit 5
+#else
+    const uint32_t sh = (pos - 5u) & 31u;
+    const uint32_t rot = sh ? ((word >> sh) | (word << (32 - sh))) : word;
+#endif
+    state = (rot & 32u) | (state >> 1);
+}
 template <int Q24> VIT_HD void vit_traceback24(uint32_t& state, const vit_u2 (&d)[24], uint32_t (&acc)[3])
 {
+    // d[k] belongs to trellis step tb + 24 Q24 + k + 6, a multiple of 6 plus k: its layout phase is k mod 6
 #pragma unroll
     for (int h = 3; h >= 0; h--) {
-#pragma unroll
-        for (int k = 5; k >= 0; k--) {
-            const uint32_t word = (state & 32u) ? d[6 * h + k].y : d[6 * h + k].x;
-#if defined(__CUDA_ARCH__)
-            const uint32_t rot = __funnelshift_r(word, word, state - 5u);       // bit (state & 31) of the word rotated to bit 5
-#else
-            const uint32_t sh = (state - 5u) & 31u;
-            const uint32_t rot = sh ? ((word >> sh) | (word << (32 - sh))) : word;
-#endif
-            state = (rot & 32u) | (state >> 1);
-        }
+        vit_tb_step<5>(state, d[6 * h + 5]); vit_tb_step<4>(state, d[6 * h + 4]); vit_tb_step<3>(state, d[6 * h + 3]);
+        vit_tb_step<2>(state, d[6 * h + 2]); vit_tb_step<1>(state, d[6 * h + 1]); vit_tb_step<0>(state, d[6 * h + 0]);
         // state = the bits of the times T .. T+5 (T = tb + 24 Q24 + 6 h), time T at bit 5
         const int lo = 96 - (24 * Q24 + 6 * h + 6);        // offset of time T+5 in the 96-bit string (0 = time tb + 95)
         acc[lo >> 5] |= state << (lo & 31);

@@ -69,7 +69,7 @@ class IO(C.Structure):
 
 
 EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_get_info", "dabb_select_subchannel",
-           "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_join_lanes", "dabb_cuda_stream", "dabb_kernel_launches",
+           "dabb_remove_subchannel", "dabb_process", "dabb_process_async", "dabb_sync", "dabb_join_lanes", "dabb_submit", "dabb_collect", "dabb_cuda_stream", "dabb_kernel_launches",
            "dabb_read_tap", "dabb_profile", "dabb_profile_read", "dabb_ofdm_demod", "dabb_find_index", "dabb_find_index_ex", "dabb_coarse_estimate", "dabb_viterbi", "dabb_fic_decode", "dabb_msc_decode",
            "dabb_rs_superframes", "dabb_dev_alloc", "dabb_dev_free", "dabb_memcpy_h2d", "dabb_memcpy_d2h"]
 
@@ -239,6 +239,33 @@ class Context:
         if sf_stride:
             out["sf"] = np.zeros((S, MAX_SUBCH, sf_stride), np.uint8); io.sf = out["sf"].ctypes.data; io.sf_stride = sf_stride
         self._ck(self.lib.dabb_process(self.h, C.byref(io)))
+        return out
+
+    def submit(self, iq, stride, buf_start, buf_len, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0):
+        """pipelined host-buffer step (dabb_submit): returns immediately; collect() hands back the output dict of the oldest step"""
+        S = self.n_streams
+        bs = np.ascontiguousarray(buf_start, np.int64)
+        io = IO()
+        io.iq = _addr(iq)
+        io.iq_is_host, io.stride_samples, io.buf_len, io.iq_format = 1, stride, buf_len, iq_format
+        io.buf_start = bs.ctypes.data
+        out = {}
+        if "results" in want:
+            out["results"] = np.zeros(S, RESULT_DTYPE); io.results = out["results"].ctypes.data
+        if "fibs" in want:
+            out["fibs"] = np.zeros((S, 12, 32), np.uint8); io.fibs = out["fibs"].ctypes.data
+        if msc_stride:
+            out["msc"] = np.zeros((S, MAX_SUBCH, 4, msc_stride), np.uint8); io.msc = out["msc"].ctypes.data; io.msc_stride = msc_stride
+        if sf_stride:
+            out["sf"] = np.zeros((S, MAX_SUBCH, sf_stride), np.uint8); io.sf = out["sf"].ctypes.data; io.sf_stride = sf_stride
+        self._ck(self.lib.dabb_submit(self.h, C.byref(io)))
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append((out, bs, iq))          # keep the buffers alive until collected
+        return None
+
+    def collect(self):
+        self._ck(self.lib.dabb_collect(self.h))
+        out, _, _ = self._pending.pop(0)
         return out
 
     def process_async(self, iq_ptr, stride, buf_start, buf_len):

@@ -48,15 +48,18 @@ int main(int argc, char** argv)
     ri.fibs = fopen((pre + ".fibs").c_str(), "wb"); ph.rs = fopen((pre + ".rs").c_str(), "w"); ri.dump = pre + ".msc"; ri.ph = &ph;
     if (argc > 3) ri.select_at = atoi(argv[3]);
     RadioReceiverOptions rro; rro.disableCoarseCorrector = argc > 4 ? atoi(argv[4]) != 0 : true;    /* default like the parity harness (welle-cli -u) */
+    double secs = 0;
     {
         RadioReceiver rx(ri, in, rro);
         ri.rx = &rx;
+        const auto t0 = std::chrono::steady_clock::now();
         rx.restart(false);
-        while (!ri.failed.load()) std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        while (!ri.failed.load()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();      /* restart .. input exhausted */
         rx.stop();
     }
     fclose(ri.fibs); fclose(ph.rs);
-    printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d cirs=%d consts=%d nulls=%d tapsizes=%d\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs,
-           ri.cirs, ri.consts, ri.nulls, (int)ri.tapsz_ok);
+    printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d cirs=%d consts=%d nulls=%d tapsizes=%d seconds=%.4f\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs,
+           ri.cirs, ri.consts, ri.nulls, (int)ri.tapsz_ok, secs);
     return 0;
 }
