@@ -218,6 +218,24 @@ def reference_stage_level_all_cores(n_procs, seconds=8.0):
             "note": "unmodified reference stage functions (OFDM demod of 76 symbols, FIC, 4 x MSC 96 kbit/s EEP-3A, RS) in a loop, one process per core over disjoint frames"}
 
 
+def effective_cores():
+    """cores this process may really use: affinity mask and the cgroup CPU quota (a container can see 128 cores and own a dozen)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    return {"visible": os.cpu_count() or 1, "affinity": n, "cgroup_quota": quota, "effective": min(n, quota) if quota else n}
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -226,7 +244,7 @@ def reference_arm(a):
     if not Ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libwelle_ref.so missing (built only where /root/reference exists)"}))
         return
-    cores = os.cpu_count() or 1
+    cores = max(1, int(effective_cores()["effective"]))
     n_procs = max(1, min(cores // 3, 48))       # one reference receiver runs ~3 busy threads (OFDM, decoder, DabAudio)
     vals = []
     for it in range(a.warmup + a.steps):
@@ -243,7 +261,7 @@ def reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int", "data": "synthetic",
             "config": config_dict(a, None),
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample,
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample, "cores_detail": effective_cores(),
                              "stage_level_all_cores": stage_all,
                              "note": "value = the stock code path (RadioReceiver with its own threads, flow-controlled memory input); stage_level_all_cores = the reference's stage functions alone on every core, the most the reference's kernels can give on this host"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -299,11 +317,11 @@ def main():
         try:
             from oracle.bind import Ref
             if Ref.available():
-                cores = os.cpu_count() or 1
+                cores = max(1, int(effective_cores()["effective"]))
                 n_procs = max(1, min(cores // 3, 48))
                 log(f"cpu baseline: {n_procs} reference receivers x {a.ref_frames} frames")
                 v, frames, busy, wall, ok, tot = run_reference_cpu(n_procs, a.ref_frames)
-                cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
+                cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "cores_detail": effective_cores(),
                        "sample": f"{n_procs} concurrent unmodified reference RadioReceiver instances x {a.ref_frames} synthetic frames (same chain: FIC + one 96 kbit/s DAB+ sub-channel), KISS-FFT build, {busy:.1f} s",
                        "fib_crc_ok": ok, "fibs": tot}
                 try:
@@ -593,7 +611,7 @@ def main():
             t0 = time.perf_counter(); h2d = 0; o = None
             for k in range(a.steps):
                 ptr, bs, bl = args(ce); ce += 1; h2d += Se * bl * bps
-                ctx_e.submit(ptr, BUF_LEN, bs, bl, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=fmt)
+                ctx_e.submit(ptr, BUF_LEN, bs, bl, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=fmt, out=o if k >= 2 else None)   # result arrays recycled
                 if k >= 1:
                     o = ctx_e.collect()
             o = ctx_e.collect()

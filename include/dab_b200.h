@@ -79,7 +79,8 @@ typedef struct {
     int32_t disable_coarse;
     int32_t fft_placement;      /* DABB_PLACEMENT_* */
     int32_t freqsync_method;    /* DABB_FREQSYNC_* */
-    int32_t reserved[5];
+    int32_t decode_tii;         /* RadioReceiverOptions::decodeTII: with keep_taps, also produce tap 4 (the two spectra TIIDecoder starts from) */
+    int32_t reserved[4];
 } dabb_options;
 
 /* replaces: RadioReceiver::RadioReceiver / ~RadioReceiver (backend/radio-receiver.h:52-116) */
@@ -193,7 +194,10 @@ int dabb_profile_read(dabb_ctx* ctx, char* json_out, size_t cap);
  *   0 = softbits int8 [n_streams][75*3072]
  *   1 = CIR float [n_streams][2048]                     RadioControllerInterface::onNewImpulseResponse (phasereference.cpp:93)
  *   2 = constellation cf32 [n_streams][75][16]          onConstellationPoints: r1 of every 96th carrier (ofdm-decoder.cpp:216-218)
- *   3 = null symbol cf32 [n_streams][2656], NCO applied  onNewNullSymbol (ofdm-processor.cpp:462-469) */
+ *   3 = null symbol cf32 [n_streams][2656], NCO applied  onNewNullSymbol (ofdm-processor.cpp:462-469)
+ *   4 = TII spectra cf32 [n_streams][2][2048] (only while dabb_options.decode_tii is set): fft::Forward of the frame's phase
+ *       reference symbol and of the last T_u samples of the null symbol that follows it, what TIIDecoder::run computes first
+ *       (tii-decoder.cpp:197-214); the pattern analysis itself is host work (welle.io_b200/host/tii.h) */
 int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -2,9 +2,10 @@
 # Builds experimental variants of libdab_b200.so (compile-time switches) next to the repo root as gpurun_exp_<name>.so (git-ignored; they
 # travel to the GPU box with the snapshot).  Run on the CPU box, then on the GPU:   bash scripts/gpu_variants.sh
 #   pairs     -DDABB_DEMAP_PAIRS           two carriers per packed reciprocal chain in the demap   (round 1: -1 % on ofdm_demod_kernel)
-#   cta6      -DDEMOD_CTAS_PER_SM=6        80 registers (spills) - only useful together with a smaller shared-memory footprint
+#   cta6      -DDEMOD_CTAS_PER_SM=6        6 CTAs/SM: 80 registers (spills), 37 KB shared memory (twiddles through L1, softbit staging inside
+#                                          the exchange buffer at the price of two more barriers per symbol)
+#   cta6pairs both
 #   vit64     -DVIT_THREADS_N=64           Viterbi CTAs of 64 codewords                              (round 1: no change)
-#   nof32x2   -DDABB_NO_F32X2              scalar fp32 arithmetic (the pre-packed baseline)
 set -eu
 cd "$(dirname "$0")/../welle.io_b200/csrc"
 make -s
@@ -18,5 +19,5 @@ build() {   # name, source, macro
 }
 build pairs ofdm -DDABB_DEMAP_PAIRS
 build cta6 ofdm -DDEMOD_CTAS_PER_SM=6
+build cta6pairs ofdm "-DDEMOD_CTAS_PER_SM=6 -DDABB_DEMAP_PAIRS"
 build vit64 viterbi -DVIT_THREADS_N=64
-build nof32x2 ofdm -DDABB_NO_F32X2

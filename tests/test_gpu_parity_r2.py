@@ -228,32 +228,44 @@ def test_s3_snr_sweep_full_chain(oracle):
 def test_reacquisition_after_gap(oracle):
     """(f) signal, 1.3 frames of near-silence, signal again at an unrelated timing.  The reference's level tracker sLevel runs over every
     sample (ofdm-processor.cpp:166,215); on the GPU it is exact while a stream searches and follows a sub-sampled estimate while it
-    tracks, so the null search after the loss may fire a few samples earlier or later than the reference's: the decoded
-    frames must be the same ones (FIBs identical), the start indices may differ by that shift."""
+    tracks, so a null search that starts from a tracked level may fire a sample or two earlier or later than the
+    reference's: every frame must sit at the same absolute position (window start + start index) and carry the same FIBs - including the
+    three frames both receivers "decode" out of the silence (findIndex returns 0 on a flat correlation) and the second loss that follows."""
     pkg = load_pkg()
     s = dabtx.DabTx(seed=0x6B).frames(22)
     a, b = s[:9 * TF + 40000], s[11 * TF - 777:]
     iq = np.concatenate([a, np.full(int(1.3 * TF), 1e-5 + 0j, np.complex64), b]).astype(np.complex64)
     ctx = pkg.Context(n_streams=1)
     d = ctx.dev(iq.reshape(1, -1))
-    fibs, status, idx = [], [], []
+    frames, status = [], []
+    pos = 0
     for _ in range(60):
         out = ctx.process(d, len(iq), np.zeros(1, np.int64), len(iq))
         r = out["results"]
         status.append(int(r["status"][0]))
-        if r["status"][0] == pkg.FRAME_DECODED and r["next_pos"][0] <= len(iq):
-            fibs.append((out["fibs"][0].copy(), int(r["fib_crc_mask"][0]))); idx.append(int(r["start_index"][0]))
+        if r["status"][0] == pkg.FRAME_DECODED:
+            # window start of this frame = next_pos - (T_u + idx + 75 T_s + T_null)
+            win = int(r["next_pos"][0]) - (TU + int(r["start_index"][0]) + 75 * TS + TNULL)
+            frames.append((win + int(r["start_index"][0]), out["fibs"][0].copy(), int(r["fib_crc_mask"][0]), int(r["start_index"][0])))
         if r["status"][0] == pkg.FRAME_NEED_SAMPLES:
             break
     ctx.close()
     o = oracle.rx_run(iq, disable_coarse=True)
-    ofr = [(o["fibs"][12 * f:12 * f + 12, 1:], int(sum(int(b) << k for k, b in enumerate(o["fibs"][12 * f:12 * f + 12, 0])))) for f in range(o["frames"])]
-    print(f"re-acquisition: GPU decoded {len(fibs)} frames, oracle {len(ofr)}; status sequence {status}")
-    good_g = [f for f, c in fibs if c == 0xFFF]; good_o = [f for f, c in ofr if c == 0xFFF]
-    assert pkg.FRAME_NO_SYNC in status or pkg.FRAME_ACQUIRING in status[3:]
-    assert len(good_o) >= 14 and len(good_g) == len(good_o)
-    for x, y in zip(good_g, good_o):
-        assert np.array_equal(x, y)
+    ofr = [(o["info"][f]["pos"] + o["info"][f]["start_index"], o["fibs"][12 * f:12 * f + 12, 1:], int(sum(int(b) << k for k, b in enumerate(o["fibs"][12 * f:12 * f + 12, 0]))), o["info"][f]["start_index"])
+           for f in range(o["frames"])]
+    print(f"re-acquisition: GPU decoded {len(frames)} frames, oracle {len(ofr)}; status sequence {status}")
+    print("  start indices GPU   ", [f[3] for f in frames])
+    print("  start indices oracle", [f[3] for f in ofr])
+    assert status.count(pkg.FRAME_NO_SYNC) == 2 and pkg.FRAME_ACQUIRING in status
+    # the GPU asks for a conservative T_u - 1 samples more than the frame finally needs: at most the very last frame of the recording is left out
+    assert len(ofr) - 1 <= len(frames) <= len(ofr) and len(frames) >= 18
+    good = 0
+    for g, c in zip(frames, ofr):
+        assert g[0] == c[0], (g[0], c[0])                       # same absolute position of the phase reference symbol
+        assert g[2] == c[2] and np.array_equal(g[1], c[1])     # same FIB bytes and CRC flags, locked or not
+        good += g[2] == 0xFFF
+    assert good >= 15
+    assert max(abs(g[3] - c[3]) for g, c in zip(frames, ofr)) <= 4      # the null search may fire a few samples apart
 
 
 def test_fast_oscillator_within_tolerance(oracle):

@@ -53,7 +53,7 @@ struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
-    int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
+    int decode_tii = 0; float2* d_tii = nullptr; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0; int osc_mismatches = -1; int osc_patched = 0; std::vector<float2> h_osc;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
@@ -82,7 +82,7 @@ struct dabb_ctx {
     int pend_head = 0, pend_count = 0; int64_t submits = 0;
     // pinned host staging for results
     dabb_frame_result* h_results = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr;
-    int groups = 1; int fc_pitch = 1; int tail_frames = 0; int nco_fast = 0;
+    int groups = 1; int fc_pitch = 1; int tail_frames = 0; int tail_groups = 15; int nco_fast = 0;
     const int32_t** d_info_tab = nullptr;
     // optional per-kernel timing: one event after every launch, durations = differences of consecutive events
     bool prof = false; std::vector<cudaEvent_t> prof_ev; std::vector<const char*> prof_name; size_t prof_used = 0;
@@ -468,7 +468,10 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     const int S = ctx->S;
     int rc = 0;
     ctx->tail_frames = (cfg->ofdm_tail_split == 0 && ctx->groups == 1) ? ofdm_tail_frames(S) : 0;
-    ctx->fc_pitch = ctx->tail_frames ? 15 : ctx->groups;
+    if (ctx->tail_frames && getenv("DABB_TAIL_FRAMES")) { const int v = atoi(getenv("DABB_TAIL_FRAMES")); if (v >= 0 && v <= S) ctx->tail_frames = v; }   // experiments
+    ctx->tail_groups = 15;
+    if (getenv("DABB_TAIL_GROUPS")) { const int v = atoi(getenv("DABB_TAIL_GROUPS")); if (v > 0 && 75 % v == 0) ctx->tail_groups = v; }
+    ctx->fc_pitch = ctx->tail_frames ? ctx->tail_groups : ctx->groups;
     // tables
     float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
     if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
@@ -761,7 +764,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.level = d_lvl; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
-    op.n_full = S - ctx->tail_frames; op.tail_groups = ctx->tail_frames ? 15 : 1; op.fc_pitch = ctx->fc_pitch; op.nco_fast = ctx->nco_fast;
+    op.n_full = S - ctx->tail_frames; op.tail_groups = ctx->tail_frames ? ctx->tail_groups : 1; op.fc_pitch = ctx->fc_pitch; op.nco_fast = ctx->nco_fast;
     // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
     op.smem_floor = serial ? 0 : ctx->ofdm_smem_floor;
     launch_ofdm_demod(ctx->dev, op, ctx->fft_mode, A);
@@ -771,6 +774,11 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     if (ctx->d_null) {
         null_tap_kernel<<<S, 256, 0, A>>>(scr, iq, stride, ctx->d_buf_start, io->buf_len, ctx->dev.osc, ctx->d_null);
         if ((rc = check_launch(ctx, "null_tap_kernel"))) return rc;
+        if (ctx->decode_tii) {
+            if (!ctx->d_tii && (rc = dalloc(ctx, &ctx->d_tii, (size_t)S * 2 * TU))) return rc;
+            launch_tii_spectra(ctx->dev, iq, stride, d_prs, d_nco_frame, d_active, ctx->d_null, ctx->d_tii, S, A);
+            if ((rc = check_launch(ctx, "tii_spectra_kernel"))) return rc;
+        }
     }
     if (!serial) { CK(cudaEventRecord(ctx->evA[par], A)); CK(cudaStreamWaitEvent(B, ctx->evA[par], 0)); }
     // ---------------- lane B: FIC chain forked onto its own stream, MSC chain per slot (longest first), then the result record.
@@ -1009,6 +1017,7 @@ int dabb_read_tap(dabb_ctx* ctx, int32_t what, void* host_out, size_t bytes)
         CK(cudaMemcpy2D(host_out, 8, ctx->d_r1, 96 * 8, 8, n, cudaMemcpyDeviceToHost));
         return 0;
     }
+    if (what == 4 && ctx->d_tii && ctx->decode_tii) { const size_t n = (size_t)ctx->S * 2 * TU * 8; CK(cudaMemcpy(host_out, ctx->d_tii, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     if (what == 3 && ctx->d_null) { const size_t n = (size_t)ctx->S * TNULL * 8; CK(cudaMemcpy(host_out, ctx->d_null, bytes < n ? bytes : n, cudaMemcpyDeviceToHost)); return 0; }
     ctx->err = "tap not available (keep_taps = 0?)";
     return DABB_E_STATE;
@@ -1077,7 +1086,7 @@ int dabb_get_info(dabb_ctx* ctx, int32_t what, int64_t* out)
 int dabb_set_options(dabb_ctx* ctx, const dabb_options* opt)
 {
     if (!ctx || !opt || opt->fft_placement < 0 || opt->fft_placement > 2 || opt->freqsync_method < 0 || opt->freqsync_method > 2) return DABB_E_ARG;
-    ctx->disable_coarse = opt->disable_coarse != 0; ctx->placement = opt->fft_placement; ctx->freqsync = opt->freqsync_method;
+    ctx->disable_coarse = opt->disable_coarse != 0; ctx->placement = opt->fft_placement; ctx->freqsync = opt->freqsync_method; ctx->decode_tii = opt->decode_tii != 0;
     return DABB_OK;
 }
 

@@ -61,6 +61,8 @@ int ofdm_init_constants();     // per-device constants of ofdm.cu (call once aft
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
 int ofdm_tail_frames(int n_frames);
 void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
+void launch_tii_spectra(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, const int32_t* nco_frame, const int32_t* active,
+                        const float2* nulls, float2* out, int n, cudaStream_t st);
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st);
 
 // ---- host-side table builders (tables.cpp) ----

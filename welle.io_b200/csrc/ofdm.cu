@@ -189,11 +189,16 @@ constexpr float LEVEL_DECAY_SYM = 0.97480279f;
 constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
 constexpr int SB_DUMMY = 1536;   // softbit staging as (re, im) byte pairs indexed by logical carrier: [0,1536) real entries, then one private
                                  // dummy entry per thread for its unused bin
+// DEMOD_CTAS_PER_SM >= 6 (experiment): 37 KB of shared memory per CTA - the small twiddles come through L1 and the softbit staging
+// area lives in the exchange buffer (two more barriers per symbol) - and 80 registers
+#define DEMOD_SLIM (DEMOD_CTAS_PER_SM >= 6)
 struct __align__(16) DemodSmem {
     float2 inbuf[IN_CAP];            // 20 KB: one symbol, guard interval first, filled by one cp.async.bulk (TMA)
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
+#if !DEMOD_SLIM
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
     uint16_t sbuf[1536 + 128];        // (re | im << 8) per logical carrier: one 16-bit scatter store per carrier
+#endif
     float2 rtab[2][16];              // DABB_NCO_FAST: e^{-j theta((128 h + 256 c) Hz)} for the PRS / the data symbols
     float red[16];
     uint64_t full;
@@ -209,6 +214,11 @@ template <bool EXACT, bool FASTNCO>
 __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0, float2 v[16], DemodSmem& sm, int t, const XIdx& xi,
                                                   const float2* __restrict__ tw_c5, const DevTables& tb, const Nco& nco, bool afc, float2& fc, const float2* rtab, float& l1_first)
 {
+#if DEMOD_SLIM
+    const float2* twp = tb.tw_fwd;
+#else
+    const float2* twp = sm.tw;
+#endif
     // l1_first: |re| + |im| of the thread's first (mixed) sample, the sub-sampled input of the running signal level (see advance_kernel)
     if (FASTNCO && nco.mix) {
         // sample n = t + 128 h + 256 c gets osc(lp - (128 h + 256 c) Hz) = osc(lp) * rtab[8 h + c]; the guard-interval correlation is
@@ -235,7 +245,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
             for (int c = 0; c < 8; c++) x[c] = cmul_fast(x[c], cmul_fast(o0, rtab[8 * h + c]));
             if (h == 0) l1_first = fabsf(x[0].x) + fabsf(x[0].y);
             float2 y[8];
-            passA_block<EXACT, false>(x, y, sm.tw);
+            passA_block<EXACT, false>(x, y, twp);
 #pragma unroll
             for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
         }
@@ -278,7 +288,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
         }
         if (h == 0) l1_first = fabsf(x[0].x) + fabsf(x[0].y);
         float2 y[8];
-        passA_block<EXACT, false>(x, y, sm.tw);
+        passA_block<EXACT, false>(x, y, twp);
 #pragma unroll
         for (int e = 0; e < 8; e++) sm.xbuf[xi.a[h] ^ e] = y[e];
     }
@@ -286,11 +296,16 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
 template <bool EXACT>
 __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int t, const XIdx& xi, const float2* __restrict__ tw_c5)
 {
+#if DEMOD_SLIM
+    const float2* twp = tw_c5 - TwLayout::C5;
+#else
+    const float2* twp = sm.tw;
+#endif
 #pragma unroll
     for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[xi.b[a] + 32 * b];
-    passB<EXACT, false>(v, xi.kk, sm.tw);
+    passB<EXACT, false>(v, xi.kk, twp);
 #pragma unroll
     for (int b = 0; b < 4; b++)
 #pragma unroll
@@ -299,6 +314,9 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
 #pragma unroll
     for (int c = 0; c < 16; c++) v[c] = sm.xbuf[(t ^ xc_of(c)) + 128 * c];
     passC_ldg<EXACT, false>(v, t, tw_c5);
+#if DEMOD_SLIM
+    __syncthreads();        // the exchange buffer is about to be reused as the softbit staging area
+#endif
 }
 
 template <bool EXACT, bool TAP, bool FASTNCO>
@@ -333,7 +351,12 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     __syncthreads();
     if (t == 0) issue(l_first - 1);
 
+#if DEMOD_SLIM
+    uint16_t* const sbuf = reinterpret_cast<uint16_t*>(sm.xbuf);
+#else
     if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
+    uint16_t* const sbuf = sm.sbuf;
+#endif
     const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
     // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
     const Nco ncoP = make_nco(p.nco ? p.nco[4 * f] : 0, p.nco ? p.nco[4 * f + 1] : 0);
@@ -381,8 +404,8 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 const float2 X0 = v[slot_c(s)], X1 = v[slot_c(s + 1)];
                 int8_t sre0, sim0, sre1, sim1; float2 r10, r11;
                 demap_two(X0, prev[s], X1, prev[s + 1], sre0, sim0, r10, sre1, sim1, r11);
-                sm.sbuf[sidx[s]] = (uint16_t)((uint8_t)sre0 | ((uint16_t)(uint8_t)sim0 << 8));
-                sm.sbuf[sidx[s + 1]] = (uint16_t)((uint8_t)sre1 | ((uint16_t)(uint8_t)sim1 << 8));
+                sbuf[sidx[s]] = (uint16_t)((uint8_t)sre0 | ((uint16_t)(uint8_t)sim0 << 8));
+                sbuf[sidx[s + 1]] = (uint16_t)((uint8_t)sre1 | ((uint16_t)(uint8_t)sim1 << 8));
                 if (TAP) {
                     if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r10;
                     if (sidx[s + 1] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s + 1]] = r11;
@@ -398,14 +421,14 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 const float2 X = v[slot_c(s)];
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
-                sm.sbuf[sidx[s]] = (uint16_t)((uint8_t)sre | ((uint16_t)(uint8_t)sim << 8));
+                sbuf[sidx[s]] = (uint16_t)((uint8_t)sre | ((uint16_t)(uint8_t)sim << 8));
                 if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
                 prev[s] = X;
             }
             __syncthreads();                   // (3)
             // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits) and store 16 B per thread and half
             if (t < 96) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(sm.sbuf) + 2 * t;     // 16 pairs
+                const uint4* s4 = reinterpret_cast<const uint4*>(sbuf) + 2 * t;     // 16 pairs
                 const uint4 a = s4[0], b = s4[1];
                 uint4 re, im;
                 re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
@@ -416,6 +439,9 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 dst[t] = re;
                 dst[96 + t] = im;
             }
+#if DEMOD_SLIM
+            __syncthreads();        // staging area read: the next symbol's first pass may overwrite the exchange buffer
+#endif
         } else {
             // reference symbol only (the PRS when l == 0): keep its spectrum, estimate SNR from the PRS
 #pragma unroll
@@ -562,6 +588,33 @@ __device__ __forceinline__ void coarse_estimate(const DevTables& tb, SyncSmem& s
         for (int i = 0; i < 72; i++) if (sm.cand[i] < mmin) { mmin = sm.cand[i]; index = TU - 36 + i; }
         *out = index - TU;
     }
+}
+
+// TII diagnostics (TIIDecoder::run, tii-decoder.cpp:197-214): the two transforms the decoder starts from - the phase reference symbol
+// (the aligned T_u samples, oscillator applied) and the last T_u samples of the null symbol that follows the frame (already mixed by
+// null_tap_kernel).  One CTA per (stream, which); spectra in natural bin order, bit-identical to the reference's fft::Forward.
+__global__ void __launch_bounds__(OFDM_THREADS, 5)
+tii_spectra_kernel(DevTables tb, const float2* iq, int64_t stride, const int64_t* prs_start, const int32_t* nco_frame, const int32_t* active,
+                   const float2* nulls, float2* out)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    OfdmSmem& sm = *reinterpret_cast<OfdmSmem*>(smraw);
+    const int t = threadIdx.x, f = blockIdx.x >> 1, which = blockIdx.x & 1;
+    float2* dst = out + ((int64_t)f * 2 + which) * TU;
+    if (active && !active[f]) { for (int c = 0; c < 16; c++) dst[t + 128 * c] = make_float2(0.f, 0.f); return; }
+    if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
+    __syncthreads();
+    const XIdx xi = make_xidx(t);
+    float2 v[16];
+    if (which == 0) {
+        const Nco nco = make_nco(nco_frame[4 * f], nco_frame[4 * f + 1]);
+        fft2048_from_global<true, false>(iq + (int64_t)f * stride + prs_start[f], 0, v, sm, t, xi, tb, nco, tb.tw_fwd + TwLayout::C5);
+    } else {
+        const Nco nco = make_nco(0, 0);
+        fft2048_from_global<true, false>(nulls + (int64_t)f * TNULL, TNULL - TU, v, sm, t, xi, tb, nco, tb.tw_fwd + TwLayout::C5);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++) dst[t + 128 * c] = v[c];
 }
 
 // stage-level processPRS: one CTA per aligned PRS
@@ -832,6 +885,12 @@ int ofdm_tail_frames(int n_frames)
     }
     if (n_frames < 2 * resident) return 0;
     return resident / 2;
+}
+
+void launch_tii_spectra(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, const int32_t* nco_frame, const int32_t* active,
+                        const float2* nulls, float2* out, int n, cudaStream_t st)
+{
+    tii_spectra_kernel<<<2 * n, OFDM_THREADS, sizeof(OfdmSmem), st>>>(tb, iq, stride, prs_start, nco_frame, active, nulls, out);
 }
 
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st)

@@ -32,7 +32,7 @@ class Config(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("disable_coarse", C.c_int32), ("fft_placement", C.c_int32), ("freqsync_method", C.c_int32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("disable_coarse", C.c_int32), ("fft_placement", C.c_int32), ("freqsync_method", C.c_int32), ("decode_tii", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 PLACEMENT_THRESHOLD_BEFORE_PEAK, PLACEMENT_STRONGEST_PEAK, PLACEMENT_EARLIEST_PEAK_WITH_BINNING = 0, 1, 2
@@ -241,14 +241,26 @@ class Context:
         self._ck(self.lib.dabb_process(self.h, C.byref(io)))
         return out
 
-    def submit(self, iq, stride, buf_start, buf_len, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0):
-        """pipelined host-buffer step (dabb_submit): returns immediately; collect() hands back the output dict of the oldest step"""
+    def submit(self, iq, stride, buf_start, buf_len, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0, out=None):
+        """pipelined host-buffer step (dabb_submit): returns immediately; collect() hands back the output dict of the oldest step.
+        `out`: a dict returned by an earlier collect() to be reused for this step's results (saves allocating the arrays again)"""
         S = self.n_streams
         bs = np.ascontiguousarray(buf_start, np.int64)
         io = IO()
         io.iq = _addr(iq)
         io.iq_is_host, io.stride_samples, io.buf_len, io.iq_format = 1, stride, buf_len, iq_format
         io.buf_start = bs.ctypes.data
+        if out is not None:
+            io.results = out["results"].ctypes.data if "results" in out else None
+            io.fibs = out["fibs"].ctypes.data if "fibs" in out else None
+            if "msc" in out:
+                io.msc = out["msc"].ctypes.data; io.msc_stride = out["msc"].shape[-1]
+            if "sf" in out:
+                io.sf = out["sf"].ctypes.data; io.sf_stride = out["sf"].shape[-1]
+            self._ck(self.lib.dabb_submit(self.h, C.byref(io)))
+            self._pending = getattr(self, "_pending", [])
+            self._pending.append((out, bs, iq))
+            return None
         out = {}
         if "results" in want:
             out["results"] = np.zeros(S, RESULT_DTYPE); io.results = out["results"].ctypes.data
@@ -279,8 +291,8 @@ class Context:
         self._ck(self.lib.dabb_get_info(self.h, int(what), C.byref(v)))
         return v.value
 
-    def set_options(self, disable_coarse=True, fft_placement=0, freqsync_method=0):
-        o = Options(); o.disable_coarse, o.fft_placement, o.freqsync_method = int(disable_coarse), int(fft_placement), int(freqsync_method)
+    def set_options(self, disable_coarse=True, fft_placement=0, freqsync_method=0, decode_tii=False):
+        o = Options(); o.disable_coarse, o.fft_placement, o.freqsync_method, o.decode_tii = int(disable_coarse), int(fft_placement), int(freqsync_method), int(decode_tii)
         self._ck(self.lib.dabb_set_options(self.h, C.byref(o)))
 
     def read_tap(self, what):
@@ -291,6 +303,8 @@ class Context:
             out = np.zeros((self.n_streams, 75, 16), np.complex64)
         elif what == 3:
             out = np.zeros((self.n_streams, 2656), np.complex64)
+        elif what == 4:
+            out = np.zeros((self.n_streams, 2, 2048), np.complex64)
         else:
             out = np.zeros((self.n_streams, TU), np.float32)
         self._ck(self.lib.dabb_read_tap(self.h, what, _vp(out), C.c_size_t(out.nbytes)))
