@@ -308,6 +308,15 @@ class Ref:
         k = self.lib.ref_superframe_filter(_p(frames), n, flen, _p(fec), n + 1, C.byref(au_err), C.byref(good))
         return fec[:2 * k].reshape(-1, 2), au_err.value, good.value
 
+    def tii_run(self, nulls, prss):
+        """the unmodified TIIDecoder fed frame by frame: nulls [n, 2656], prss [n, 2048] complex64 -> [(comb, pattern, delay_samples, error), ...]"""
+        nulls = np.ascontiguousarray(nulls, np.complex64); prss = np.ascontiguousarray(prss, np.complex64)
+        n = nulls.shape[0]
+        out = np.zeros(4 * 256, np.float32)
+        self.lib.ref_tii_run.restype = C.c_int
+        k = self.lib.ref_tii_run(_p(nulls), _p(prss), n, _p(out), 256)
+        return [tuple(out[4 * i: 4 * i + 4].tolist()) for i in range(min(k, 256))]
+
     def e2e(self, iq, disable_coarse=True, select_at_fib=24, dump_path="/tmp/ref_e2e.msc", keep_cir=False, fft_placement=0, freqsync_method=0):
         """fft_placement / freqsync_method use this repository's numbering (0 = the reference's defaults), see Oracle.find_index / coarse"""
         iq = np.ascontiguousarray(iq, np.complex64)

@@ -595,3 +595,31 @@ extern "C" int ref_fib_dump(const uint8_t* fibs, int n, char* out, int cap)
     memcpy(out, o.c_str(), o.size() + 1);
     return (int)o.size();
 }
+
+
+/* ---- TIIDecoder (backend/tii-decoder.cpp): the unmodified class fed frame by frame; the harness waits until its thread is idle again
+ * before the next frame so that every frame is analysed (the receiver itself drops frames while the decoder is busy).
+ * nulls: n x 2656 complex floats (the null symbol, oscillator applied), prss: n x 2048; out: 4 floats per measurement */
+extern "C" int ref_tii_run(const float* nulls, const float* prss, int n, float* out, int cap)
+{
+    struct Ri : NullRadioController {
+        std::vector<tii_measurement_t> got; std::mutex m;
+        void onTIIMeasurement(tii_measurement_t&& t) override { std::lock_guard<std::mutex> l(m); got.push_back(t); }
+    } ri;
+    DABParams params(1);
+    int k = 0;
+    {
+        TIIDecoder dec(params, ri);
+        for (int f = 0; f < n; f++) {
+            std::vector<complexf> nul(reinterpret_cast<const complexf*>(nulls) + (size_t)f * 2656, reinterpret_cast<const complexf*>(nulls) + (size_t)(f + 1) * 2656);
+            std::vector<complexf> prs(reinterpret_cast<const complexf*>(prss) + (size_t)f * 2048, reinterpret_cast<const complexf*>(prss) + (size_t)(f + 1) * 2048);
+            dec.pushSymbols(nul, prs);
+            for (;;) {
+                { std::unique_lock<std::mutex> l(dec.m_state_mutex); if (dec.m_state == TIIDecoder::State::Idle) break; }
+                std::this_thread::sleep_for(std::chrono::microseconds(200));
+            }
+        }
+    }
+    for (const auto& t : ri.got) { if (k < cap) { out[4 * k] = (float)t.comb; out[4 * k + 1] = (float)t.pattern; out[4 * k + 2] = (float)t.delay_samples; out[4 * k + 3] = t.error; } k++; }
+    return k;
+}

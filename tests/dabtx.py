@@ -284,8 +284,28 @@ class DabTx:
             cifs.append(cif)
         return np.concatenate([fic, np.concatenate(cifs)]).reshape(75, 3072)
 
+    def tii_null(self):
+        """the null symbol with the transmitter identification carriers of self.tii = [(comb, pattern, delay_samples, gain), ...]
+        (EN 300 401 clause 14.8: pairs of adjacent carriers k, k + 1, both with the phase of the phase reference symbol's carrier k, in four
+        blocks of 384 carriers; pattern p = the p-th 8-bit word with four ones picks which of the eight groups of a comb are on)"""
+        pats = [w for w in range(256) if bin(w).count("1") == 4]
+        Z = np.zeros(TU, np.complex128)
+        for comb, pattern, delay, gain in self.tii:
+            z = np.zeros(TU, np.complex128)
+            for b in range(8):
+                if (pats[pattern] >> (7 - b)) & 1:
+                    k0 = 1 + 2 * comb + 48 * b
+                    for k in (k0 - 769, k0 - 385, k0, k0 + 384):
+                        z[k % TU] = self.prs[k % TU]; z[(k + 1) % TU] = self.prs[k % TU]
+            kk = np.fft.fftfreq(TU, 1.0 / TU)
+            Z += gain * z * np.exp(-2j * np.pi * kk * delay / TU)
+        x = np.fft.ifft(Z) * (TU / np.sqrt(K) * self.amp)
+        return np.concatenate([x[-(TNULL - TU):], x])
+
     def modulate(self, bits75):
         out = np.zeros(TF, np.complex128)
+        if getattr(self, "tii", None):
+            out[:TNULL] = self.tii_null()
         Z = self.prs.copy()
         scale = TU / np.sqrt(K) * self.amp
         pos = TNULL

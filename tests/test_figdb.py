@@ -213,3 +213,32 @@ def test_random_fig_bodies(dumps):
         if "exception" in theirs:
             continue
         assert mine == theirs, trial
+
+
+def test_tii_analysis_matches_reference(oracle, ref):
+    """welle.io_b200/host/tii.h (pattern analysis of the glue) against the unmodified TIIDecoder (tii-decoder.cpp) frame by frame: two
+    transmitters (different comb / pattern / delay) in the null symbol, noise, 12 frames -> the same measurements (comb, pattern, delay in
+    samples, error sum) in the same order.  The glue's analyser starts from the two spectra - here made with the oracle's FFT, which is
+    bit-identical to the reference's fft::Forward (tests/test_oracle_vs_ref.py); on the GPU they are tap 4 (tests/test_gpu_glue.py)."""
+    import ctypes as C
+    import dabtx
+    lib = C.CDLL(os.path.join(ROOT, "welle.io_b200", "libwelle_b200_host.so"))
+    lib.welle_b200_tii_run.restype = C.c_int
+    tx = dabtx.DabTx(seed=0x711)
+    tx.tii = [(4, 17, 23, 0.5), (11, 52, 140, 0.35)]
+    sig = dabtx.add_awgn(tx.frames(13), 25.0, seed=4)
+    TF, TU, TNULL = 196608, 2048, 2656
+    nulls, prss = [], []
+    for f in range(1, 13):
+        base = f * TF
+        nulls.append(sig[base: base + TNULL]); prss.append(sig[base + TNULL + 504: base + TNULL + 504 + TU])     # aligned PRS (useful part)
+    # the reference pairs the PRS of frame n with the null symbol that FOLLOWS it
+    nulls, prss = np.stack(nulls[1:]), np.stack(prss[:-1])
+    want = ref.tii_run(nulls, prss)
+    assert len(want) >= 2 and {(int(w[0]), int(w[1])) for w in want} == {(4, 17), (11, 52)}
+    assert {(4, 23), (11, 140)} <= {(int(w[0]), int(w[2])) for w in want}, want          # the delays come out
+    nspec = np.stack([oracle.fft(x[TNULL - TU:]) for x in nulls]); pspec = np.stack([oracle.fft(x) for x in prss])
+    out = np.zeros(4 * 64, np.float32)
+    k = lib.welle_b200_tii_run(nspec.ctypes.data_as(C.c_void_p), pspec.ctypes.data_as(C.c_void_p), len(nulls), out.ctypes.data_as(C.c_void_p), 64)
+    got = [tuple(out[4 * i: 4 * i + 4].tolist()) for i in range(k)]
+    assert got == want, (got, want)

@@ -119,3 +119,45 @@ def test_scan_reports_signal_presence(tmp_path):
     s2 = dict(kv.split("=") for kv in subprocess.run([exe, str(f2), str(tmp_path / "b"), "12", "1", "1"], capture_output=True, text=True, timeout=600).stdout.split())
     assert s1["presence_true"] == "1" and s1["presence_false"] == "0" and int(s1["ok"]) > 0
     assert s2["presence_true"] == "0" and s2["presence_false"] == "1" and int(s2["fibs"]) == 0
+
+
+def test_tii_spectra_tap_and_glue_measurements(oracle, ref, tmp_path):
+    """RadioReceiverOptions::decodeTII.  (1) tap 4 of the library = fft::Forward of the frame's phase reference symbol and of the last
+    T_u samples of the null symbol that follows it, bit for bit (oracle FFT = reference FFT); (2) the glue's onTIIMeasurement stream on a
+    recording with two TII transmitters = the unmodified TIIDecoder fed with the same frames (positions: the reference's steady-state
+    windows)."""
+    from conftest import load_pkg
+    pkg = load_pkg()
+    TF, TU, TNULL = 196608, 2048, 2656
+    tx = dabtx.DabTx(seed=0x711)
+    tx.tii = [(4, 17, 23, 0.5), (11, 52, 140, 0.35)]
+    sig = dabtx.add_awgn(tx.frames(16), 25.0, seed=4)
+    # (1) the tap
+    ctx = pkg.Context(n_streams=1, keep_taps=True)
+    ctx.set_options(disable_coarse=True, decode_tii=True)
+    d = ctx.dev(sig.reshape(1, -1))
+    checked = 0
+    for step in range(15):
+        r = ctx.process(d, len(sig), np.zeros(1, np.int64), len(sig))["results"]
+        if r["status"][0] != pkg.FRAME_DECODED or r["next_pos"][0] > len(sig):
+            continue
+        spec = ctx.read_tap(4)[0]
+        null_start = int(r["next_pos"][0]) - TNULL
+        prs0 = null_start - 75 * 2552 - TU
+        assert np.array_equal(spec[0].view(np.uint32), oracle.fft(sig[prs0: prs0 + TU]).view(np.uint32))
+        assert np.array_equal(spec[1].view(np.uint32), oracle.fft(sig[null_start + TNULL - TU: null_start + TNULL]).view(np.uint32))
+        checked += 1
+    ctx.close()
+    assert checked >= 12
+    # (2) through the glue
+    exe = os.path.join(ROOT, "welle.io_b200", "glue_test")
+    f = tmp_path / "tii.cf32"; sig.tofile(f)
+    out = subprocess.run([exe, str(f), str(tmp_path / "t"), "12", "1", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = [tuple(float(x) for x in ln.split()) for ln in open(tmp_path / "t.tii").read().splitlines()]
+    nfr = len(np.fromfile(tmp_path / "t.fibs", np.uint8)) // (33 * 12)
+    nulls = np.stack([sig[(k + 1) * TF - 199: (k + 1) * TF - 199 + TNULL] for k in range(1, 1 + nfr)])
+    prss = np.stack([sig[k * TF + 2961: k * TF + 2961 + TU] for k in range(1, 1 + nfr)])
+    want = ref.tii_run(nulls, prss)
+    print(f"TII through the glue: {nfr} frames, measurements {got}")
+    assert len(want) >= 2 and got == want, (got, want)

@@ -294,7 +294,7 @@ __device__ __forceinline__ void fft2048_from_smem(const float2* in, int64_t idx0
     }
 }
 template <bool EXACT>
-__device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int t, const XIdx& xi, const float2* __restrict__ tw_c5)
+__device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int t, const XIdx& xi, const float2* __restrict__ tw_c5, const TwB2& b2)
 {
 #if DEMOD_SLIM
     const float2* twp = tw_c5 - TwLayout::C5;
@@ -305,7 +305,7 @@ __device__ __forceinline__ void fft2048_finish(float2 v[16], DemodSmem& sm, int 
     for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int a = 0; a < 4; a++) v[a + 4 * b] = sm.xbuf[xi.b[a] + 32 * b];
-    passB<EXACT, false>(v, xi.kk, twp);
+    passB_w<EXACT, false>(v, xi.kk, twp, b2);
 #pragma unroll
     for (int b = 0; b < 4; b++)
 #pragma unroll
@@ -367,6 +367,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         sm.rtab[t >> 4][k] = osc_fast(mod_rate64(-(int64_t)(128 * (k >> 3) + 256 * (k & 7)) * n.ph));
     }
     const XIdx xi = make_xidx(t);
+    const TwB2 b2 = load_twb2(tb.tw_fwd, xi.kk);
     // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
     int sidx[NSLOT];
 #pragma unroll
@@ -394,7 +395,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(l + 1);
         }
-        fft2048_finish<EXACT>(v, sm, t, xi, tw_c5);   // contains barrier (2)
+        fft2048_finish<EXACT>(v, sm, t, xi, tw_c5, b2);   // contains barrier (2)
 
         if (l >= l_first) {
             // demap owned bins against the previous symbol, scatter softbits into logical order (branch free)
@@ -426,18 +427,20 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 prev[s] = X;
             }
             __syncthreads();                   // (3)
-            // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits) and store 16 B per thread and half
+            // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits): thread t < 96 takes the 16-byte
+            // chunks t and t + 96 of the staging area (lane-consecutive: conflict-free; 8 carriers each) and stores 8 bytes per chunk and half
             if (t < 96) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(sbuf) + 2 * t;     // 16 pairs
-                const uint4 a = s4[0], b = s4[1];
-                uint4 re, im;
-                re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
-                re.y = __byte_perm(a.z, a.w, 0x6420); im.y = __byte_perm(a.z, a.w, 0x7531);
-                re.z = __byte_perm(b.x, b.y, 0x6420); im.z = __byte_perm(b.x, b.y, 0x7531);
-                re.w = __byte_perm(b.z, b.w, 0x6420); im.w = __byte_perm(b.z, b.w, 0x7531);
-                uint4* dst = reinterpret_cast<uint4*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
-                dst[t] = re;
-                dst[96 + t] = im;
+                const uint4* s4 = reinterpret_cast<const uint4*>(sbuf);
+                uint2* dst = reinterpret_cast<uint2*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint4 a = s4[t + 96 * h];
+                    uint2 re, im;
+                    re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
+                    re.y = __byte_perm(a.z, a.w, 0x6420); im.y = __byte_perm(a.z, a.w, 0x7531);
+                    dst[t + 96 * h] = re;               // carriers 8 (t + 96 h) .. + 7
+                    dst[192 + t + 96 * h] = im;
+                }
             }
 #if DEMOD_SLIM
             __syncthreads();        // staging area read: the next symbol's first pass may overwrite the exchange buffer

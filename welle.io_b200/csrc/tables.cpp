@@ -2,6 +2,9 @@
 // All values are derived from the ETSI EN 300 401 rules the reference implements; each builder cites the
 // reference file:line whose behaviour it reproduces.  (Independent of oracle/: the product never links it.)
 #include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include "osc_factors.h"
 #include <cmath>
 #include <cstring>
@@ -45,6 +48,11 @@ void build_host_tables(HostTables& t)
 {
     fill_twiddles(t.tw_fwd, false);
     fill_twiddles(t.tw_inv, true);
+    // the literals of ofdm_core.cuh's tw_a3() must be the table's values
+    for (int j = 0; j < 3; j++) {
+        const float2 f = tw_a3<false>(j), i = tw_a3<true>(j);
+        if (memcmp(&f, &t.tw_fwd[TwLayout::A3 + j], sizeof f) != 0 || memcmp(&i, &t.tw_inv[TwLayout::A3 + j], sizeof i) != 0) { fprintf(stderr, "libdab_b200: twiddle literal %d differs from the table\n", j); abort(); }
+    }
     // frequency interleaver (freq-interleaver.cpp:35-59)
     {
         int pi = 0, n = 0;

@@ -27,33 +27,6 @@ namespace {
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------ prep kernels
 // MSC collect: copy the sub-channel's slice of each of this frame's 4 CIFs into the de-interleaver ring, residue-major:
 // ring[(stream*slots + slot)][cif mod 20][r][j] = softbit (start_cu*64 + r + 16 j) of that CIF.
@@ -141,35 +114,54 @@ constexpr int VIT_MIN_CTAS = 512 / VIT_THREADS;   // 512 threads of 128 register
 constexpr int VIT_ROW_PITCH = 144;      // 128 B of softbits + 16 B pad (rows stay 16-byte aligned for the bulk copies)
 constexpr int VIT_STAGE_BYTES = VIT_THREADS * VIT_ROW_PITCH;
 
+constexpr int VIT_WARPS = VIT_THREADS / 32;
+constexpr int VIT_TAB_BYTES = VIT_STAGE_STEPS * 8;      // one stage's expansion entries (24 x 8 bytes = 12 x 16)
 template <int VIT_STAGES> struct __align__(16) VitSmemT {
-    unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];
-    uint64_t full[VIT_STAGES];
+    unsigned char stage[VIT_STAGES][VIT_STAGE_BYTES];        // per thread: the 128 bytes that hold its next <= 96 softbits
+    unsigned char tab[VIT_STAGES][VIT_WARPS][VIT_TAB_BYTES]; // per warp: the stage's expansion entries
 };
 
-// VIT_STAGES = 3: stand-alone launches (deep prefetch).  VIT_STAGES = 1: 18 KB of shared memory so that one CTA fits into
-// what four OFDM CTAs leave free on an SM (the copy latency is then hidden by the co-resident OFDM warps).
+// per-thread asynchronous copy global -> shared, 16 bytes (SASS: LDGSTS); completion by commit / wait groups of the issuing thread
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Staging.  Every thread owns one codeword and reads only ITS OWN row of a stage buffer, so its data needs no CTA-wide barrier: it
+// copies the 16-byte aligned 128 bytes that cover the stage's softbits with eight per-thread cp.async, three stages ahead, and waits
+// for its own copy groups.  (Round 1 / the first version of this round used one cp.async.bulk per thread: the bulk engine takes its
+// addresses from uniform registers, so the compiler emitted a 32-iteration lane loop per warp and stage - ncu: 10 % of the samples.)
+// The stage's expansion entries (the same for all codewords) are copied once per WARP by twelve of its lanes into a warp-private
+// area and read after a __syncwarp: no __syncthreads in the loop at all.
+// VIT_STAGES = 3: stand-alone launches (deep prefetch).  VIT_STAGES = 1: 19 KB of shared memory (co-residency experiment).
 template <int VIT_STAGES>
 __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int block)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     VitSmemT<VIT_STAGES>& sm = *reinterpret_cast<VitSmemT<VIT_STAGES>*>(smraw);
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cw = block * VIT_THREADS + t;
     const bool have = cw < p.n_cw;
     const int groups = p.nsteps / 6;                 // 6 steps per group, 4 groups per stage
     const int nstages = (groups + 3) / 4;
     const int cwc = have ? cw : 0;
     const unsigned char* frag = reinterpret_cast<const unsigned char*>(p.frag) + (int64_t)(cwc / p.cw_div) * p.outer_stride + (int64_t)(cwc % p.cw_div) * p.inner_stride;
+    const unsigned char* tabsrc = reinterpret_cast<const unsigned char*>(p.steptab);
 
-    if (t == 0) { for (int s = 0; s < VIT_STAGES; s++) mbar_init(&sm.full[s], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    // stage s needs the softbits [stage_off[s], stage_off[s+1]) of the fragment: copy the 16-byte aligned 128 bytes that cover them
+    // stage s needs the softbits [stage_off[s], stage_off[s+1]) of the fragment; always one commit group per call
     auto issue = [&](int s, int buf) {
-        if (t == 0) mbar_expect_tx(&sm.full[buf], VIT_THREADS * 128);
-        bulk_g2s(&sm.stage[buf][t * VIT_ROW_PITCH], frag + (__ldg(p.stage_off + s) & ~15u), 128, &sm.full[buf]);
+        if (s < nstages) {
+            const unsigned char* src = frag + (__ldg(p.stage_off + s) & ~15u);
+            unsigned char* dst = &sm.stage[buf][t * VIT_ROW_PITCH];
+#pragma unroll
+            for (int k = 0; k < 8; k++) cp_async16(dst + 16 * k, src + 16 * k);
+            if (lane < VIT_TAB_BYTES / 16) cp_async16(&sm.tab[buf][warp][16 * lane], tabsrc + (size_t)s * VIT_TAB_BYTES + 16 * lane);   // table is padded to whole stages
+        }
+        cp_async_commit();
     };
-    for (int s = 0; s < VIT_STAGES && s < nstages; s++) issue(s, s);
+    for (int s = 0; s < VIT_STAGES; s++) issue(s, s);
 
     uint32_t Q[32];
     vit_init(Q);
@@ -177,25 +169,27 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
 
     for (int s = 0; s < nstages; s++) {
         const int buf = s % VIT_STAGES;
-        mbar_wait(&sm.full[buf], (s / VIT_STAGES) & 1);
+        cp_async_wait<VIT_STAGES - 1>();            // this thread's copies of stage s have landed ...
+        __syncwarp();                               // ... and so have the other lanes' parts of the warp's table
         vit_normalize(Q);
         // 8-byte window (w0, w1) over the thread's row; everything about the window but its content is the same for all threads
         const uint32_t* my = reinterpret_cast<const uint32_t*>(&sm.stage[buf][t * VIT_ROW_PITCH]);
+        const uint2* tab = reinterpret_cast<const uint2*>(&sm.tab[buf][warp][0]);
         int nx = (int)((__ldg(p.stage_off + s) & 15u) >> 2);
         uint32_t w0 = my[nx], w1 = my[nx + 1];
         nx += 2;
         // the expansion of group g + 1 (table loads, window loads) is issued before the add-compare-select of group g: independent work
         // the scheduler interleaves, so that the window's load latency does not sit in front of every six steps
-        auto expand = [&](int g, uint32_t (&wo)[6]) {
+        auto expand = [&](int gq, uint32_t (&wo)[6]) {
 #pragma unroll
             for (int k = 0; k < 6; k++) {
-                const uint2 e = __ldg(p.steptab + 6 * g + k);           // {byte selector | advance << 16, byte mask}
+                const uint2 e = tab[6 * gq + k];                         // {byte selector | advance << 16, byte mask}: a broadcast read
                 wo[k] = vit_expand_step(w0, w1, e.x, e.y);
                 if (e.x & 0x10000u) { w0 = w1; w1 = my[nx]; nx++; }       // warp-uniform
             }
         };
         uint32_t wn[6];
-        if (4 * s < groups) expand(4 * s, wn);
+        if (4 * s < groups) expand(0, wn);
 #pragma unroll 1
         for (int gq = 0; gq < 4; gq++) {
             const int g = 4 * s + gq;
@@ -203,7 +197,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
             uint32_t w[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) w[k] = wn[k];
-            if (gq < 3 && g + 1 < groups) expand(g + 1, wn);
+            if (gq < 3 && g + 1 < groups) expand(gq + 1, wn);
             uint32_t d[12];
             vit_six_steps(Q, w, d, p.one);
             if (have) {
@@ -211,9 +205,10 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
                 for (int k = 0; k < 6; k++) dec[(int64_t)(6 * g + k) * VIT_THREADS] = make_uint2(d[2 * k], d[2 * k + 1]);
             }
         }
-        __syncthreads();   // every thread is done with this buffer's phase before it is re-armed
-        if (s + VIT_STAGES < nstages) issue(s + VIT_STAGES, buf);
+        __syncwarp();                               // every lane is done with the warp's table of this buffer before it is refilled
+        issue(s + VIT_STAGES, buf);
     }
+    cp_async_wait<0>();
     if (!have) return;
     if (p.valid && !p.valid[cw]) return;
     // traceback (vit_traceback24): 96 steps (nbits is a multiple of 96) give three output words; the decision words are read in
@@ -224,8 +219,11 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
     for (int tb = p.nbits - 96; tb >= 0; tb -= 96) {
         uint32_t acc[3] = {0, 0, 0};
         vit_u2 d[24];
+        // the decision words of a 32 768-codeword launch (0.6 GB) have mostly left the L2 by the time the traceback wants them: the batch
+        // after next (48 steps further down) is requested into the L2 while this one is walked
 #define VIT_TB_QUARTER(Q) do { \
             _Pragma("unroll") for (int k = 0; k < 24; k++) { const uint2 v = dec[(int64_t)(tb + 24 * (Q) + k + 6) * VIT_THREADS]; d[k].x = v.x; d[k].y = v.y; } \
+            if (tb + 24 * (Q) - 48 + 6 >= 0) { _Pragma("unroll") for (int k = 0; k < 24; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(dec + (int64_t)(tb + 24 * (Q) - 48 + k + 6) * VIT_THREADS)); } \
             vit_traceback24<(Q)>(state, d, acc); } while (0)
         VIT_TB_QUARTER(3); VIT_TB_QUARTER(2); VIT_TB_QUARTER(1); VIT_TB_QUARTER(0);
 #undef VIT_TB_QUARTER
@@ -279,6 +277,7 @@ __global__ void unpack_bits_kernel(const uint8_t* __restrict__ bytes, int64_t st
 void build_vit_tables_u2(const int16_t* map, int nsteps, std::vector<uint2>& steps, std::vector<uint32_t>& stage_off)
 {
     build_vit_tables(map, nsteps, steps, stage_off);     // viterbi_core.cuh
+    while (steps.size() % VIT_STAGE_STEPS) steps.push_back(make_uint2(0, 0));      // the kernel copies whole stages of the table
 }
 
 void launch_clamp_copy(const int8_t* src, int8_t* dst, int64_t n, cudaStream_t st)

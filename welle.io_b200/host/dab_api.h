@@ -150,7 +150,10 @@ struct Subchannel {
 };
 
 struct dab_date_time_t { int year = 0, month = 0, day = 0, hour = 0, minutes = 0, seconds = 0, hourOffset = 0, minuteOffset = 0; };
-struct tii_measurement_t { int comb = 0, pattern = 0; float error = 0; int delay_samples = 0; };
+struct tii_measurement_t {
+    int comb = 0, pattern = 0; float error = 0; int delay_samples = 0;
+    float getDelayKm(void) const { return delay_samples * (3e8f / 1000.0f / 2048000.0f); }      /* tii-decoder.cpp:133-137 */
+};
 struct mot_file_t { std::vector<uint8_t> data; int content_sub_type = 0; std::string content_name, click_through_url; uint8_t category = 0, slide_id = 0; std::string category_title; };
 enum class message_level_t { Information, Error };
 

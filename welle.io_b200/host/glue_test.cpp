@@ -38,7 +38,8 @@ struct Ctl : RadioControllerInterface {
     void onNewImpulseResponse(std::vector<float>&& v) override { cirs++; tapsz_ok &= v.size() == 2048; }
     void onConstellationPoints(std::vector<DSPCOMPLEX>&& v) override { consts++; tapsz_ok &= v.size() == 1200; }   /* (L-1) K / 96 */
     void onNewNullSymbol(std::vector<DSPCOMPLEX>&& v) override { nulls++; tapsz_ok &= v.size() == 2656; }
-    void onTIIMeasurement(tii_measurement_t&&) override {} void onMessage(message_level_t, const std::string& a, const std::string& b) override { fprintf(stderr, "msg: %s %s\n", a.c_str(), b.c_str()); }
+    FILE* tii = nullptr; int tiis = 0;
+    void onTIIMeasurement(tii_measurement_t&& m) override { tiis++; if (tii) fprintf(tii, "%d %d %d %.1f\n", m.comb, m.pattern, m.delay_samples, m.error); } void onMessage(message_level_t, const std::string& a, const std::string& b) override { fprintf(stderr, "msg: %s %s\n", a.c_str(), b.c_str()); }
     void onInputFailure() override { failed = true; }
 };
 int main(int argc, char** argv)
@@ -48,6 +49,8 @@ int main(int argc, char** argv)
     ri.fibs = fopen((pre + ".fibs").c_str(), "wb"); ph.rs = fopen((pre + ".rs").c_str(), "w"); ri.dump = pre + ".msc"; ri.ph = &ph;
     if (argc > 3) ri.select_at = atoi(argv[3]);
     RadioReceiverOptions rro; rro.disableCoarseCorrector = argc > 4 ? atoi(argv[4]) != 0 : true;    /* default like the parity harness (welle-cli -u) */
+    rro.decodeTII = argc > 5 && atoi(argv[5]) != 0;                                                /* welle-cli -T */
+    if (rro.decodeTII) ri.tii = fopen((pre + ".tii").c_str(), "w");
     double secs = 0;
     {
         RadioReceiver rx(ri, in, rro);
@@ -58,7 +61,8 @@ int main(int argc, char** argv)
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();      /* restart .. input exhausted */
         rx.stop();
     }
-    fclose(ri.fibs); fclose(ph.rs);
+    fclose(ri.fibs); fclose(ph.rs); if (ri.tii) fclose(ri.tii);
+    printf("tii=%d ", ri.tiis);
     printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d cirs=%d consts=%d nulls=%d tapsizes=%d seconds=%.4f\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs,
            ri.cirs, ri.consts, ri.nulls, (int)ri.tapsz_ok, secs);
     return 0;

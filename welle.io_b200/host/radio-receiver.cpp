@@ -10,6 +10,7 @@
  */
 #include "dab_api.h"
 #include "fig-db.h"
+#include "tii.h"
 #include "../../include/dab_b200.h"
 
 #include <atomic>
@@ -86,6 +87,7 @@ struct RadioReceiver::Impl {
     bool synced = false; float snr = 0; int snrCount = 0; long sampleCnt = 0;
     /* OFDMProcessor::scanMode / attempts (ofdm-processor.cpp:258-262,351-355): set by restart(doScan) */
     std::atomic<bool> scanMode{false}; int failedSearches = 0;
+    dabb_host::TiiAnalyzer tii;            /* RadioReceiverOptions::decodeTII (ofdm-processor.cpp:383-386,464-466) */
 
     /* the reference's enumerators (radio-receiver-options.h:35-64) -> DABB_PLACEMENT_* / DABB_FREQSYNC_* (0 = the reference's default) */
     static int placementOf(FFTPlacementMethod m) { return m == FFTPlacementMethod::StrongestPeak ? DABB_PLACEMENT_STRONGEST_PEAK : m == FFTPlacementMethod::EarliestPeakWithBinning ? DABB_PLACEMENT_EARLIEST_PEAK_WITH_BINNING : DABB_PLACEMENT_THRESHOLD_BEFORE_PEAK; }
@@ -94,6 +96,7 @@ struct RadioReceiver::Impl {
     {
         dabb_options op; memset(&op, 0, sizeof op);
         op.disable_coarse = o.disableCoarseCorrector ? 1 : 0; op.fft_placement = placementOf(o.fftPlacementMethod); op.freqsync_method = freqsyncOf(o.freqsyncMethod);
+        op.decode_tii = o.decodeTII ? 1 : 0;
         std::lock_guard<std::mutex> l(ctxMutex);
         dabb_set_options(ctx, &op);
     }
@@ -106,6 +109,7 @@ struct RadioReceiver::Impl {
         cfg.disable_coarse = o.disableCoarseCorrector ? 1 : 0; cfg.fft_placement = placementOf(o.fftPlacementMethod); cfg.freqsync_method = freqsyncOf(o.freqsyncMethod);
         cfg.keep_taps = 1; cfg.n_subch_slots = DABB_MAX_SUBCH; cfg.max_subch_cu = 416; cfg.ofdm_groups = 25;
         if (dabb_create(&cfg, &ctx) != DABB_OK) throw std::runtime_error(std::string("B200 backend: ") + dabb_last_error(nullptr));
+        applyOptions(o);
     }
     ~Impl() { stopWorker(); closeSlots(); if (ctx) dabb_destroy(ctx); }
 
@@ -217,6 +221,12 @@ struct RadioReceiver::Impl {
             int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 3, nul.data(), nul.size() * sizeof(DSPCOMPLEX)); }
             if (trc == DABB_OK) rci.onNewNullSymbol(std::move(nul));
         }
+        if (rro.decodeTII) {
+            /* TIIDecoder::pushSymbols(nullSymbol, prs): the two transforms come from the GPU (tap 4), the pattern analysis runs here */
+            std::vector<complexf> spec(2 * DABB_TU);
+            int trc; { std::lock_guard<std::mutex> l(ctxMutex); trc = dabb_read_tap(ctx, 4, spec.data(), spec.size() * sizeof(complexf)); }
+            if (trc == DABB_OK) tii.process(spec.data() + DABB_TU, spec.data(), [this](tii_measurement_t&& m) { rci.onTIIMeasurement(std::move(m)); });
+        }
         for (int f = 0; f < 12; f++) {
             uint8_t bits[256];
             for (int i = 0; i < 256; i++) bits[i] = (fibs[32 * f + (i >> 3)] >> (7 - (i & 7))) & 1;
@@ -295,7 +305,7 @@ RadioReceiver::~RadioReceiver() {}
 
 void RadioReceiver::restart(bool doScan)
 {
-    d->stopWorker(); d->closeSlots(); d->db.clear();
+    d->stopWorker(); d->closeSlots(); d->db.clear(); d->tii.clear();
     d->scanMode = doScan;                                    /* OFDMProcessor::set_scanMode (radio-receiver.cpp:84) */
     { std::lock_guard<std::mutex> l(d->ctxMutex); for (int k = 0; k < DABB_MAX_SUBCH; k++) dabb_remove_subchannel(d->ctx, 0, 1, k); }
     d->input.restart();
@@ -366,6 +376,17 @@ RadioReceiverStats RadioReceiver::getReceiverStats() const
     std::lock_guard<std::mutex> l(d->db.m);
     s.timeLastFCT0Frame = d->db.timeLastFCT0Frame;          /* radio-receiver.cpp:225-230 */
     return s;
+}
+
+/* test hook: the TII analysis of n frames of spectra (natural bin order, 2048 complex floats each); out: 4 floats per measurement
+ * (comb, pattern, delay_samples, error) in the order of the onTIIMeasurement callbacks; returns their number */
+extern "C" int welle_b200_tii_run(const float* null_specs, const float* prs_specs, int n, float* out, int cap)
+{
+    dabb_host::TiiAnalyzer an; int k = 0;
+    for (int f = 0; f < n; f++)
+        an.process(reinterpret_cast<const complexf*>(null_specs) + (size_t)f * 2048, reinterpret_cast<const complexf*>(prs_specs) + (size_t)f * 2048,
+                   [&](tii_measurement_t&& m) { if (k < cap) { out[4 * k] = (float)m.comb; out[4 * k + 1] = (float)m.pattern; out[4 * k + 2] = (float)m.delay_samples; out[4 * k + 3] = m.error; } k++; });
+    return k;
 }
 
 /* test hook: feeds n FIBs (32 bytes each) to a fresh service database and writes its text dump (callbacks first) */
