@@ -375,6 +375,7 @@ struct GatedMemInput : CVirtualInput {
     const DSPCOMPLEX* d; size_t n; std::atomic<size_t> pos{0};
     std::atomic<long> frames_done{0};
     std::atomic<bool> stopped{false};
+    long slack = 0;          /* frames consumed without a decoded frame coming out (acquisition, sync losses): each 250 ms stall adds one, for good */
     long T_F;
     GatedMemInput(const float* iq, size_t nsamples, long tf) : d(reinterpret_cast<const DSPCOMPLEX*>(iq)), n(nsamples), T_F(tf) {}
     CDeviceID getID() override { return CDeviceID::RAWFILE; }
@@ -387,13 +388,12 @@ struct GatedMemInput : CVirtualInput {
     void stop() override { stopped = true; }
     void reset() override {}
     int32_t getSamples(DSPCOMPLEX* b, int32_t cnt) override {
-        /* gate: never run more than two frames ahead of the decoder worker; a 500 ms stall opens the gate
-         * by one frame so that (re-)acquisition, which consumes samples without producing frames, cannot deadlock */
+        /* gate: never run more than two frames ahead of the decoder worker; a 250 ms stall opens the gate
+         * by one frame - permanently - so that (re-)acquisition, which consumes samples without producing frames, cannot deadlock */
         auto t0 = std::chrono::steady_clock::now();
-        long extra = 0;
-        while (!stopped && (long)pos.load() + cnt > (frames_done.load() + 2 + extra) * T_F) {
+        while (!stopped && (long)pos.load() + cnt > (frames_done.load() + 2 + slack) * T_F) {
             std::this_thread::sleep_for(std::chrono::microseconds(50));
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(500)) { extra++; t0 = std::chrono::steady_clock::now(); }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(250)) { slack++; t0 = std::chrono::steady_clock::now(); }
         }
         size_t p = pos.load();
         size_t m = p < n ? std::min<size_t>(cnt, n - p) : 0;

@@ -17,7 +17,5 @@ build() {   # name, source, macro
     nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../gpurun_exp_$1.so $objs -lcudart
     echo "built gpurun_exp_$1.so"
 }
-build pairs ofdm -DDABB_DEMAP_PAIRS
-build cta6 ofdm -DDEMOD_CTAS_PER_SM=6
-build cta6pairs ofdm "-DDEMOD_CTAS_PER_SM=6 -DDABB_DEMAP_PAIRS"
-build vit64 viterbi -DVIT_THREADS_N=64
+build nopairs ofdm -DDABB_NO_DEMAP_PAIRS
+build vittfma viterbi -DVIT_T_FMA
