@@ -473,9 +473,9 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     if (getenv("DABB_TAIL_GROUPS")) { const int v = atoi(getenv("DABB_TAIL_GROUPS")); if (v > 0 && 75 % v == 0) ctx->tail_groups = v; }
     ctx->fc_pitch = ctx->tail_frames ? ctx->tail_groups : ctx->groups;
     // tables
-    float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
+    float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm, *sbp, *sbc; uint8_t *ge, *gl, *pb;
     if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
-        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
+        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &sbp, TU)) || (rc = dalloc(ctx, &sbc, SoftStage::CHUNKS)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
         return fail(rc);
     {
         ctx->h_osc.resize(INPUT_RATE);
@@ -485,13 +485,15 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpyAsync(ti, ctx->host->tw_inv, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pr, ctx->host->prs_ref, sizeof(float2) * TU, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ip, ctx->host->invperm, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(sbp, ctx->host->sb_pos, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(sbc, ctx->host->sb_chunk, sizeof(int16_t) * SoftStage::CHUNKS, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(fm, ctx->host->fic_map, sizeof(int16_t) * 3096, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ge, ctx->host->gf_exp, 512, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(gl, ctx->host->gf_log, 256, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pb, ctx->host->prbs, sizeof ctx->host->prbs, cudaMemcpyHostToDevice, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "table upload failed"; return fail(DABB_E_CUDA); }
     }
-    ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.fic_map = fm;
+    ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.sb_pos = sbp; ctx->dev.sb_chunk = sbc; ctx->dev.fic_map = fm;
     ctx->dev.gf_exp = ge; ctx->dev.gf_log = gl; ctx->dev.prbs = pb;
     {
         // on-the-fly oscillator: upload the factors, compare against the table for every index on the device, adopt it only when
