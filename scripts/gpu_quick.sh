@@ -19,5 +19,5 @@ PY
 }
 unset DABB_LIB
 one default
-DABB_TAIL_GROUPS=5 one tailg5
-for lib in $(ls gpurun_exp_*.so 2>/dev/null); do export DABB_LIB=$PWD/$lib; one "$lib"; DABB_TAIL_GROUPS=5 one "${lib}_tailg5"; done
+DABB_CORESIDENT=1 one coresident
+for lib in $(ls gpurun_exp_*.so 2>/dev/null); do export DABB_LIB=$PWD/$lib; one "$lib"; done

@@ -95,36 +95,3 @@ def test_decoder_kernel_emulation_depuncture_and_traceback(oracle):
             out = np.zeros(nbits // 8, np.uint8)
             rc = lib.emul_vitdec(C.c_void_p(raw.ctypes.data + off), m.ctypes.data_as(C.c_void_p), nbits, None, out.ctypes.data_as(C.c_void_p))
             assert rc == 0 and np.array_equal(out, exp), (name, trial, int((out != exp).sum()))
-
-
-def test_softbit_staging_placement_recount():
-    """the bank-group table of the OFDM kernel's softbit staging area (tables.cpp: kSoftStageGroup, layout in common.cuh: SoftStage):
-    every group holds at most 27 blocks, and the 52 scatter-store instructions of a CTA (4 warps x 13 owned bins per thread) need 116
-    shared-memory wavefronts per symbol with it against 171 when a carrier's entry is its logical index"""
-    import re
-    import dabtx
-    src = open(os.path.join(os.path.dirname(HERE), "..", "welle.io_b200", "csrc", "tables.cpp")).read()
-    grp = [int(x) for x in re.search(r"kSoftStageGroup\[96\] = \{([^}]*)\}", src).group(1).replace("\n", "").split(",")]
-    assert len(grp) == 96 and max(np.bincount(grp, minlength=4)) <= 27
-    perm = dabtx.perm_table()
-    inv = -np.ones(2048, int)
-    for i, k in enumerate(perm):
-        inv[k % 2048] = i
-    nxt, slot = [0, 0, 0, 0], []
-    for b in range(96):
-        slot.append(4 * nxt[grp[b]] + grp[b]); nxt[grp[b]] += 1
-
-    def count(pos_of):
-        tot = 0
-        for w in range(4):
-            for s in range(13):
-                c = s if s < 7 else s + 3
-                banks = {}
-                for t in range(32 * w, 32 * w + 32):
-                    iv = inv[t + 128 * c]
-                    pos = pos_of(iv, t)
-                    banks.setdefault((pos >> 1) & 31, set()).add(pos >> 1)
-                tot += max(len(v) for v in banks.values())
-        return tot
-    assert count(lambda iv, t: iv if iv >= 0 else 1536 + t) == 171
-    assert count(lambda iv, t: 16 * slot[iv >> 4] + (iv & 15) if iv >= 0 else 16 * 108 + t) == 116

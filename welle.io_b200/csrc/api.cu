@@ -104,6 +104,15 @@ template <typename T> int dalloc(dabb_ctx* ctx, T** p, size_t n, bool zero = tru
     return 0;
 }
 
+// frees a device allocation made through dalloc / tracked in ctx->allocs
+template <typename T> void dfree(dabb_ctx* ctx, T*& p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < ctx->allocs.size(); i++) if (ctx->allocs[i] == (void*)p) { ctx->allocs.erase(ctx->allocs.begin() + i); break; }
+    cudaFree((void*)p);
+    p = nullptr;
+}
+
 void prof_mark(dabb_ctx* ctx, const char* what)
 {
     if (!ctx->prof) return;
@@ -415,6 +424,7 @@ __global__ void convert_iq_kernel(const uint8_t* __restrict__ raw, int64_t raw_s
 int ensure_dec(dabb_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->dec_bytes) return 0;
+    if (ctx->d_dec) { cudaStreamSynchronize(ctx->stream); dfree(ctx, ctx->d_dec); ctx->dec_bytes = 0; }
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(decisions): ") + cudaGetErrorString(e); return DABB_E_NOMEM; }
@@ -456,7 +466,10 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     {
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lane B gets the higher priority: its CTAs take the SM resources lane A leaves free
         if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
-        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 50 * 1024 : 0;   // experimental co-residency cap (measured slower: off by default)
+        // co-residency experiment: 46 KB per OFDM CTA -> four of them per SM (49 152 registers, 188 KB), leaving exactly the 16 384 registers
+        // and 40 KB one two-stage Viterbi CTA needs, so that the integer ACS work runs in the issue slots the shared-memory-bound OFDM
+        // kernel leaves free instead of taking turns with it
+        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 46 * 1024 : 0;
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
@@ -473,9 +486,9 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     if (getenv("DABB_TAIL_GROUPS")) { const int v = atoi(getenv("DABB_TAIL_GROUPS")); if (v > 0 && 75 % v == 0) ctx->tail_groups = v; }
     ctx->fc_pitch = ctx->tail_frames ? ctx->tail_groups : ctx->groups;
     // tables
-    float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm, *sbp, *sbc; uint8_t *ge, *gl, *pb;
+    float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
     if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
-        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &sbp, TU)) || (rc = dalloc(ctx, &sbc, SoftStage::CHUNKS)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
+        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
         return fail(rc);
     {
         ctx->h_osc.resize(INPUT_RATE);
@@ -485,15 +498,13 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpyAsync(ti, ctx->host->tw_inv, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pr, ctx->host->prs_ref, sizeof(float2) * TU, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ip, ctx->host->invperm, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(sbp, ctx->host->sb_pos, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(sbc, ctx->host->sb_chunk, sizeof(int16_t) * SoftStage::CHUNKS, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(fm, ctx->host->fic_map, sizeof(int16_t) * 3096, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ge, ctx->host->gf_exp, 512, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(gl, ctx->host->gf_log, 256, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pb, ctx->host->prbs, sizeof ctx->host->prbs, cudaMemcpyHostToDevice, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "table upload failed"; return fail(DABB_E_CUDA); }
     }
-    ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.sb_pos = sbp; ctx->dev.sb_chunk = sbc; ctx->dev.fic_map = fm;
+    ctx->dev.tw_fwd = tf; ctx->dev.tw_inv = ti; ctx->dev.prs_ref = pr; ctx->dev.osc = osc; ctx->dev.invperm = ip; ctx->dev.fic_map = fm;
     ctx->dev.gf_exp = ge; ctx->dev.gf_log = gl; ctx->dev.prbs = pb;
     {
         // on-the-fly oscillator: upload the factors, compare against the table for every index on the device, adopt it only when
@@ -619,6 +630,9 @@ int dabb_select_subchannel(dabb_ctx* ctx, int32_t first, int32_t count, int32_t 
         bool others = false;
         for (int i = 0; i < S; i++) if ((i < first || i >= first + count) && ctx->h_slots[(size_t)i * ctx->n_slots + slot].enabled) others = true;
         if (others) { ctx->err = "streams sharing a slot must use the same bitrate/protection; use another slot"; return DABB_E_UNSUPPORTED; }
+        // the slot changes its code geometry: give back the buffers sized for the old one (all streams are idle: sync_all above)
+        dfree(ctx, sl.d_steptab); dfree(ctx, sl.d_stage_off); dfree(ctx, sl.d_prbs_words); dfree(ctx, sl.d_frag); dfree(ctx, sl.d_valid);
+        dfree(ctx, sl.d_logical); dfree(ctx, sl.d_window); dfree(ctx, sl.d_sf); dfree(ctx, sl.d_info); dfree(ctx, sl.d_dec);
         sl.configured = false;
     }
     if (!sl.configured) {
@@ -739,7 +753,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     // serially on the main stream.
     const int par = (int)(ctx->step & 1);
     const bool serial = ctx->prof;
-    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 1;
+    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 2;
     cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
     StepScratch* scr = ctx->d_scr + (size_t)par * S;
     int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;

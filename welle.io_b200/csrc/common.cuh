@@ -12,8 +12,6 @@ struct DevTables {
     const float2* tw_fwd;      // TwLayout::TOTAL entries, forward transform
     const float2* tw_inv;      // inverse transform
     const int16_t* invperm;    // [2048] bin -> logical carrier index 0..1535, -1 for unused bins (freq-interleaver.cpp:35-91)
-    const int16_t* sb_pos;     // [2048] bin -> entry of the OFDM kernel's softbit staging area (SoftStage layout below), -1 for unused bins
-    const int16_t* sb_chunk;   // [SoftStage::CHUNKS] 16-byte chunk of the staging area -> index of its 8 carriers' output (carrier / 8), -1 = empty
     const float2* prs_ref;     // [2048] PhaseReference::refTable (phasereference.cpp:45-51)
     const float2* osc;         // [2 048 000] oscillator table (ofdm-processor.cpp:92-94)
     // the same values computed on the fly (osc_mode = 1): osc[m] == float(H[m >> 10] * exp(j theta (m & 1023))) in double, the small
@@ -27,13 +25,6 @@ struct DevTables {
     const uint8_t* gf_exp;     // [512]
     const uint8_t* gf_log;     // [256]
 };
-
-// Softbit staging area of the OFDM kernel: (re | im << 8) per logical carrier.  The frequency de-interleaver scatters a warp's 32
-// carriers pseudo-randomly over the 1536 entries (3.3 shared-memory wavefronts per 16-bit store when entry = logical index).  Blocks of
-// 16 consecutive carriers (32 bytes = 8 banks) are therefore placed in one of four bank groups chosen per block so that the 52
-// (warp, slot) store instructions collide least (kSoftStageGroup in tables.cpp, found offline by annealing: 2.2 wavefronts per store);
-// slot = 4 q + group, q < ROWS.  Read back linearly (chunk t, t + 108: conflict-free) through sb_chunk.
-struct SoftStage { static constexpr int ROWS = 27, SLOTS = 4 * ROWS, ENTRIES = 16 * SLOTS, CHUNKS = 2 * SLOTS, DUMMY = ENTRIES; };
 
 // ---- OFDM demod launch parameters ----
 struct OfdmParams {
@@ -77,7 +68,7 @@ void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const 
 // ---- host-side table builders (tables.cpp) ----
 struct HostTables {
     float2 tw_fwd[TwLayout::TOTAL], tw_inv[TwLayout::TOTAL];
-    int16_t perm[KC]; int16_t invperm[TU]; int16_t sb_pos[TU]; int16_t sb_chunk[SoftStage::CHUNKS];
+    int16_t perm[KC]; int16_t invperm[TU];
     float2 prs_ref[TU];
     uint8_t prbs[16384];
     int16_t fic_map[3096];

@@ -187,8 +187,8 @@ constexpr float LEVEL_DECAY_SYM = 0.97480279f;
 #define DEMOD_CTAS_PER_SM 5
 #endif
 constexpr int IN_CAP = 2560;     // staged samples per symbol: 2552 + 1 (16-byte alignment shift) + 1 (round-up), padded
-constexpr int SB_DUMMY = SoftStage::DUMMY;   // softbit staging as (re, im) byte pairs, SoftStage::ENTRIES real entries (placement: common.cuh), then one
-                                             // private dummy entry per thread for its unused bin
+constexpr int SB_DUMMY = 1536;   // softbit staging as (re, im) byte pairs indexed by logical carrier: [0,1536) real entries, then one private
+                                 // dummy entry per thread for its unused bin
 // DEMOD_CTAS_PER_SM >= 6 (experiment): 37 KB of shared memory per CTA - the small twiddles come through L1 and the softbit staging
 // area lives in the exchange buffer (two more barriers per symbol) - and 80 registers
 #define DEMOD_SLIM (DEMOD_CTAS_PER_SM >= 6)
@@ -197,7 +197,7 @@ struct __align__(16) DemodSmem {
     float2 xbuf[TU];                 // 16 KB swizzled exchange buffer
 #if !DEMOD_SLIM
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
-    uint16_t sbuf[SoftStage::ENTRIES + 128];        // (re | im << 8) per carrier: one 16-bit scatter store per carrier
+    uint16_t sbuf[1536 + 128];        // (re | im << 8) per logical carrier: one 16-bit scatter store per carrier
 #endif
     float2 rtab[2][16];              // DABB_NCO_FAST: e^{-j theta((128 h + 256 c) Hz)} for the PRS / the data symbols
     float red[16];
@@ -371,8 +371,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
     int sidx[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; s++) { const int iv = tb.sb_pos[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy entry
-    const int cdst0 = t < SoftStage::CHUNKS / 2 ? tb.sb_chunk[t] : -1, cdst1 = t < SoftStage::CHUNKS / 2 ? tb.sb_chunk[t + SoftStage::CHUNKS / 2] : -1;
+    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
     __syncthreads();
 
     float2 prev[NSLOT];
@@ -409,9 +408,8 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 sbuf[sidx[s]] = (uint16_t)((uint8_t)sre0 | ((uint16_t)(uint8_t)sim0 << 8));
                 sbuf[sidx[s + 1]] = (uint16_t)((uint8_t)sre1 | ((uint16_t)(uint8_t)sim1 << 8));
                 if (TAP) {
-                    const int i0 = tb.invperm[t + 128 * slot_c(s)], i1 = tb.invperm[t + 128 * slot_c(s + 1)];
-                    if (i0 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + i0] = r10;
-                    if (i1 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + i1] = r11;
+                    if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r10;
+                    if (sidx[s + 1] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s + 1]] = r11;
                 }
                 prev[s] = X0; prev[s + 1] = X1;
             }
@@ -425,26 +423,23 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
                 sbuf[sidx[s]] = (uint16_t)((uint8_t)sre | ((uint16_t)(uint8_t)sim << 8));
-                if (TAP) { const int i0 = tb.invperm[t + 128 * slot_c(s)]; if (i0 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + i0] = r1; }
+                if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
                 prev[s] = X;
             }
             __syncthreads();                   // (3)
-            // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits): thread t < 108 takes the 16-byte chunks
-            // t and t + 108 of the staging area (lane-consecutive: conflict-free; 8 carriers each, sb_chunk says which) and stores 8 bytes
-            // per chunk and half
-            if (t < SoftStage::CHUNKS / 2) {
+            // de-interleave the pairs into the reference's layout (1536 Re bits, then 1536 Im bits): thread t < 96 takes the 16-byte
+            // chunks t and t + 96 of the staging area (lane-consecutive: conflict-free; 8 carriers each) and stores 8 bytes per chunk and half
+            if (t < 96) {
                 const uint4* s4 = reinterpret_cast<const uint4*>(sbuf);
                 uint2* dst = reinterpret_cast<uint2*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int cd = h ? cdst1 : cdst0;
-                    if (cd < 0) continue;
-                    const uint4 a = s4[t + (SoftStage::CHUNKS / 2) * h];
+                    const uint4 a = s4[t + 96 * h];
                     uint2 re, im;
                     re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
                     re.y = __byte_perm(a.z, a.w, 0x6420); im.y = __byte_perm(a.z, a.w, 0x7531);
-                    dst[cd] = re;                       // carriers 8 cd .. 8 cd + 7
-                    dst[192 + cd] = im;
+                    dst[t + 96 * h] = re;               // carriers 8 (t + 96 h) .. + 7
+                    dst[192 + t + 96 * h] = im;
                 }
             }
 #if DEMOD_SLIM

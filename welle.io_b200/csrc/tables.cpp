@@ -44,13 +44,6 @@ static float prs_phi(int k)
     return (float)(M_PI / 2.0f * (kPrsH[kPrsI[b]][(k - kmin) & 15] + kPrsN[b]));
 }
 
-// bank group (0..3) of each block of 16 logical carriers in the OFDM kernel's softbit staging area (common.cuh: SoftStage): minimises
-// the bank conflicts of the de-interleaving scatter stores (annealing over the 52 store instructions of a CTA, at most 27 blocks per
-// group; 116 wavefronts per symbol and CTA instead of 171 for the identity placement - tests/test_host_emul.py recounts them)
-static const uint8_t kSoftStageGroup[96] = {
-    2,3,1,1,2,2,0,2,3,3,0,2,2,1,3,3,0,3,2,2,0,2,1,0,3,3,1,3,3,3,1,0,1,2,1,1,3,2,1,1,2,3,0,3,3,1,2,0,0,3,1,3,1,2,1,2,0,0,2,3,3,0,1,2,0,3,1,3,0,3,0,1,
-    0,3,1,0,1,0,2,2,0,0,3,2,0,3,2,3,3,0,2,1,0,1,1,0};
-
 void build_host_tables(HostTables& t)
 {
     fill_twiddles(t.tw_fwd, false);
@@ -72,18 +65,6 @@ void build_host_tables(HostTables& t)
             t.invperm[carrier < 0 ? carrier + TU : carrier] = (int16_t)n;
             n++;
         }
-    }
-    // softbit staging placement
-    {
-        int next_row[4] = {0, 0, 0, 0}, slot_of[96];
-        for (int c = 0; c < SoftStage::CHUNKS; c++) t.sb_chunk[c] = -1;
-        for (int b = 0; b < 96; b++) {
-            const int g = kSoftStageGroup[b], q = next_row[g]++;
-            if (q >= SoftStage::ROWS) { fprintf(stderr, "libdab_b200: softbit staging group overflow\n"); abort(); }
-            slot_of[b] = 4 * q + g;
-            t.sb_chunk[2 * slot_of[b]] = (int16_t)(2 * b); t.sb_chunk[2 * slot_of[b] + 1] = (int16_t)(2 * b + 1);
-        }
-        for (int i = 0; i < TU; i++) t.sb_pos[i] = t.invperm[i] < 0 ? (int16_t)-1 : (int16_t)(16 * slot_of[t.invperm[i] >> 4] + (t.invperm[i] & 15));
     }
     // phase reference (phasereference.cpp:45-51): float phase, float cos/sin
     memset(t.prs_ref, 0, sizeof t.prs_ref);

@@ -60,7 +60,7 @@ msc_collect_kernel(MscCollectParams p)
     }
 }
 
-// MSC gather: one CTA per stream, its four CIFs in turn.  Copies the 16 residue rows of the time-de-interleaved fragment
+// MSC gather: one CTA per (stream, CIF c).  Copies the 16 residue rows of the time-de-interleaved fragment
 // (out[i] = CIF[n - (16 - map[i & 15])][i], dab-audio.cpp:113-143) from the ring into shared memory, still residue-major
 // (row r at word stride `sw`, odd so that the 16 rows start in different banks), and writes the fragment in natural order
 // (softbit i of the fragment sits at (i & 15) * 4 sw + (i >> 4) in shared memory) as one 4-byte store per thread and word.
@@ -69,35 +69,32 @@ __global__ void __launch_bounds__(128)
 msc_gather_kernel(MscPrepParams p)
 {
     extern __shared__ __align__(16) int8_t frag_s[];
-    const int s = blockIdx.x, t = threadIdx.x;          // one CTA per stream: its four CIFs one after the other (8192 fat CTAs instead of 32 768 thin ones)
+    const int s = blockIdx.x / 4, c = blockIdx.x % 4, t = threadIdx.x;
     if (p.active && !p.active[s]) return;
     const MscSlotState st = p.slots[s * p.n_slots + p.slot];
     if (!st.enabled) return;
-    const int frag = st.frag, per_w = frag / 64, sw = per_w | 1, sb = 4 * sw;
+    const int64_t n = st.cif_count + c;           // index (since selection) of the CIF being completed
+    if (n < 16) return;                           // de-interleaver not yet filled (dab-audio.cpp:146-149)
+    const int frag = st.frag, per_w = frag / 64, sw = per_w | 1;
     const int8_t* ring = p.ring + (int64_t)s * MSC_RING * p.ring_pitch;
     uint32_t* frag_w = reinterpret_cast<uint32_t*>(frag_s);
-    const uint8_t* fs = reinterpret_cast<const uint8_t*>(frag_s);
-    for (int c = 0; c < 4; c++) {
-        const int64_t n = st.cif_count + c;           // index (since selection) of the CIF being completed
-        if (n < 16) continue;                         // de-interleaver not yet filled (dab-audio.cpp:146-149); CTA-uniform
-        const int nm = (int)(n % MSC_RING);           // one 64-bit modulo; the 16 slices follow with 32-bit arithmetic
-        __syncthreads();                              // the previous CIF's fragment has been written out
+    const int nm = (int)(n % MSC_RING);           // one 64-bit modulo; the 16 slices follow with 32-bit arithmetic
 #pragma unroll 4
-        for (int r = 0; r < 16; r++) {
-            int slice = nm - c_deint_delay[r];        // delay <= 16 < MSC_RING
-            if (slice < 0) slice += MSC_RING;
-            const uint32_t* srow = reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w;
-            for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
-        }
-        __syncthreads();
-        const int cw = s * 4 + c;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(p.frag_out + (int64_t)cw * p.frag_pitch);
-        for (int q = t; q < frag / 4; q += 128) {
-            const uint8_t* b = fs + (4 * (q & 3)) * sb + (q >> 2);      // bytes i = 4q .. 4q+3: residues 4 (q & 3) + k, column q >> 2
-            dst[q] = (uint32_t)b[0] | ((uint32_t)b[sb] << 8) | ((uint32_t)b[2 * sb] << 16) | ((uint32_t)b[3 * sb] << 24);
-        }
-        if (t == 0 && p.valid) p.valid[cw] = 1;
+    for (int r = 0; r < 16; r++) {
+        int slice = nm - c_deint_delay[r];        // delay <= 16 < MSC_RING
+        if (slice < 0) slice += MSC_RING;
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w;
+        for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
     }
+    __syncthreads();
+    const int cw = s * 4 + c, sb = 4 * sw;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.frag_out + (int64_t)cw * p.frag_pitch);
+    const uint8_t* fs = reinterpret_cast<const uint8_t*>(frag_s);
+    for (int q = t; q < frag / 4; q += 128) {
+        const uint8_t* b = fs + (4 * (q & 3)) * sb + (q >> 2);      // bytes i = 4q .. 4q+3: residues 4 (q & 3) + k, column q >> 2
+        dst[q] = (uint32_t)b[0] | ((uint32_t)b[sb] << 8) | ((uint32_t)b[2 * sb] << 16) | ((uint32_t)b[3 * sb] << 24);
+    }
+    if (t == 0 && p.valid) p.valid[cw] = 1;
 }
 
 // stage-level API helper: copy with -128 -> -127 (both are symbol 0 after the reference's clamp, viterbi.cpp:232-237), so that the
@@ -293,7 +290,7 @@ void launch_msc_gather(const MscPrepParams& p, int n_streams, cudaStream_t st)
 {
     const int smem = p.ring_pitch + 64;      // 16 residue rows, each padded to an odd word count
     if (smem > 48 * 1024) cudaFuncSetAttribute(msc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    msc_gather_kernel<<<n_streams, 128, smem, st>>>(p);
+    msc_gather_kernel<<<n_streams * 4, 128, smem, st>>>(p);
 }
 
 void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
@@ -302,6 +299,8 @@ void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
     const int blocks = (p.n_cw + VIT_THREADS - 1) / VIT_THREADS;
     if (stages == 1) {
         viterbi_kernel<1><<<blocks, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(p);
+    } else if (stages == 2) {
+        viterbi_kernel<2><<<blocks, VIT_THREADS, sizeof(VitSmemT<2>), st>>>(p);      // 39 KB: fits beside four 46 KB OFDM CTAs on an SM
     } else {
         cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemT<3>));
         viterbi_kernel<3><<<blocks, VIT_THREADS, sizeof(VitSmemT<3>), st>>>(p);
