@@ -1,8 +1,7 @@
 #!/bin/bash
 # quick GPU check: stage + pipeline + glue parity tests, then the short variant bench of the default library and gpurun_exp_*.so
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_stages.py tests/test_gpu_pipeline.py tests/test_gpu_glue.py tests/test_gpu_fullsize.py -m gpu -q -s 2>&1 | tail -25 > gpurun_out/pytest_quick.log
-tail -3 gpurun_out/pytest_quick.log
+if [ -z "${SKIP_TESTS:-}" ]; then python -m pytest tests/test_gpu_stages.py tests/test_gpu_pipeline.py tests/test_gpu_glue.py tests/test_gpu_fullsize.py -m gpu -q -s 2>&1 | tail -25 > gpurun_out/pytest_quick.log; tail -3 gpurun_out/pytest_quick.log; fi
 one() {
     python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 10 > gpurun_out/bench_var_$1.json 2> gpurun_out/bench_var_$1.err
     python - "$1" <<'PY'
@@ -19,5 +18,5 @@ PY
 }
 unset DABB_LIB
 one default
-DABB_CORESIDENT=1 one coresident
+DABB_CORESIDENT=1 DABB_CORESIDENT_SERIAL=1 one coresident_serial
 for lib in $(ls gpurun_exp_*.so 2>/dev/null); do export DABB_LIB=$PWD/$lib; one "$lib"; done
