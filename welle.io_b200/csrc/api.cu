@@ -53,7 +53,7 @@ struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
-    int decode_tii = 0; float2* d_tii = nullptr; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
+    int decode_tii = 0; float2* d_tii = nullptr; TraceBuf trace{nullptr, nullptr, 0}; std::string trace_path; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0; int osc_mismatches = -1; int osc_patched = 0; std::vector<float2> h_osc;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
@@ -531,6 +531,10 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_fic_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice);
     }
+    if (getenv("DABB_TRACE")) {
+        ctx->trace_path = getenv("DABB_TRACE"); ctx->trace.cap = 1u << 20;
+        if ((rc = dalloc(ctx, &ctx->trace.rec, (size_t)3 * ctx->trace.cap)) || (rc = dalloc(ctx, &ctx->trace.count, 1))) return fail(rc);
+    }
     ctx->ring_pitch = ctx->max_cu * 64;
     if ((rc = dalloc(ctx, &ctx->d_state, S)) || (rc = dalloc(ctx, &ctx->d_scr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fic_ratio, S)) || (rc = dalloc(ctx, &ctx->d_coarse, S)) || (rc = dalloc(ctx, &ctx->d_slots, (size_t)S * ctx->n_slots)) ||
         (rc = dalloc(ctx, &ctx->d_buf_start, S)) || (rc = dalloc(ctx, &ctx->d_win, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_prs, 2 * (size_t)S)) ||
@@ -561,6 +565,13 @@ void dabb_destroy(dabb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
+    if (ctx->trace.rec && !ctx->trace_path.empty()) {       // CTA timeline: kind, sm, start ns, end ns per line
+        unsigned int n = 0; cudaMemcpy(&n, ctx->trace.count, 4, cudaMemcpyDeviceToHost);
+        if (n > ctx->trace.cap) n = ctx->trace.cap;
+        std::vector<unsigned long long> h((size_t)3 * n);
+        cudaMemcpy(h.data(), ctx->trace.rec, h.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(ctx->trace_path.c_str(), "w")) { for (unsigned int i = 0; i < n; i++) fprintf(f, "%llu %llu %llu %llu\n", h[3 * i] >> 32, h[3 * i] & 0xFFFFFFFFull, h[3 * i + 1], h[3 * i + 2]); fclose(f); }
+    }
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->d_iq_stage) cudaFree(ctx->d_iq_stage);
@@ -685,6 +696,7 @@ static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const
     vp.frag = soft; vp.cw_div = 4; vp.outer_stride = soft_stride; vp.inner_stride = 2304; vp.steptab = ctx->d_fic_steptab; vp.stage_off = ctx->d_fic_stage_off;
     vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
     vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
+    vp.trace = ctx->trace; vp.trace_kind = 2;
     launch_viterbi(vp, st, ctx->vit_stages_now);
     if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
     launch_fic_crc(fibs, active, n_frames, crc, st);
@@ -780,6 +792,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.level = d_lvl; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
+    op.trace = ctx->trace;
     op.n_full = S - ctx->tail_frames; op.tail_groups = ctx->tail_frames ? ctx->tail_groups : 1; op.fc_pitch = ctx->fc_pitch; op.nco_fast = ctx->nco_fast;
     // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
     op.smem_floor = (serial && !getenv("DABB_CORESIDENT_SERIAL")) ? 0 : ctx->ofdm_smem_floor;     // DABB_CORESIDENT_SERIAL: time the capped kernel alone
@@ -820,6 +833,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
         ViterbiParams vp{}; vp.frag = sl.d_frag; vp.cw_div = 1; vp.outer_stride = sl.frag_pitch; vp.inner_stride = 0; vp.steptab = sl.d_steptab; vp.stage_off = sl.d_stage_off;
         vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
+        vp.trace = ctx->trace; vp.trace_kind = 3;
         launch_viterbi(vp, B, ctx->vit_stages_now);
         if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
         SuperframeParams fp{}; fp.active = d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;

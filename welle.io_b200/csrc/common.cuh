@@ -26,6 +26,19 @@ struct DevTables {
     const uint8_t* gf_log;     // [256]
 };
 
+// ---- optional CTA timeline (environment DABB_TRACE=<file>): every CTA of the two hot kernels records {kind, SM, start, end} (global
+// nanosecond timer) so that the overlap of the two lanes can be drawn; off (nullptr) in normal operation
+struct TraceBuf { unsigned long long* rec; unsigned int* count; unsigned int cap; };
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int trace_smid() { unsigned int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+__device__ __forceinline__ void trace_put(const TraceBuf& tb, unsigned int kind, unsigned long long t0)
+{
+    const unsigned int i = atomicAdd(tb.count, 1u);
+    if (i < tb.cap) { tb.rec[3 * i] = ((unsigned long long)kind << 32) | trace_smid(); tb.rec[3 * i + 1] = t0; tb.rec[3 * i + 2] = trace_now(); }
+}
+#endif
+
 // ---- OFDM demod launch parameters ----
 struct OfdmParams {
     const float2* iq; int64_t stride;            // complex samples
@@ -41,6 +54,7 @@ struct OfdmParams {
     int n_full; int tail_groups;                 // frames >= n_full are cut into tail_groups CTAs each (tail_groups divides 75; 1 / 0 = off)
     int fc_pitch;                                // freqcorr entries per frame (>= groups, tail_groups); 0 -> the larger of the two
     int nco_fast;                                // DABB_NCO_FAST: fp32 oscillator (tolerance mode)
+    TraceBuf trace;                              // rec == nullptr: off
     int smem_floor;                              // request at least this much dynamic shared memory (caps CTAs/SM so that other kernels fit beside it)
 };
 

@@ -332,6 +332,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     if ((int)blockIdx.x < p.n_full * p.groups) { f = blockIdx.x / p.groups; g = blockIdx.x % p.groups; spc = p.sym_per_cta; ng = p.groups; }
     else { const int r = blockIdx.x - p.n_full * p.groups; f = p.n_full + r / p.tail_groups; g = r % p.tail_groups; spc = 75 / p.tail_groups; ng = p.tail_groups; }
     if (p.active && !p.active[f]) return;
+    const unsigned long long trace_t0 = p.trace.rec ? trace_now() : 0ull;
 
     const float2* src = p.iq + (int64_t)f * p.stride + p.prs_start[f];
     const int l_first = 1 + g * spc, l_last = l_first + spc;   // data symbols [l_first, l_last)
@@ -485,6 +486,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         if (t == 0) p.level[(int64_t)f * p.fc_pitch + g] = s * (1.0f / 128.0f) * powf(LEVEL_DECAY_SYM, (float)(76 - l_last));
         if (g == 0 && t > 0 && t < p.fc_pitch - ng + 1) p.level[(int64_t)f * p.fc_pitch + ng - 1 + t] = 0.f;
     }
+    if (p.trace.rec && t == 0) trace_put(p.trace, 1u, trace_t0);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -142,6 +142,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
     extern __shared__ __align__(16) unsigned char smraw[];
     VitSmemT<VIT_STAGES>& sm = *reinterpret_cast<VitSmemT<VIT_STAGES>*>(smraw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long trace_t0 = p.trace.rec ? trace_now() : 0ull;
     const int cw = block * VIT_THREADS + t;
     const bool have = cw < p.n_cw;
     const int groups = p.nsteps / 6;                 // 6 steps per group, 4 groups per stage
@@ -209,6 +210,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
         issue(s + VIT_STAGES, buf);
     }
     cp_async_wait<0>();
+    if (p.trace.rec && t == 0) trace_put(p.trace, p.trace_kind, trace_t0);       // forward pass of thread 0 done
     if (!have) return;
     if (p.valid && !p.valid[cw]) return;
     // traceback (vit_traceback24): 96 steps (nbits is a multiple of 96) give three output words; the decision words are read in
@@ -234,6 +236,7 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
             out[wi] = prbs ? v ^ prbs[wi] : v;
         }
     }
+    if (p.trace.rec && t == 0) trace_put(p.trace, p.trace_kind + 10u, trace_t0);  // ... and its traceback
 }
 
 template <int VIT_STAGES>
