@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+one() {
+    python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 10 > gpurun_out/bench_var_$1.json 2> gpurun_out/bench_var_$1.err
+    python - "$1" <<'PY'
+import json, sys
+lib = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/bench_var_{lib}.json").read().strip().splitlines()[-1]); k = d["kernels"]
+    print(lib, "|", round(d["value"]), "frames/s", round(d["ms_per_step"], 3), "ms/step | ofdm", round(d["roofline"]["ms_per_launch"], 4), "| viterbi FIC", round(k["viterbi_kernel(FIC)"]["ms_per_step"], 3), "MSC", round(k["viterbi_kernel(MSC)"]["ms_per_step"], 3), flush=True)
+except Exception as e:
+    print(lib, "| bench failed:", e, flush=True)
+PY
+}
+one stages2
+DABB_VIT_STAGES=3 one stages3
+DABB_CORESIDENT=1 one floor45_stages2
+DABB_TRACE=$PWD/gpurun_out/trace_s2.txt python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 4 > /dev/null 2>&1

@@ -469,7 +469,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         // co-residency experiment: 46 KB per OFDM CTA -> four of them per SM (49 152 registers, 188 KB), leaving exactly the 16 384 registers
         // and 40 KB one two-stage Viterbi CTA needs, so that the integer ACS work runs in the issue slots the shared-memory-bound OFDM
         // kernel leaves free instead of taking turns with it
-        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 46 * 1024 : 0;
+        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 45 * 1024 : 0;
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
@@ -765,7 +765,12 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     // serially on the main stream.
     const int par = (int)(ctx->step & 1);
     const bool serial = ctx->prof;
-    ctx->vit_stages_now = (serial || !ctx->ofdm_smem_floor) ? 3 : 2;
+    // Two staging buffers (39 KB per CTA), not three: a Viterbi CTA then fits into what ONE retiring OFDM CTA frees on an SM (12 288
+    // registers + the 4 096 spare = its 16 384; 43 KB + the 13 KB spare >= its 40 KB).  Lane B has the higher stream priority, so it takes
+    // that slot - and no second one on the same SM (only 12 288 registers come free next time): every SM settles at four OFDM CTAs and
+    // one Viterbi CTA, and the integer ACS work runs in the issue slots the shared-memory-bound OFDM kernel leaves idle.  With three
+    // buffers (57.6 KB) the CTA did not fit and lane B waited for the OFDM launch to drain (DABB_TRACE timeline).
+    ctx->vit_stages_now = getenv("DABB_VIT_STAGES") ? atoi(getenv("DABB_VIT_STAGES")) : 2;
     cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
     StepScratch* scr = ctx->d_scr + (size_t)par * S;
     int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
