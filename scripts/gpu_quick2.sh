@@ -12,7 +12,6 @@ except Exception as e:
     print(lib, "| bench failed:", e, flush=True)
 PY
 }
-one stages2
-DABB_VIT_STAGES=3 one stages3
-DABB_CORESIDENT=1 one floor45_stages2
-DABB_TRACE=$PWD/gpurun_out/trace_s2.txt python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 4 > /dev/null 2>&1
+one burst
+DABB_LANES=partition one partition
+DABB_LANES=partition DABB_TRACE=$PWD/gpurun_out/trace_part.txt python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 4 > /dev/null 2>&1

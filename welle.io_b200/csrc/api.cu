@@ -460,20 +460,29 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     ctx->nco_fast = cfg->nco_mode == DABB_NCO_FAST;
     auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+    // Stream priorities and the SM partition (DABB_TRACE timelines).  Lane A (time sync + OFDM of frame n+1) and lane B
+    // (FIC / MSC Viterbi + RS of frame n) become runnable at the same moment.  DABB_LANES=partition: lane A gets the HIGHER priority, so the
+    // next OFDM launch starts at once, and the OFDM kernel asks for 45 KB of shared memory per CTA, so only four of its CTAs fit on an SM:
+    // what stays free - 16 384 registers, 48 KB - is exactly one two-buffer Viterbi CTA, a slot no OFDM CTA can take.  Lane B then runs
+    // inside the OFDM launch, in the issue slots the shared-memory-bound OFDM kernel leaves idle, instead of before it.
+    // DABB_LANES=burst (round-1 behaviour): lane B higher, no cap - lane B runs first and squeezes the time-sync kernels of lane A.
+    const char* lanes_env = getenv("DABB_LANES");
+    const bool partition = lanes_env ? !strcmp(lanes_env, "partition") : false;
+    int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, partition ? prio_hi : prio_lo) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
     if (ofdm_init_constants() != 0) { ctx->err = "cudaMemcpyToSymbol(ofdm constants) failed"; return fail(DABB_E_CUDA); }
     // lane B (FIC/MSC/RS of frame n) runs on its own stream so that it overlaps lane A (time sync + OFDM of frame n+1)
     {
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lane B gets the higher priority: its CTAs take the SM resources lane A leaves free
-        if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+        if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, partition ? lo : hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
         // co-residency experiment: 46 KB per OFDM CTA -> four of them per SM (49 152 registers, 188 KB), leaving exactly the 16 384 registers
         // and 40 KB one two-stage Viterbi CTA needs, so that the integer ACS work runs in the issue slots the shared-memory-bound OFDM
         // kernel leaves free instead of taking turns with it
-        ctx->ofdm_smem_floor = getenv("DABB_CORESIDENT") ? 45 * 1024 : 0;
+        ctx->ofdm_smem_floor = (getenv("DABB_CORESIDENT") || partition) ? 45 * 1024 : 0;
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
-    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); } }
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, partition ? lo : hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); } }
     if ( cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream/event creation failed"; return fail(DABB_E_CUDA); }
     ctx->host = new HostTables();
