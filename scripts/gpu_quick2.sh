@@ -12,6 +12,7 @@ except Exception as e:
     print(lib, "| bench failed:", e, flush=True)
 PY
 }
+DABB_LANES=partition python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_fullsize.py -m gpu -q 2>&1 | tail -3
 one burst
 DABB_LANES=partition one partition
 DABB_LANES=partition DABB_TRACE=$PWD/gpurun_out/trace_part.txt python bench.py --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 --steps 4 > /dev/null 2>&1

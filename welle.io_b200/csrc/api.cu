@@ -53,7 +53,7 @@ struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
-    int decode_tii = 0; float2* d_tii = nullptr; TraceBuf trace{nullptr, nullptr, 0}; std::string trace_path; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
+    int decode_tii = 0; float2* d_tii = nullptr; bool persistent = false; unsigned int* d_work = nullptr; TraceBuf trace{nullptr, nullptr, 0}; std::string trace_path; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0; int osc_mismatches = -1; int osc_patched = 0; std::vector<float2> h_osc;
     HostTables* host = nullptr; DevTables dev{};
     std::vector<void*> allocs;
@@ -479,6 +479,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         // and 40 KB one two-stage Viterbi CTA needs, so that the integer ACS work runs in the issue slots the shared-memory-bound OFDM
         // kernel leaves free instead of taking turns with it
         ctx->ofdm_smem_floor = (getenv("DABB_CORESIDENT") || partition) ? 45 * 1024 : 0;
+        ctx->persistent = partition;
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
@@ -807,6 +808,11 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.level = d_lvl; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
     op.trace = ctx->trace;
+    if (ctx->persistent && !serial) {
+        if (!ctx->d_work && (rc = dalloc(ctx, &ctx->d_work, 1))) return rc;
+        CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), A));
+        op.work = ctx->d_work;
+    }
     op.n_full = S - ctx->tail_frames; op.tail_groups = ctx->tail_frames ? ctx->tail_groups : 1; op.fc_pitch = ctx->fc_pitch; op.nco_fast = ctx->nco_fast;
     // pipelined mode: 50 KB per CTA -> four OFDM CTAs per SM, leaving registers and 23 KB of shared memory for one lane-B CTA
     op.smem_floor = (serial && !getenv("DABB_CORESIDENT_SERIAL")) ? 0 : ctx->ofdm_smem_floor;     // DABB_CORESIDENT_SERIAL: time the capped kernel alone

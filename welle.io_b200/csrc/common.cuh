@@ -55,6 +55,7 @@ struct OfdmParams {
     int fc_pitch;                                // freqcorr entries per frame (>= groups, tail_groups); 0 -> the larger of the two
     int nco_fast;                                // DABB_NCO_FAST: fp32 oscillator (tolerance mode)
     TraceBuf trace;                              // rec == nullptr: off
+    unsigned int* work;                          // persistent launch: item counter (zeroed by the caller before the launch); nullptr: one CTA per item
     int smem_floor;                              // request at least this much dynamic shared memory (caps CTAs/SM so that other kernels fit beside it)
 };
 

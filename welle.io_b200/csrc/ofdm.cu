@@ -199,6 +199,7 @@ struct __align__(16) DemodSmem {
     float2 tw[TwLayout::C4];         // 1 KB: twiddles of passes A and B (pass C reads its 15 KB through L1 with __ldg)
     uint16_t sbuf[1536 + 128];        // (re | im << 8) per logical carrier: one 16-bit scatter store per carrier
 #endif
+    int item;                        // persistent launch: the work item all threads of the CTA process next
     float2 rtab[2][16];              // DABB_NCO_FAST: e^{-j theta((128 h + 256 c) Hz)} for the PRS / the data symbols
     float red[16];
     uint64_t full;
@@ -326,11 +327,42 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     extern __shared__ __align__(16) unsigned char smraw[];
     DemodSmem& sm = *reinterpret_cast<DemodSmem*>(smraw);
     const int t = threadIdx.x;
-    // the first n_full frames are walked by `groups` CTAs each; the remaining (tail) frames are cut into tail_groups short CTAs, which
-    // are dispatched last and fill the SM slots the long CTAs free one by one at the end of the launch
+    // ---- once per CTA
+    if (t == 0) { mbar_init(&sm.full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#if DEMOD_SLIM
+    uint16_t* const sbuf = reinterpret_cast<uint16_t*>(sm.xbuf);
+#else
+    if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
+    uint16_t* const sbuf = sm.sbuf;
+#endif
+    const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
+    const XIdx xi = make_xidx(t);
+    const TwB2 b2 = load_twb2(tb.tw_fwd, xi.kk);
+    // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
+    int sidx[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
+    uint32_t parity = 0;
+    const int n_items = p.n_full * p.groups + (p.n_frames - p.n_full) * p.tail_groups;
+    __syncthreads();
+
+    // Work items: the first n_full frames are walked by `groups` items each; the remaining (tail) frames are cut into tail_groups short
+    // items, which come last and fill the slots the long ones free one by one at the end of the launch.  Classic launch (p.work ==
+    // nullptr): one CTA per item.  Persistent launch: a fixed set of CTAs (as many as are resident at once) pulls items from a counter -
+    // a grid with no undispatched CTAs, so that the block scheduler hands the SM resources this kernel cannot use (the slot its
+    // shared-memory request leaves free) to the other lane's kernels while it runs.
+    for (int item = p.work ? -1 : (int)blockIdx.x; ; ) {
+        if (p.work) {
+            __syncthreads();                                  // the previous item is finished by every thread (inbuf, xbuf, red reusable)
+            if (t == 0) sm.item = (int)atomicAdd(p.work, 1u);
+            __syncthreads();
+            item = sm.item;
+        }
+        if (item >= n_items) break;
+        [&]() {
     int f, g, spc, ng;
-    if ((int)blockIdx.x < p.n_full * p.groups) { f = blockIdx.x / p.groups; g = blockIdx.x % p.groups; spc = p.sym_per_cta; ng = p.groups; }
-    else { const int r = blockIdx.x - p.n_full * p.groups; f = p.n_full + r / p.tail_groups; g = r % p.tail_groups; spc = 75 / p.tail_groups; ng = p.tail_groups; }
+    if (item < p.n_full * p.groups) { f = item / p.groups; g = item % p.groups; spc = p.sym_per_cta; ng = p.groups; }
+    else { const int r = item - p.n_full * p.groups; f = p.n_full + r / p.tail_groups; g = r % p.tail_groups; spc = 75 / p.tail_groups; ng = p.tail_groups; }
     if (p.active && !p.active[f]) return;
     const unsigned long long trace_t0 = p.trace.rec ? trace_now() : 0ull;
 
@@ -348,17 +380,8 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         mbar_expect_tx(&sm.full, bytes);
         bulk_g2s(sm.inbuf, g0 - shift, bytes, &sm.full);
     };
-    if (t == 0) { mbar_init(&sm.full, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
     if (t == 0) issue(l_first - 1);
 
-#if DEMOD_SLIM
-    uint16_t* const sbuf = reinterpret_cast<uint16_t*>(sm.xbuf);
-#else
-    if (t < TwLayout::C4) sm.tw[t] = tb.tw_fwd[t];
-    uint16_t* const sbuf = sm.sbuf;
-#endif
-    const float2* tw_c5 = tb.tw_fwd + TwLayout::C5;
     // nco[f] = {phase applied to PRS sample 0, Hz for the PRS, phase at index 0 extrapolated for the data symbols, Hz}
     const Nco ncoP = make_nco(p.nco ? p.nco[4 * f] : 0, p.nco ? p.nco[4 * f + 1] : 0);
     const Nco ncoS = make_nco(p.nco ? p.nco[4 * f + 2] : 0, p.nco ? p.nco[4 * f + 3] : 0);
@@ -367,18 +390,11 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         const int k = t & 15;
         sm.rtab[t >> 4][k] = osc_fast(mod_rate64(-(int64_t)(128 * (k >> 3) + 256 * (k & 7)) * n.ph));
     }
-    const XIdx xi = make_xidx(t);
-    const TwB2 b2 = load_twb2(tb.tw_fwd, xi.kk);
-    // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
-    int sidx[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
-    __syncthreads();
+    if (FASTNCO) __syncthreads();
 
     float2 prev[NSLOT];
     float2 fc = make_float2(0.f, 0.f);
     float lvl = 0.f;                                  // decayed sum of one sample magnitude per symbol and thread (signal level estimate)
-    uint32_t parity = 0;
 
     for (int l = l_first - 1; l < l_last; l++) {
         const int64_t s0 = (l == 0) ? 0 : (int64_t)TU + (int64_t)(l - 1) * TS;
@@ -487,6 +503,9 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
         if (g == 0 && t > 0 && t < p.fc_pitch - ng + 1) p.level[(int64_t)f * p.fc_pitch + ng - 1 + t] = 0.f;
     }
     if (p.trace.rec && t == 0) trace_put(p.trace, 1u, trace_t0);
+        }();
+        if (!p.work) break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -865,8 +884,18 @@ void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p_in, int fft_mode
     if (p.tail_groups < 1 || 75 % p.tail_groups) { p.tail_groups = 1; }
     if (p.n_full < 0 || p.n_full > p.n_frames || p.tail_groups == 1) p.n_full = p.n_frames;
     if (p.fc_pitch < 1) p.fc_pitch = p.groups > p.tail_groups ? p.groups : p.tail_groups;
-    const dim3 grid(p.n_full * p.groups + (p.n_frames - p.n_full) * p.tail_groups), block(OFDM_THREADS);
     const size_t sm = sizeof(DemodSmem) > (size_t)p.smem_floor ? sizeof(DemodSmem) : (size_t)p.smem_floor;
+    int n_ctas = p.n_full * p.groups + (p.n_frames - p.n_full) * p.tail_groups;
+    if (p.work) {
+        // persistent: as many CTAs as are resident at once with this shared-memory request
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        set_smem(ofdm_demod_kernel<true, false, false>, sm);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ofdm_demod_kernel<true, false, false>, OFDM_THREADS, sm);
+        const int resident = sms * (per_sm > 0 ? per_sm : 1);
+        if (n_ctas > resident) n_ctas = resident;
+    }
+    const dim3 grid(n_ctas), block(OFDM_THREADS);
     const bool tap = p.r1 != nullptr, fast = p.nco_fast != 0 && p.nco != nullptr;
 #define LAUNCH(E, T, F) do { set_smem(ofdm_demod_kernel<E, T, F>, sm); ofdm_demod_kernel<E, T, F><<<grid, block, sm, st>>>(tb, p); } while (0)
 #define LAUNCH_F(E, T) do { if (fast) LAUNCH(E, T, true); else LAUNCH(E, T, false); } while (0)
