@@ -844,6 +844,9 @@ template <typename K> static void set_smem(K k, size_t bytes)
 {
     // every template instantiation is its own function: set the attribute per launch (it is a cheap host-side call)
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // always the largest shared-memory carve-out: with a smaller one (chosen by the driver from this kernel's own footprint) the CTAs of
+    // the other lane's kernels cannot be placed beside this kernel's on the same SM even when registers and bytes would allow it
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
 namespace {

@@ -300,6 +300,9 @@ void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
 {
     ViterbiParams p = p_in; p.one = 1u;
     const int blocks = (p.n_cw + VIT_THREADS - 1) / VIT_THREADS;
+    cudaFuncSetAttribute(viterbi_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(viterbi_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (stages == 1) {
         viterbi_kernel<1><<<blocks, VIT_THREADS, sizeof(VitSmemT<1>), st>>>(p);
     } else if (stages == 2) {
