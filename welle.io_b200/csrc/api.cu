@@ -460,12 +460,12 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     ctx->nco_fast = cfg->nco_mode == DABB_NCO_FAST;
     auto fail = [&](int code) { g_create_error = ctx->err; dabb_destroy(ctx); return code; };
     if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(DABB_E_CUDA); }
-    // Stream priorities and the SM partition (DABB_TRACE timelines).  Lane A (time sync + OFDM of frame n+1) and lane B
-    // (FIC / MSC Viterbi + RS of frame n) become runnable at the same moment.  DABB_LANES=partition: lane A gets the HIGHER priority, so the
-    // next OFDM launch starts at once, and the OFDM kernel asks for 45 KB of shared memory per CTA, so only four of its CTAs fit on an SM:
-    // what stays free - 16 384 registers, 48 KB - is exactly one two-buffer Viterbi CTA, a slot no OFDM CTA can take.  Lane B then runs
-    // inside the OFDM launch, in the issue slots the shared-memory-bound OFDM kernel leaves idle, instead of before it.
-    // DABB_LANES=burst (round-1 behaviour): lane B higher, no cap - lane B runs first and squeezes the time-sync kernels of lane A.
+    // Stream priorities.  Lane A (time sync + OFDM of frame n+1) and lane B (FIC / MSC Viterbi + RS of frame n) become runnable at the
+    // same moment; lane B gets the higher priority and runs first, in a burst (its CTAs take every slot the OFDM launch frees).
+    // DABB_LANES=partition is the measured alternative (CTA timelines with DABB_TRACE): lane A higher, the OFDM kernel
+    // persistent and capped at four CTAs per SM by a 45 KB shared-memory request, so that one two-buffer Viterbi CTA (16 384 registers,
+    // 40 KB) runs beside them for the whole launch.  The two kernels then do share every SM - and slow each other down by as much as
+    // they overlap (OFDM 3.2 -> 4.3 ms with the Viterbi CTAs beside it; step 4.94 vs 4.70 ms), so the burst order stays the default.
     const char* lanes_env = getenv("DABB_LANES");
     const bool partition = lanes_env ? !strcmp(lanes_env, "partition") : false;
     int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -775,12 +775,8 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     // serially on the main stream.
     const int par = (int)(ctx->step & 1);
     const bool serial = ctx->prof;
-    // Two staging buffers (39 KB per CTA), not three: a Viterbi CTA then fits into what ONE retiring OFDM CTA frees on an SM (12 288
-    // registers + the 4 096 spare = its 16 384; 43 KB + the 13 KB spare >= its 40 KB).  Lane B has the higher stream priority, so it takes
-    // that slot - and no second one on the same SM (only 12 288 registers come free next time): every SM settles at four OFDM CTAs and
-    // one Viterbi CTA, and the integer ACS work runs in the issue slots the shared-memory-bound OFDM kernel leaves idle.  With three
-    // buffers (57.6 KB) the CTA did not fit and lane B waited for the OFDM launch to drain (DABB_TRACE timeline).
-    ctx->vit_stages_now = getenv("DABB_VIT_STAGES") ? atoi(getenv("DABB_VIT_STAGES")) : 2;
+    // three staging buffers by default; DABB_LANES=partition uses two (39 KB) so that one Viterbi CTA fits beside four OFDM CTAs
+    ctx->vit_stages_now = getenv("DABB_VIT_STAGES") ? atoi(getenv("DABB_VIT_STAGES")) : (ctx->persistent && !serial ? 2 : 3);
     cudaStream_t A = ctx->stream, B = serial ? ctx->stream : ctx->streamB;
     StepScratch* scr = ctx->d_scr + (size_t)par * S;
     int64_t* d_win = ctx->d_win + (size_t)par * S; int64_t* d_prs = ctx->d_prs + (size_t)par * S;
