@@ -424,8 +424,11 @@ def main():
     kms = prof["ofdm_demod_kernel"]["ms"] / prof["ofdm_demod_kernel"]["n"]
     ach = S * OFDM_BYTES_PER_FRAME / (kms * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_ofdm_traffic.json")
-    if os.path.exists(tp):
+    # DRAM bytes per frame of the kernel from the latest committed `ncu --set full` capture (profiles/rNN_ofdm_traffic.json)
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ofdm_traffic.json")))
+    tp = tps[-1] if tps else ""
+    if tp:
         try:
             per = json.load(open(tp)).get("dram_bytes_per_frame")
             traffic = per * S if per else None

@@ -51,12 +51,18 @@ def test_oscillator_on_the_fly_equals_table_for_every_index():
     assert patched.value == 3
 
 
-def test_decoder_kernel_emulation_depuncture_and_traceback(oracle):
+import pytest as _pytest
+
+
+@_pytest.mark.parametrize("variant", ["one_thread", "two_threads"])
+def test_decoder_kernel_emulation_depuncture_and_traceback(oracle, variant):
     """one thread of the decoder kernel (expansion tables from a de-puncturing map, 8-byte window expansion, packed ACS, 24-step
     traceback, MSB-first packing) on the CPU from the shared header code: FIC puncturing, EEP-A/B and UEP profiles, no puncturing -
     output bytes equal to oracle de-puncture + Viterbi + pack"""
-    so = os.path.join(HERE, "libemuld.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "emul_vitdec.cpp")])
+    # two_threads: the same decoder with one codeword on a pair of threads (viterbi_core2.cuh: 16 registers each, one exchange per six steps)
+    src, fn = ("emul_vitdec.cpp", "emul_vitdec") if variant == "one_thread" else ("emul_viterbi2.cpp", "emul_vitdec2")
+    so = os.path.join(HERE, f"libemuld_{variant}.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, src)])
     lib = C.CDLL(so)
     rng = np.random.default_rng(21)
     pc = oracle.pcodes()
@@ -93,5 +99,5 @@ def test_decoder_kernel_emulation_depuncture_and_traceback(oracle):
             raw[off:off + n_in] = frag
             raw[off + n_in:off + n_in + 160] = rng.integers(-127, 128, 160)          # whatever follows must not matter
             out = np.zeros(nbits // 8, np.uint8)
-            rc = lib.emul_vitdec(C.c_void_p(raw.ctypes.data + off), m.ctypes.data_as(C.c_void_p), nbits, None, out.ctypes.data_as(C.c_void_p))
+            rc = getattr(lib, fn)(C.c_void_p(raw.ctypes.data + off), m.ctypes.data_as(C.c_void_p), nbits, None, out.ctypes.data_as(C.c_void_p))
             assert rc == 0 and np.array_equal(out, exp), (name, trial, int((out != exp).sum()))
