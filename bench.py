@@ -78,6 +78,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+        self.ready = threading.Event()       # set once NVML is initialised (that can take longer than the whole timed region on a fresh box)
+        self.armed = False                   # samples count only while the timed region runs
 
     def run(self):
         try:
@@ -87,15 +89,18 @@ class ClockSampler(threading.Thread):
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
+                if self.armed:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
                 time.sleep(0.002)
         except Exception as e:  # noqa
             self.err = repr(e)
+            self.ready.set()
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
@@ -379,18 +384,20 @@ def main():
     ctx.sync()
     log("warm-up done")
     sampler = ClockSampler(local); sampler.start()
-    time.sleep(0.05)
+    sampler.ready.wait(20.0)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.armed = True
     e0.record(ext)
     for _ in range(a.steps):
         ctx.process_async(buf.data_ptr(), BUF_LEN, buf_start_for(call), BUF_LEN); call += 1
     ctx.join_lanes()       # the FIC / MSC / RS lane of the last steps runs on other streams: the closing event waits for it
     e1.record(ext)
     torch.cuda.synchronize()
+    sampler.armed = False
     ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - l0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
