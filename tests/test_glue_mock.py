@@ -114,3 +114,30 @@ def test_stock_crawfile_drives_the_glue_with_mock_backend(oracle, tmp_path):
     assert m >= 288 * 20 and np.array_equal(msc[:m], o["msc"][:m])
     # getReceiverStats().timeLastFCT0Frame is served (set when the ensemble was cleared at restart / by FIG 0/0 with CIF count 0)
     assert 0.0 <= float(summary["fct0_age_s"]) < 120.0
+
+
+def test_service_selection_from_the_controller_thread_with_mock_backend(oracle, tmp_path):
+    """the glue's controller-thread path (playSingleProgramme / removeServiceToDecode from another thread while the worker decodes; every
+    dabb_* call serialised by the glue's context mutex) on the test double; the same flow runs on the GPU in tests/test_gpu_glue.py"""
+    exe = os.path.join(ROOT, "welle.io_b200", "glue_test")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "welle.io_b200", "host")])
+    mock = tmp_path / "libdab_b200.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(mock), os.path.join(ROOT, "tests", "mock_backend", "mock_dab_b200.c"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    iq = dabtx.DabTx(seed=0x2A9).frames(44)
+    f = tmp_path / "in.cf32"; iq.tofile(f)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(tmp_path), DABB_MOCK_IQ=str(f))
+    out = subprocess.run([exe, str(f), str(tmp_path / "o"), "12", "1", "0", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    summary = dict(kv.split("=") for kv in out.stdout.split())
+    assert int(summary["zaps"]) >= 2 and summary["selected"] == "1", summary
+    fibs = np.fromfile(tmp_path / "o.fibs", np.uint8).reshape(-1, 33)
+    msc = np.fromfile(tmp_path / "o.msc", np.uint8)
+    o = oracle.rx_run(iq, prot=oracle.prot_eep(96, 1, 3), start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    n = min(len(fibs), len(o["fibs"]))
+    assert n >= 12 * 40 and np.array_equal(fibs[:n], o["fibs"][:n])
+    ref = o["msc"].tobytes()
+    assert len(msc) >= 288 * 8
+    at = ref.find(msc[:288 * 2].tobytes())
+    m = min(len(msc), len(ref) - at)
+    assert at >= 0 and at % 288 == 0 and m >= 288 * 8 and msc[:m].tobytes() == ref[at:at + m]

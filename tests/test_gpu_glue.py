@@ -161,3 +161,33 @@ def test_tii_spectra_tap_and_glue_measurements(oracle, ref, tmp_path):
     want = ref.tii_run(nulls, prss)
     print(f"TII through the glue: {nfr} frames, measurements {got}")
     assert len(want) >= 2 and got == want, (got, want)
+
+
+def test_service_selection_from_the_controller_thread(oracle, tmp_path):
+    """playSingleProgramme / removeServiceToDecode called from the controller thread while the worker thread is
+    inside dabb_process.  glue_test's controller mode selects, removes and re-selects the service four times a few milliseconds apart
+    during decoding; every dabb_* call of the glue is serialised by its context mutex.  The run must stay error-free, every FIB must
+    equal the oracle's, and the .msc dump written after the last selection must be a contiguous run of the oracle's logical frames."""
+    exe = os.path.join(ROOT, "welle.io_b200", "glue_test")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "welle.io_b200", "host")])
+    tx = dabtx.DabTx(seed=0x2A9)
+    iq = tx.frames(90)
+    f = tmp_path / "in.cf32"; iq.tofile(f)
+    out = subprocess.run([exe, str(f), str(tmp_path / "o"), "12", "1", "0", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "CUDA" not in out.stderr and "msg:" not in out.stderr, out.stderr
+    summary = dict(kv.split("=") for kv in out.stdout.split())
+    assert summary["zaps"] == "4" and summary["selected"] == "1", summary
+    fibs = np.fromfile(tmp_path / "o.fibs", np.uint8).reshape(-1, 33)
+    msc = np.fromfile(tmp_path / "o.msc", np.uint8)
+    o = oracle.rx_run(iq, prot=oracle.prot_eep(96, 1, 3), start_cu=0, len_cu=72, select_after_frames=1, disable_coarse=True)
+    n = min(len(fibs), len(o["fibs"]))
+    assert n >= 12 * 85 and np.array_equal(fibs[:n], o["fibs"][:n]) and fibs[:n, 0].all()
+    # the dump restarts at every selection; what it holds afterwards is the oracle's stream from some logical frame on
+    assert len(msc) >= 288 * 4 * 20, (len(msc), summary)
+    ref = o["msc"].tobytes()
+    at = ref.find(msc[:288 * 2].tobytes())
+    assert at >= 0 and at % 288 == 0
+    m = min(len(msc), len(ref) - at)
+    assert m >= 288 * 4 * 20 and msc[:m].tobytes() == ref[at:at + m]
+    print(f"controller-thread selection: {summary['zaps']} selections, dump = oracle logical frames {at // 288} .. {(at + m) // 288}")

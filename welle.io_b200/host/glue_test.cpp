@@ -1,6 +1,8 @@
 // glue_test — drives the host glue (RadioReceiver over libdab_b200.so) the way the reference's harnesses do
 // (src/tests/backend_tests.cpp:103-155, welle-cli -D): file-backed InputInterface, FIB + .msc dumps, RS statistics.
-//   glue_test <in.cf32> <out-prefix> [select_at_fib=12]
+//   glue_test <in.cf32> <out-prefix> [select_at_fib=12] [disable_coarse=1] [decode_tii=0] [controller_thread=0]
+// controller_thread=1: the service is selected, removed and selected again from the main thread while the receiver's worker thread
+// is decoding (what a GUI does; RadioReceiver serialises the calls into the context), instead of from the FIB callback
 #include "radio-receiver.h"
 #include <atomic>
 #include <cstdio>
@@ -33,12 +35,12 @@ struct Ctl : RadioControllerInterface {
     void onFIBDecodeSuccess(bool o, const uint8_t* fib) override {
         uint8_t rec[33]; rec[0] = o; for (int i = 0; i < 32; i++) { uint8_t b = 0; for (int j = 0; j < 8; j++) b = (b << 1) | (fib[8 * i + j] & 1); rec[1 + i] = b; }
         fwrite(rec, 33, 1, fibs); nfib++; ok += o;
-        if (!sel && nfib >= select_at) { auto l = rx->getServiceList(); if (!l.empty()) { sel = true; selok = rx->playSingleProgramme(*ph, dump, l.front()); } }
+        if (!from_controller && !sel && nfib >= select_at) { auto l = rx->getServiceList(); if (!l.empty()) { sel = true; selok = rx->playSingleProgramme(*ph, dump, l.front()); } }
     }
     void onNewImpulseResponse(std::vector<float>&& v) override { cirs++; tapsz_ok &= v.size() == 2048; }
     void onConstellationPoints(std::vector<DSPCOMPLEX>&& v) override { consts++; tapsz_ok &= v.size() == 1200; }   /* (L-1) K / 96 */
     void onNewNullSymbol(std::vector<DSPCOMPLEX>&& v) override { nulls++; tapsz_ok &= v.size() == 2656; }
-    FILE* tii = nullptr; int tiis = 0;
+    FILE* tii = nullptr; int tiis = 0; bool from_controller = false; std::atomic<int> zaps{0};
     void onTIIMeasurement(tii_measurement_t&& m) override { tiis++; if (tii) fprintf(tii, "%d %d %d %.1f\n", m.comb, m.pattern, m.delay_samples, m.error); } void onMessage(message_level_t, const std::string& a, const std::string& b) override { fprintf(stderr, "msg: %s %s\n", a.c_str(), b.c_str()); }
     void onInputFailure() override { failed = true; }
 };
@@ -51,18 +53,32 @@ int main(int argc, char** argv)
     RadioReceiverOptions rro; rro.disableCoarseCorrector = argc > 4 ? atoi(argv[4]) != 0 : true;    /* default like the parity harness (welle-cli -u) */
     rro.decodeTII = argc > 5 && atoi(argv[5]) != 0;                                                /* welle-cli -T */
     if (rro.decodeTII) ri.tii = fopen((pre + ".tii").c_str(), "w");
+    ri.from_controller = argc > 6 && atoi(argv[6]) != 0;
     double secs = 0;
     {
         RadioReceiver rx(ri, in, rro);
         ri.rx = &rx;
         const auto t0 = std::chrono::steady_clock::now();
         rx.restart(false);
+        if (ri.from_controller) {
+            /* select - remove - select ... from this thread, a few milliseconds apart, while the worker decodes */
+            while (!ri.failed.load() && rx.getServiceList().empty()) std::this_thread::sleep_for(std::chrono::microseconds(200));
+            for (int z = 0; z < 4 && !ri.failed.load(); z++) {
+                auto l = rx.getServiceList();
+                if (l.empty()) break;
+                ri.selok = rx.playSingleProgramme(ph, ri.dump, l.front()); ri.sel = true; ri.zaps++;
+                if (z == 3) break;
+                std::this_thread::sleep_for(std::chrono::milliseconds(4));
+                rx.removeServiceToDecode(l.front());
+                std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            }
+        }
         while (!ri.failed.load()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
         secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();      /* restart .. input exhausted */
         rx.stop();
     }
     fclose(ri.fibs); fclose(ph.rs); if (ri.tii) fclose(ri.tii);
-    printf("tii=%d ", ri.tiis);
+    printf("tii=%d zaps=%d ", ri.tiis, ri.zaps.load());
     printf("fibs=%d ok=%d services=%d selected=%d logical_frames=%d superframes=%d syncs=%d cirs=%d consts=%d nulls=%d tapsizes=%d seconds=%.4f\n", ri.nfib, ri.ok, ri.services, ri.selok ? 1 : 0, ph.frames, ph.sfs, ri.syncs,
            ri.cirs, ri.consts, ri.nulls, (int)ri.tapsz_ok, secs);
     return 0;
