@@ -576,7 +576,11 @@ def main():
                 pass
             return 64 << 30
         Se = min(a.e2e_batch, S) if a.e2e_batch > 0 else S
+        # pinned ring per rank: within the host's free memory, and at N > 1 within 160 GB over all ranks (page-locking tens of GB per rank
+        # on every rank at once takes minutes; the pipelined path is PCIe-bound from a few hundred frames per step on)
         budget = mem_available() * 0.55 / max(1, min(world, 8))
+        if world > 1:
+            budget = min(budget, 160e9 / world)
         while Se > 64 and Se * BUF_LEN * 8 > budget:
             Se //= 2
         # PCIe host->device peak of this box: 1 GiB pinned -> device, best of 5
