@@ -568,19 +568,28 @@ def main():
     e2e = None
     if not a.no_e2e:
         def mem_available():
+            """host bytes this process may still take: MemAvailable, further limited by the cgroup's memory limit (v2 or v1)"""
+            avail = 64 << 30
             try:
                 for ln in open("/proc/meminfo"):
                     if ln.startswith("MemAvailable"):
-                        return int(ln.split()[1]) * 1024
+                        avail = int(ln.split()[1]) * 1024
             except Exception:
                 pass
-            return 64 << 30
+            for lim_f, cur_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                                 ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+                try:
+                    lim = open(lim_f).read().strip()
+                    if lim != "max" and int(lim) < (1 << 60):
+                        avail = min(avail, int(lim) - int(open(cur_f).read().strip()))
+                except Exception:
+                    pass
+            return max(avail, 0)
         Se = min(a.e2e_batch, S) if a.e2e_batch > 0 else S
-        # pinned ring per rank: within the host's free memory, and at N > 1 within 160 GB over all ranks (page-locking tens of GB per rank
-        # on every rank at once takes minutes; the pipelined path is PCIe-bound from a few hundred frames per step on)
-        budget = mem_available() * 0.55 / max(1, min(world, 8))
-        if world > 1:
-            budget = min(budget, 160e9 / world)
+        # pinned ring per rank: within the host's free memory (cgroup limit included), and never more than 80 GB over all ranks of the
+        # box - the N = 1 run pins the headline batch (77.6 GB), N ranks share that (the pipelined path is PCIe-bound from a few hundred
+        # frames per step on, and page-locking tens of GB on every rank at once takes minutes)
+        budget = min(mem_available() * 0.45, 80e9) / max(1, min(world, 8))
         while Se > 64 and Se * BUF_LEN * 8 > budget:
             Se //= 2
         # PCIe host->device peak of this box: 1 GiB pinned -> device, best of 5
@@ -615,6 +624,13 @@ def main():
                     return host.data_ptr(), np.zeros(Se, np.int64), 3 * TF
                 off = (n % RING_FRAMES) * TF
                 return host.data_ptr() + off * bps, np.full(Se, n * TF, np.int64), min(WIN, BUF_LEN - off)
+
+            def carry_of(c):
+                # window c starts at (c + 1) TF; window c - 1 ended at its start + length: the overlap stays on the device (carry_samples)
+                if c == 0:
+                    return 0
+                _, pbs, pbl = args(c - 1)
+                return int(pbs[0] + pbl - (c + 1) * TF)
             ce = 0
             for _ in range(a.warmup):
                 ptr, bs, bl = args(ce)
@@ -622,10 +638,11 @@ def main():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            t0 = time.perf_counter(); h2d = 0; o = None
+            t0 = time.perf_counter(); h2d = 0; o = None; pipelined_started = False    # the warm-up used dabb_process: the first submit ships its whole window
             for k in range(a.steps):
-                ptr, bs, bl = args(ce); ce += 1; h2d += Se * bl * bps
-                ctx_e.submit(ptr, BUF_LEN, bs, bl, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=fmt, out=o if k >= 2 else None)   # result arrays recycled
+                ptr, bs, bl = args(ce); cy = carry_of(ce) if pipelined_started else 0; ce += 1; h2d += Se * (bl - cy) * bps
+                ctx_e.submit(ptr, BUF_LEN, bs, bl, msc_stride=3 * BITRATE, sf_stride=15 * BITRATE, iq_format=fmt, out=o if k >= 2 else None, carry=cy)   # result arrays recycled
+                pipelined_started = True
                 if k >= 1:
                     o = ctx_e.collect()
             o = ctx_e.collect()
@@ -645,14 +662,14 @@ def main():
             e_cf = run_e2e("cf32")
             e2e = dict(e_cf)
             e2e["note"] = ("host pinned cf32 -> dabb_submit/dabb_collect, two steps in flight (H2D of step n+1 overlaps the kernels of step n and the result "
-                           "read-back of step n-1); bound by the PCIe link: 1.64 MB of samples per frame")
+                           "read-back of step n-1; every sample crosses the link once: the 8192-sample window overlap is carried on the device); bound by the PCIe link: 1.57 MB of samples per frame")
             e2e["pcie_h2d_peak_gbs"] = best
             e2e["cf32_input"] = e_cf
         except Exception as e:  # noqa
             e2e = {"error": repr(e)}
         try:
             e2e["u8_input"] = run_e2e("u8")
-            e2e["u8_input"]["note"] = "RAW u8 IQ (CRAWFile .u8.iq, the RTL-SDR format) shipped as bytes and converted on the device (SURVEY 8(f) rank 2): 0.41 MB per frame"
+            e2e["u8_input"]["note"] = "RAW u8 IQ (CRAWFile .u8.iq, the RTL-SDR format) shipped as bytes and converted on the device (SURVEY 8(f) rank 2): 0.39 MB per frame"
         except Exception as e:  # noqa
             e2e["u8_input"] = {"error": repr(e)}
 

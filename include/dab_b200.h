@@ -164,7 +164,10 @@ typedef struct {
     dabb_frame_result* results; uint8_t* fibs; uint8_t* msc; int32_t msc_stride; uint8_t* sf; int32_t sf_stride;
     int32_t iq_format;   /* DABB_IQ_*: raw sample format of `iq` (strides and lengths stay in complex samples); converted on the
                             device exactly like CRAWFile::convertSamples (input/raw_file.cpp:324-366) */
-    int32_t reserved;
+    int32_t carry_samples;   /* dabb_submit only: the first `carry_samples` complex samples of every stream's window are the LAST
+                                `carry_samples` of the window given to the previous dabb_submit (a receiver reads its input once; the overlap
+                                a frame needs is kept on the device): they are taken from the previous staging slot instead of being copied
+                                host->device again.  0 = copy the whole window.  Ignored by dabb_process / dabb_process_async. */
 } dabb_io;
 enum { DABB_IQ_CF32 = 0, DABB_IQ_U8 = 1, DABB_IQ_S8 = 2, DABB_IQ_S16LE = 3, DABB_IQ_S16BE = 4 };
 int dabb_process(dabb_ctx* ctx, const dabb_io* io);

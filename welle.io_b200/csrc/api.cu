@@ -74,6 +74,7 @@ struct dabb_ctx {
     // pipelined host-buffer path (dabb_submit / dabb_collect): copy stream, two device staging slots, two result slots in pinned memory
     cudaStream_t streamC = nullptr; cudaEvent_t evH2D[2] = {nullptr, nullptr}, evStageFree[2] = {nullptr, nullptr}; bool stageFreeValid[2] = {false, false};
     void* d_stage2[2] = {nullptr, nullptr}; size_t stage2_bytes[2] = {0, 0};
+    int stage_last_fmt = -1; int64_t stage_last_len = 0; std::vector<int64_t> stage_last_start;     // the previous dabb_submit's window (carry_samples)
     struct Pending {
         bool used = false; cudaEvent_t done = nullptr; dabb_io io{};
         dabb_frame_result* h_res = nullptr; uint8_t* h_fibs = nullptr; uint8_t* h_msc = nullptr; uint8_t* h_sf = nullptr; size_t msc_bytes = 0, sf_bytes = 0;
@@ -953,7 +954,21 @@ int dabb_submit(dabb_ctx* ctx, const dabb_io* io)
     }
     // the staging slot was last read by the step submitted two calls ago
     if (ctx->stageFreeValid[slot]) CK(cudaStreamWaitEvent(Cs, ctx->evStageFree[slot], 0));
-    CK(cudaMemcpy2DAsync(ctx->d_stage2[slot], (size_t)io->buf_len * bps, io->iq, (size_t)io->stride_samples * bps, (size_t)io->buf_len * bps, S, cudaMemcpyHostToDevice, Cs));
+    // carry_samples: the head of every window is the tail of the previous one, which still lies in the other staging slot
+    const int64_t carry = io->carry_samples;
+    if (carry) {
+        if (carry < 0 || carry >= io->buf_len || ctx->submits == 0 || ctx->stage_last_fmt != fmt || carry > ctx->stage_last_len || !ctx->d_stage2[slot ^ 1]) {
+            ctx->err = "carry_samples needs a previous dabb_submit of the same format with a window at least that long"; return DABB_E_ARG;
+        }
+        for (int s = 0; s < S; s++)
+            if (io->buf_start[s] != ctx->stage_last_start[s] + ctx->stage_last_len - carry) { ctx->err = "carry_samples: a window does not start where the previous one ended minus the carry"; return DABB_E_ARG; }
+        const unsigned char* prev = reinterpret_cast<const unsigned char*>(ctx->d_stage2[slot ^ 1]);
+        CK(cudaMemcpy2DAsync(ctx->d_stage2[slot], (size_t)io->buf_len * bps, prev + (size_t)(ctx->stage_last_len - carry) * bps, (size_t)ctx->stage_last_len * bps,
+                             (size_t)carry * bps, S, cudaMemcpyDeviceToDevice, Cs));          // same stream as the copy that filled the other slot
+    }
+    CK(cudaMemcpy2DAsync(reinterpret_cast<unsigned char*>(ctx->d_stage2[slot]) + (size_t)carry * bps, (size_t)io->buf_len * bps,
+                         reinterpret_cast<const unsigned char*>(io->iq) + (size_t)carry * bps, (size_t)io->stride_samples * bps, (size_t)(io->buf_len - carry) * bps, S, cudaMemcpyHostToDevice, Cs));
+    ctx->stage_last_fmt = fmt; ctx->stage_last_len = io->buf_len; ctx->stage_last_start.assign(io->buf_start, io->buf_start + S);
     CK(cudaEventRecord(ctx->evH2D[slot], Cs));
     CK(cudaStreamWaitEvent(A, ctx->evH2D[slot], 0));
     const float2* iq = reinterpret_cast<const float2*>(ctx->d_stage2[slot]);

@@ -4,8 +4,9 @@
 //   rs_superframes_kernel  the same without window state, for the stage-level API
 // RS(120,110) over GF(2^8) (field polynomial 0x11D, first root alpha^0, 10 roots, shortened by 135): one thread per
 // interleaved codeword column; syndromes by Horner, then — only when a syndrome is non-zero — Berlekamp-Massey, Chien
-// search over all 255 locations and Forney, following the same algebra as libs/fec/decode_rs.h:71-298 so that the
-// behaviour on uncorrectable words matches.  Latency/issue bound with negligible volume (12 codewords per 96 kbit/s
+// search over all 255 locations and Forney.  rs_decode_column is transliterated from libs/fec/decode_rs.h:159-298 (KA9Q libfec, index
+// form -> polynomial form, same step sequence and early exits) because the behaviour on uncorrectable words - which positions get
+// touched, what count is reported - is defined by that sequence and must match.  Latency/issue bound with negligible volume (12 codewords per 96 kbit/s
 // superframe every 120 ms of signal).
 #include "common.cuh"
 #include "viterbi.cuh"

@@ -65,7 +65,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(FrameResult), (RESULT_DTYPE.itemsize, C
 class IO(C.Structure):
     _fields_ = [("iq", C.c_void_p), ("iq_is_host", C.c_int32), ("stride_samples", C.c_int64), ("buf_start", C.c_void_p), ("buf_len", C.c_int64),
                 ("results", C.c_void_p), ("fibs", C.c_void_p), ("msc", C.c_void_p), ("msc_stride", C.c_int32), ("sf", C.c_void_p), ("sf_stride", C.c_int32),
-                ("iq_format", C.c_int32), ("reserved", C.c_int32)]
+                ("iq_format", C.c_int32), ("carry_samples", C.c_int32)]
 
 
 EXPORTS = ["dabb_create", "dabb_destroy", "dabb_last_error", "dabb_abi_version", "dabb_stream_reset", "dabb_set_options", "dabb_get_info", "dabb_select_subchannel",
@@ -241,14 +241,16 @@ class Context:
         self._ck(self.lib.dabb_process(self.h, C.byref(io)))
         return out
 
-    def submit(self, iq, stride, buf_start, buf_len, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0, out=None):
+    def submit(self, iq, stride, buf_start, buf_len, msc_stride=0, sf_stride=0, want=("results", "fibs"), iq_format=0, out=None, carry=0):
         """pipelined host-buffer step (dabb_submit): returns immediately; collect() hands back the output dict of the oldest step.
-        `out`: a dict returned by an earlier collect() to be reused for this step's results (saves allocating the arrays again)"""
+        `out`: a dict returned by an earlier collect() to be reused for this step's results (saves allocating the arrays again).
+        `carry`: the first `carry` samples of every window repeat the end of the previous submit's window and are not copied again"""
         S = self.n_streams
         bs = np.ascontiguousarray(buf_start, np.int64)
         io = IO()
         io.iq = _addr(iq)
         io.iq_is_host, io.stride_samples, io.buf_len, io.iq_format = 1, stride, buf_len, iq_format
+        io.carry_samples = int(carry)
         io.buf_start = bs.ctypes.data
         if out is not None:
             io.results = out["results"].ctypes.data if "results" in out else None
