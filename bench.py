@@ -278,6 +278,9 @@ def config_dict(a, groups):
             "batch_frames_per_gpu": a.batch, "subchannel": "96 kbit/s EEP 3-A, 72 CU, DAB+", "snr_db": a.snr, "fft_mode": "exact(KISS-bit-identical)" if a.fft_mode == 0 else "fma",
             "parallelism": f"streams sharded over {a.gpus} GPU(s), no data-path collective", "l2_policy": "inputs (12.9 GB/step at batch 8192) far exceed the 126 MB L2; no flush needed",
             "carrier_offset": "0 Hz (headline): fine corrector stays 0 and the oscillator multiply is skipped; roofline.oscillator_active repeats the run with an offset",
+            "input": "8 distinct 5-frame periodic rings (different seeds) replicated over the batch + per-stream AWGN; the timed region is steps x ~4.7 ms",
+            "ofdm_tail_split": "last resident/2 frames of the launch as 5 CTAs of 15 symbols" if not getattr(a, "no_tail_split", False) else "off",
+            "nco_mode": "exact (headline; oscillator_active reports exact and fast)",
             "ofdm_groups": groups}
 
 
@@ -289,6 +292,33 @@ def make_rings(n_distinct):
         _, ring = dabtx.periodic_ring(0xB200 + i, RING_FRAMES)
         rings.append(ring)
     return np.stack(rings)
+
+
+def prefer_host_memory_near_gpu(index):
+    """Host allocations of this rank (the pinned IQ ring of the e2e leg) should come from the NUMA node its GPU hangs off: what
+    `numactl --preferred` per rank does, through set_mempolicy(MPOL_PREFERRED).  Returns what was done (goes into `config`)."""
+    info = {"gpu_numa_node": None, "policy": "default"}
+    try:
+        import ctypes
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = -1
+        for cand in (bus.lower(), bus.lower()[4:] if len(bus) > 12 else bus.lower()):
+            pth = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(pth):
+                node = int(open(pth).read().strip()); break
+        info["gpu_numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node >= 0 and len(nodes) > 1:
+            mask = ctypes.c_ulong(1 << node)
+            libc = ctypes.CDLL(None, use_errno=True)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), 8 * ctypes.sizeof(mask))       # x86-64 SYS_set_mempolicy, MPOL_PREFERRED
+            info["policy"] = f"preferred node {node}" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:  # noqa
+        info["policy"] = "default (" + type(e).__name__ + ")"
+    return info
 
 
 def main():
@@ -343,6 +373,7 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    numa_info = prefer_host_memory_near_gpu(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -729,7 +760,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int16x2", "data": "synthetic",
-                "config": config_dict(a, None), "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline, "roofline_viterbi": vit,
+                "config": dict(config_dict(a, None), host_numa=numa_info), "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline, "roofline_viterbi": vit,
                 "cpu_baseline": cpu, "check": check, "kernels": kern, "other_configs": other}
         print(json.dumps(line))
     ctx.close()
