@@ -59,7 +59,7 @@ struct dabb_ctx {
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
     int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
-    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float* d_cir_work = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
     int8_t* d_soft = nullptr; uint2* d_fic_steptab = nullptr; uint32_t* d_fic_stage_off = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
     dabb_frame_result* d_results = nullptr;
     // per slot
@@ -553,7 +553,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         (rc = dalloc(ctx, &ctx->d_index, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_snr, 2 * (size_t)S)) || (rc = dalloc(ctx, &ctx->d_fc, 2 * (size_t)S * ctx->fc_pitch)) || (rc = dalloc(ctx, &ctx->d_lvl, 2 * (size_t)S * ctx->fc_pitch)) ||
         (rc = dalloc(ctx, &ctx->d_soft, 2 * (size_t)S * DABB_SOFT_PER_FRAME + VIT_FRAG_SLACK, false)) ||
         (rc = dalloc(ctx, &ctx->d_fibs, (size_t)S * 12 * 32)) || (rc = dalloc(ctx, &ctx->d_crc, S)) || (rc = dalloc(ctx, &ctx->d_results, S)) ||
-        (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)))
+        (rc = dalloc(ctx, &ctx->d_info_tab, DABB_MAX_SUBCH)) || (rc = dalloc(ctx, &ctx->d_cir_work, (size_t)S * TU, false)))
         return fail(rc);
     if (ctx->keep_taps && ((rc = dalloc(ctx, &ctx->d_cir, (size_t)S * TU)) || (rc = dalloc(ctx, &ctx->d_r1, (size_t)S * 75 * 1536)) || (rc = dalloc(ctx, &ctx->d_null, (size_t)S * TNULL)))) return fail(rc);
     if ((rc = ensure_dec(ctx, vit_dec_bytes(S * 4, 774)))) return fail(rc);
@@ -798,8 +798,15 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
     SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = d_win; sp.nco = d_nco_sync; sp.active = d_active; sp.index_out = d_index; sp.cir_out = ctx->d_cir; sp.n = S;
     sp.fic_ratio = ctx->d_fic_ratio; sp.coarse_out = ctx->disable_coarse ? nullptr : ctx->d_coarse; sp.placement = ctx->placement; sp.freqsync = ctx->freqsync;
-    launch_find_index(ctx->dev, sp, ctx->fft_mode, A);
+    sp.cir_work = ctx->d_cir_work;
+    launch_find_index(ctx->dev, sp, ctx->fft_mode, A, 0);
     if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
+    launch_find_index(ctx->dev, sp, ctx->fft_mode, A, 1);
+    if ((rc = check_launch(ctx, "find_search_kernel"))) return rc;
+    if (sp.coarse_out) {
+        launch_find_index(ctx->dev, sp, ctx->fft_mode, A, 2);
+        if ((rc = check_launch(ctx, "find_coarse_kernel"))) return rc;
+    }
     post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, ctx->disable_coarse ? nullptr : ctx->d_coarse, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
@@ -1115,8 +1122,15 @@ int dabb_find_index_ex(dabb_ctx* ctx, const float* iq, int64_t stride, const int
     cudaSetDevice(ctx->device);
     sync_all(ctx);
     SyncParams sp{}; sp.iq = reinterpret_cast<const float2*>(iq); sp.stride = stride; sp.win_start = win_start; sp.nco = nullptr; sp.active = nullptr; sp.index_out = index_out; sp.cir_out = cir_out; sp.n = n; sp.fic_ratio = nullptr; sp.coarse_out = nullptr; sp.placement = placement; sp.freqsync = 0;
+    // magnitudes between the transform and the search kernel: the context's buffer when the batch fits, else a temporary
+    float* work = n <= ctx->S ? ctx->d_cir_work : nullptr;
+    bool temp = false;
+    if (!work) { if (cudaMalloc((void**)&work, (size_t)n * TU * sizeof(float)) != cudaSuccess) { ctx->err = "cudaMalloc(findIndex work buffer)"; return DABB_E_NOMEM; } temp = true; }
+    sp.cir_work = work;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
-    return check_launch(ctx, "find_index_kernel");
+    int rc = check_launch(ctx, "find_index_kernel");
+    if (temp) { cudaStreamSynchronize(ctx->stream); cudaFree(work); }
+    return rc;
 }
 
 int dabb_find_index(dabb_ctx* ctx, const float* iq, int64_t stride, const int64_t* win_start, int32_t n, int32_t* index_out, float* cir_out)

@@ -65,6 +65,7 @@ struct SyncParams {
     const int32_t* nco;                          // [n][2] or nullptr
     const int32_t* active;
     int32_t* index_out; float* cir_out; int n;
+    float* cir_work;                             // [n][T_u] magnitudes between the transform kernel and the search kernel
     // coarse frequency corrector (OFDMProcessor::processPRS, PatternOfZeros): evaluated for streams whose FIC success
     // counter is below 5 (ofdm-processor.cpp:397); result = carrier offset, or 100 when not evaluated / no estimate
     const int32_t* fic_ratio; int32_t* coarse_out;
@@ -75,7 +76,7 @@ struct SyncParams {
 int ofdm_init_constants();     // per-device constants of ofdm.cu (call once after cudaSetDevice)
 void launch_ofdm_demod(const DevTables& tb, const OfdmParams& p, int fft_mode, cudaStream_t st);
 int ofdm_tail_frames(int n_frames);
-void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st);
+void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st, int part = -1);
 void launch_tii_spectra(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, const int32_t* nco_frame, const int32_t* active,
                         const float2* nulls, float2* out, int n, cudaStream_t st);
 void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const int64_t* prs_start, int n, int freqsync, int32_t* out, cudaStream_t st);

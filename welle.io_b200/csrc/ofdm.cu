@@ -711,19 +711,55 @@ find_index_kernel(DevTables tb, SyncParams p)
         for (int c = 0; c < 16; c++) v[c] = sm.o.xbuf[(t ^ xc_of(c)) + 128 * c];
         passC_ldg<EXACT, true>(v, t, tb.tw_inv + TwLayout::C5);
     }
-    // scale by 1/2048 (fft.cpp:146-158) and take the magnitude the way glibc's hypotf does (double sqrt, narrowed)
+    // scale by 1/2048 (fft.cpp:146-158) and take the magnitude the way glibc's hypotf does (double sqrt, narrowed); the magnitudes go to
+    // global memory: the search over them (find_search_kernel) is a different kind of work - a 2048-step sequential sum beside a few
+    // short parallel phases - and runs as its own kernel at a much higher residency than this register-heavy transform kernel
     const float factor = 1.0f / 2048.0f;
+    float* cw = p.cir_work + (int64_t)f * TU;
 #pragma unroll
     for (int c = 0; c < 16; c++) {
         const float re = fmul_<true>(v[c].x, factor), im = fmul_<true>(v[c].y, factor);
         const double m = __dsqrt_rn(__dadd_rn(__dmul_rn((double)re, (double)re), __dmul_rn((double)im, (double)im)));
-        sm.cir[t + 128 * c] = (float)m;
+        cw[t + 128 * c] = (float)m;
+    }
+}
+
+// findIndex, second part: the placement search over the 2048 magnitudes of one window (phasereference.cpp:93-253).  One 128-thread CTA
+// per window, 24 KB of shared memory and few registers: many windows per SM hide the sequential sum each of them carries.
+struct __align__(16) SearchSmem {
+    float cir[TU];
+    float m2[2 * TU];
+    float wmax[4]; int wmin[4];
+    float sum;
+};
+__global__ void __launch_bounds__(OFDM_THREADS)
+find_search_kernel(SyncParams p)
+{
+    __shared__ SearchSmem sm;
+    const int t = threadIdx.x, f = blockIdx.x;
+    if (p.active && !p.active[f]) return;
+    {
+        const float4* src4 = reinterpret_cast<const float4*>(p.cir_work + (int64_t)f * TU);
+        float4* dst4 = reinterpret_cast<float4*>(sm.cir);
+#pragma unroll
+        for (int c = 0; c < 4; c++) dst4[t + 128 * c] = src4[t + 128 * c];
     }
     __syncthreads();
     // the binning placement never computes the last 8 magnitudes (loop bound i + 20 < Tu, phasereference.cpp:148)
     if (p.cir_out) for (int i = t; i < TU; i += OFDM_THREADS) p.cir_out[(int64_t)f * TU + i] = (p.placement == 2 && i >= 2040) ? 0.f : sm.cir[i];
-    float* ma = reinterpret_cast<float*>(sm.o.xbuf);
+    float* ma = sm.m2;
     float* mb = ma + TU;
+    // the sequential float sum of the magnitudes in index order (the CPU loop's order, so the same float): 16-byte loads, and the loop
+    // unrolled so that the loads run ahead of the dependent adds
+    auto seq_sum = [&](float acc, int q0, int nq) {
+        const float4* c4 = reinterpret_cast<const float4*>(sm.cir);
+#pragma unroll 8
+        for (int q = q0; q < q0 + nq; q++) {
+            const float4 x = c4[q];
+            acc = __fadd_rn(acc, x.x); acc = __fadd_rn(acc, x.y); acc = __fadd_rn(acc, x.z); acc = __fadd_rn(acc, x.w);
+        }
+        return acc;
+    };
     int result;                 // what findIndex returns: >= 0 sample index, < 0 no synchronisation
     if (p.placement == 0) {
         // ---- ThresholdBeforePeak (phasereference.cpp:212-253).
@@ -741,7 +777,7 @@ find_index_kernel(DevTables tb, SyncParams p)
                 const int sh = 1 << lvl;
 #pragma unroll
                 for (int c = 0; c < 16; c++) { const int i = t + 128 * c; dstm[i] = fmaxf(srcm[i], srcm[min(i + sh, TU - 1)]); }
-                if (t == 0) { for (int i = 293 * lvl; i < 293 * (lvl + 1); i++) ssum = __fadd_rn(ssum, sm.cir[i]); }
+                if (t == 0) ssum = seq_sum(ssum, 74 * lvl, 74);
                 __syncthreads();
                 srcm = dstm; dstm = (dstm == ma) ? mb : ma;
             }
@@ -755,7 +791,7 @@ find_index_kernel(DevTables tb, SyncParams p)
             if (i + 100 < TU) { m = fmaxf(mb[i], mb[i + 36]); gmax = fmaxf(gmax, m); }
             pk[i] = m;
         }
-        if (t == 0) { for (int i = 293 * 6; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
+        if (t == 0) { ssum = seq_sum(ssum, 74 * 6, TU / 4 - 74 * 6); sm.sum = ssum; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
         if ((t & 31) == 0) sm.wmax[t >> 5] = gmax;
@@ -784,7 +820,7 @@ find_index_kernel(DevTables tb, SyncParams p)
             if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
         }
         if ((t & 31) == 0) { sm.wmax[t >> 5] = mx; sm.wmin[t >> 5] = mi; }
-        if (t == 32) { float ssum = 0.f; for (int i = 0; i < TU; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = ssum; }
+        if (t == 32) sm.sum = seq_sum(0.f, 0, TU / 4);
         __syncthreads();
         mx = sm.wmax[0]; mi = sm.wmin[0];
 #pragma unroll
@@ -804,7 +840,7 @@ find_index_kernel(DevTables tb, SyncParams p)
             for (int j = 0; j < 20; j++) { const float val = sm.cir[20 * t + j]; if (val > pv) { pv = val; pi = 20 * t + j; } }
             bval[t] = pv; bidx[t] = pi;
         }
-        if (t == 127) { float ssum = 0.f; for (int i = 0; i < 20 * NB; i++) ssum = __fadd_rn(ssum, sm.cir[i]); sm.sum = __fdiv_rn(ssum, 2048.0f); }
+        if (t == 127) sm.sum = __fdiv_rn(seq_sum(0.f, 0, 20 * NB / 4), 2048.0f);
         __syncthreads();
         if (t == 0) {
             int top = 0;
@@ -830,10 +866,27 @@ find_index_kernel(DevTables tb, SyncParams p)
         __syncthreads();
         result = sm.wmin[0];
     }
-    if (t == 0) p.index_out[f] = result;
-    if (!p.coarse_out) return;
-    if (t == 0) p.coarse_out[f] = 100;          // 100 = not evaluated (OFDMProcessor::processPRS returns 100 for "no estimate" too)
+    if (t == 0) {
+        p.index_out[f] = result;
+        if (p.coarse_out) p.coarse_out[f] = 100;          // 100 = not evaluated (OFDMProcessor::processPRS returns 100 for "no estimate" too)
+    }
+}
+
+// findIndex, third part: the coarse frequency estimate for the windows whose FIC success counter is low (ofdm-processor.cpp:397);
+// every other CTA leaves at once
+template <bool EXACT, bool NCO>
+__global__ void __launch_bounds__(OFDM_THREADS, 5)
+find_coarse_kernel(DevTables tb, SyncParams p)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    SyncSmem& sm = *reinterpret_cast<SyncSmem*>(smraw);
+    const int t = threadIdx.x, f = blockIdx.x;
+    if (p.active && !p.active[f]) return;
+    const int result = p.index_out[f];
     if (result < 0 || p.fic_ratio[f] * 10 >= 50) return;      // CTA-uniform
+    const float2* src = p.iq + (int64_t)f * p.stride + p.win_start[f];
+    const Nco nco = make_nco((NCO && p.nco) ? p.nco[2 * f] : 0, (NCO && p.nco) ? p.nco[2 * f + 1] : 0);
+    const XIdx xi = make_xidx(t);
     coarse_estimate<EXACT>(tb, sm, src, result, nco, xi, t, p.freqsync, &p.coarse_out[f]);
 }
 
@@ -936,14 +989,27 @@ void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const 
     coarse_kernel<<<n, OFDM_THREADS, sizeof(SyncSmem), st>>>(tb, iq, stride, prs_start, freqsync, out);
 }
 
-void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st)
+// part: 0 transforms -> magnitudes, 1 placement search -> index, 2 coarse estimate where the FIC counter asks for it, -1 all three
+void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, cudaStream_t st, int part)
 {
     const dim3 grid(p.n), block(OFDM_THREADS);
-    const size_t sm = sizeof(SyncSmem);
     const bool nco = p.nco != nullptr;
     (void)fft_mode;   // time sync always uses the exact arithmetic: its integer result feeds the closed loop
-    if (nco) { set_smem(find_index_kernel<true, true>, sm); find_index_kernel<true, true><<<grid, block, sm, st>>>(tb, p); }
-    else { set_smem(find_index_kernel<true, false>, sm); find_index_kernel<true, false><<<grid, block, sm, st>>>(tb, p); }
+    if (part < 0 || part == 0) {
+        const size_t sm = sizeof(OfdmSmem);
+        if (nco) { set_smem(find_index_kernel<true, true>, sm); find_index_kernel<true, true><<<grid, block, sm, st>>>(tb, p); }
+        else { set_smem(find_index_kernel<true, false>, sm); find_index_kernel<true, false><<<grid, block, sm, st>>>(tb, p); }
+    }
+    if (part < 0 || part == 1) {
+        // 24 KB of static shared memory per CTA: ask for the largest carve-out, or the driver sizes it for far fewer CTAs than the 9 that fit
+        cudaFuncSetAttribute(find_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        find_search_kernel<<<grid, block, 0, st>>>(p);
+    }
+    if ((part < 0 || part == 2) && p.coarse_out) {
+        const size_t sc = sizeof(SyncSmem);
+        if (nco) { set_smem(find_coarse_kernel<true, true>, sc); find_coarse_kernel<true, true><<<grid, block, sc, st>>>(tb, p); }
+        else { set_smem(find_coarse_kernel<true, false>, sc); find_coarse_kernel<true, false><<<grid, block, sc, st>>>(tb, p); }
+    }
 }
 
 } // namespace dabb

@@ -79,20 +79,34 @@ msc_gather_kernel(MscPrepParams p)
     const int8_t* ring = p.ring + (int64_t)s * MSC_RING * p.ring_pitch;
     uint32_t* frag_w = reinterpret_cast<uint32_t*>(frag_s);
     const int nm = (int)(n % MSC_RING);           // one 64-bit modulo; the 16 slices follow with 32-bit arithmetic
+    // phase 1: the 16 residue rows, flattened over the CTA (16 per_w words; every thread has all its loads in flight at once)
+    const int total = 16 * per_w;
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)per_w + 1u;      // idx / per_w = umulhi(idx, magic) for idx < 2^16
 #pragma unroll 4
-    for (int r = 0; r < 16; r++) {
+    for (int idx = t; idx < total; idx += 128) {
+        const int r = (int)__umulhi((uint32_t)idx, magic), j = idx - r * per_w;
         int slice = nm - c_deint_delay[r];        // delay <= 16 < MSC_RING
         if (slice < 0) slice += MSC_RING;
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w;
-        for (int j = t; j < per_w; j += 128) frag_w[r * sw + j] = __ldg(srow + j);
+        frag_w[r * sw + j] = __ldg(reinterpret_cast<const uint32_t*>(ring + (int64_t)slice * p.ring_pitch) + r * per_w + j);
     }
     __syncthreads();
-    const int cw = s * 4 + c, sb = 4 * sw;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(p.frag_out + (int64_t)cw * p.frag_pitch);
-    const uint8_t* fs = reinterpret_cast<const uint8_t*>(frag_s);
-    for (int q = t; q < frag / 4; q += 128) {
-        const uint8_t* b = fs + (4 * (q & 3)) * sb + (q >> 2);      // bytes i = 4q .. 4q+3: residues 4 (q & 3) + k, column q >> 2
-        dst[q] = (uint32_t)b[0] | ((uint32_t)b[sb] << 8) | ((uint32_t)b[2 * sb] << 16) | ((uint32_t)b[3 * sb] << 24);
+    // phase 2: natural order.  Word j of row r holds softbits r + 16 (4j .. 4j+3); output word q = bytes 4q .. 4q+3 = residues
+    // 4 (q & 3) .. +3 of column q >> 2.  One thread per column word j: four 4x4 byte transposes (PRMT, as in msc_collect_kernel)
+    // turn its 16 row words into the 16 consecutive output words 16 j .. 16 j + 15 (four 16-byte stores).
+    const int cw = s * 4 + c;
+    uint4* dst = reinterpret_cast<uint4*>(p.frag_out + (int64_t)cw * p.frag_pitch);
+    for (int j = t; j < per_w; j += 128) {
+        uint32_t o[4][4];        // [column m][residue group g]
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t w0 = frag_w[(4 * g + 0) * sw + j], w1 = frag_w[(4 * g + 1) * sw + j], w2 = frag_w[(4 * g + 2) * sw + j], w3 = frag_w[(4 * g + 3) * sw + j];
+            const uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+            const uint32_t t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+            o[0][g] = __byte_perm(t0, t1, 0x5410); o[1][g] = __byte_perm(t0, t1, 0x7632);
+            o[2][g] = __byte_perm(t2, t3, 0x5410); o[3][g] = __byte_perm(t2, t3, 0x7632);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) dst[4 * j + m] = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
     }
     if (t == 0 && p.valid) p.valid[cw] = 1;
 }
@@ -244,26 +258,30 @@ __global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
 viterbi_kernel(ViterbiParams p) { viterbi_cta<VIT_STAGES>(p, blockIdx.x); }
 
 
-// one thread per frame: CRC of the 12 FIBs (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80)
+// CRC of the 12 FIBs of a frame (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80): one thread per FIB, 16
+// lanes per frame (12 used), the frame's mask assembled with a ballot
 __global__ void fic_crc_kernel(const uint8_t* __restrict__ fibs, const int32_t* __restrict__ active, int n_frames, int32_t* __restrict__ mask_out)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_frames) return;
-    if (active && !active[f]) { mask_out[f] = 0; return; }
-    int32_t mask = 0;
-    for (int fib = 0; fib < 12; fib++) {
-        const uint8_t* b = fibs + ((int64_t)f * 12 + fib) * 32;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = gt >> 4, fib = gt & 15;
+    bool ok = false;
+    if (f < n_frames && fib < 12 && !(active && !active[f])) {
+        const uint4* b4 = reinterpret_cast<const uint4*>(fibs + ((int64_t)f * 12 + fib) * 32);
+        const uint4 lo = __ldg(b4), hi = __ldg(b4 + 1);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         uint32_t reg = 0xFFFF;
+#pragma unroll
         for (int i = 0; i < 32; i++) {
-            uint32_t byte = b[i];
+            uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             if (i >= 30) byte ^= 0xFF;
             reg ^= byte << 8;
 #pragma unroll
             for (int k = 0; k < 8; k++) reg = (reg & 0x8000) ? ((reg << 1) ^ 0x1021) & 0xFFFF : (reg << 1) & 0xFFFF;
         }
-        if (reg == 0) mask |= 1 << fib;
+        ok = reg == 0;
     }
-    mask_out[f] = mask;
+    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok);
+    if (f < n_frames && fib == 0) mask_out[f] = (int32_t)((bits >> (threadIdx.x & 16)) & 0xFFFu);      // inactive frames: 0
 }
 
 // packed bytes -> one bit per byte (stage-level API output format of Viterbi::deconvolve)
@@ -318,7 +336,7 @@ size_t vit_dec_bytes(int n_cw, int nsteps) { return (size_t)((n_cw + VIT_THREADS
 
 void launch_fic_crc(const uint8_t* fibs, const int32_t* active, int n_frames, int32_t* mask_out, cudaStream_t st)
 {
-    fic_crc_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(fibs, active, n_frames, mask_out);
+    fic_crc_kernel<<<(n_frames * 16 + 127) / 128, 128, 0, st>>>(fibs, active, n_frames, mask_out);
 }
 
 void launch_unpack_bits(const uint8_t* bytes, int64_t stride, int n_cw, int nbits, uint8_t* bits, cudaStream_t st)
