@@ -90,6 +90,40 @@ def test_find_index(ctx, oracle, iq12):
     assert idx[0] == 504
 
 
+def test_find_index_threshold_search_many_windows(oracle, iq12):
+    """ThresholdBeforePeak over the whole range of peak positions (window starts swept over more than a symbol, so the correlation peak
+    lands everywhere incl. the first 200 and the last samples, and outside: no synchronisation), on clean, noisy, pre-echo and
+    noise-only input.  The library's warp-per-window search (no sliding maximum: DESIGN.md 3) and its literal sliding-maximum form
+    (DABB_SEARCH_GENERIC) must both equal the oracle's index for every window."""
+    from conftest import load_pkg
+    import os
+    pkg = load_pkg()
+    tx, iq = iq12
+    rng = np.random.default_rng(77)
+    base = iq[2 * TF: 3 * TF]
+    variants = [base, dabtx.add_awgn(iq, 3.0, seed=5)[2 * TF: 3 * TF], (base + 0.8 * np.roll(base, -150)).astype(np.complex64),
+                (base * 0.02 + (rng.standard_normal(TF) + 1j * rng.standard_normal(TF)) * 0.05).astype(np.complex64)]
+    frames = []
+    for v, sig in enumerate(variants):
+        for d in range(-260, 2300, 17 + v):
+            st = TNULL + 504 - d
+            frames.append(sig[st: st + TU])
+    frames = np.stack(frames); starts = np.zeros(len(frames), np.int64)
+    exp = np.array([oracle.find_index(frames[i])[0] for i in range(len(frames))])
+    assert len(set(exp.tolist())) > 100 and (exp < 0).any() and (exp < 200).any() and (exp > 1800).any()
+    for generic in (False, True):
+        if generic:
+            os.environ["DABB_SEARCH_GENERIC"] = "1"
+        try:
+            c = pkg.Context(n_streams=len(starts))
+        finally:
+            os.environ.pop("DABB_SEARCH_GENERIC", None)
+        idx = c.find_index(frames, starts)
+        c.close()
+        bad = np.nonzero(idx != exp)[0]
+        assert bad.size == 0, (generic, bad[:10], idx[bad[:10]], exp[bad[:10]])
+
+
 @pytest.mark.parametrize("placement", [1, 2])
 def test_find_index_other_placements(ctx, oracle, iq12, placement):
     """StrongestPeak / EarliestPeakWithBinning (phasereference.cpp:93-211): index (incl. the negative scores) and CIR bit-equal"""

@@ -59,7 +59,7 @@ struct dabb_ctx {
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
     int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
-    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float* d_cir_work = nullptr; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float* d_cir_work = nullptr; int search_generic = 0; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
     int8_t* d_soft = nullptr; uint2* d_fic_steptab = nullptr; uint32_t* d_fic_stage_off = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
     dabb_frame_result* d_results = nullptr;
     // per slot
@@ -542,6 +542,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_fic_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice);
     }
+    ctx->search_generic = getenv("DABB_SEARCH_GENERIC") != nullptr;     // A/B: ThresholdBeforePeak through the literal sliding maximum
     if (getenv("DABB_TRACE")) {
         ctx->trace_path = getenv("DABB_TRACE"); ctx->trace.cap = 1u << 20;
         if ((rc = dalloc(ctx, &ctx->trace.rec, (size_t)3 * ctx->trace.cap)) || (rc = dalloc(ctx, &ctx->trace.count, 1))) return fail(rc);
@@ -798,7 +799,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     if ((rc = check_launch(ctx, "plan_kernel"))) return rc;
     SyncParams sp{}; sp.iq = iq; sp.stride = stride; sp.win_start = d_win; sp.nco = d_nco_sync; sp.active = d_active; sp.index_out = d_index; sp.cir_out = ctx->d_cir; sp.n = S;
     sp.fic_ratio = ctx->d_fic_ratio; sp.coarse_out = ctx->disable_coarse ? nullptr : ctx->d_coarse; sp.placement = ctx->placement; sp.freqsync = ctx->freqsync;
-    sp.cir_work = ctx->d_cir_work;
+    sp.cir_work = ctx->d_cir_work; sp.search_generic = ctx->search_generic;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, A, 0);
     if ((rc = check_launch(ctx, "find_index_kernel"))) return rc;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, A, 1);
@@ -1126,7 +1127,7 @@ int dabb_find_index_ex(dabb_ctx* ctx, const float* iq, int64_t stride, const int
     float* work = n <= ctx->S ? ctx->d_cir_work : nullptr;
     bool temp = false;
     if (!work) { if (cudaMalloc((void**)&work, (size_t)n * TU * sizeof(float)) != cudaSuccess) { ctx->err = "cudaMalloc(findIndex work buffer)"; return DABB_E_NOMEM; } temp = true; }
-    sp.cir_work = work;
+    sp.cir_work = work; sp.search_generic = ctx->search_generic;
     launch_find_index(ctx->dev, sp, ctx->fft_mode, ctx->stream);
     int rc = check_launch(ctx, "find_index_kernel");
     if (temp) { cudaStreamSynchronize(ctx->stream); cudaFree(work); }

@@ -71,6 +71,7 @@ struct SyncParams {
     const int32_t* fic_ratio; int32_t* coarse_out;
     int placement;      // DABB_PLACEMENT_*: 0 ThresholdBeforePeak, 1 StrongestPeak, 2 EarliestPeakWithBinning
     int freqsync;       // DABB_FREQSYNC_*: 0 PatternOfZeros, 1 GetMiddle, 2 CorrelatePRS
+    int search_generic; // 1: ThresholdBeforePeak through the literal sliding-maximum search (find_search_kernel) instead of the warp-per-window form (A/B tests)
 };
 
 int ofdm_init_constants();     // per-device constants of ofdm.cu (call once after cudaSetDevice)

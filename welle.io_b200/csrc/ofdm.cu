@@ -872,6 +872,68 @@ find_search_kernel(SyncParams p)
     }
 }
 
+// ThresholdBeforePeak (the default placement, phasereference.cpp:212-253) without the sliding maximum.  The reference takes
+// pk[i] = max(cir[i .. i+99]) for i + 100 < T_u (0 beyond), gmax = max pk, and - if gmax > 3 sum / T_u - returns the first i with
+// pk[i + 100] > gmax / 2.  Since max() is exact: gmax = max(cir[0 .. T_u - 2]); and a window [j, j + 99], j >= 100, holds a value above
+// the threshold exactly when j >= k* - 99 for the first k* >= 100 with cir[k*] > gmax / 2, so the first such window starts at
+// j = max(100, k* - 99) (always < T_u - 100 for k* <= T_u - 2) and the result is j - 100.  What is left per window is the sequential
+// float sum (one lane, 2048 dependent adds - the CPU loop's order, so the same float), one maximum and one first-above-threshold
+// search: one WARP per window, four windows per CTA, 8 KB of shared memory each, so ~28 sums are in flight per SM.
+__global__ void __launch_bounds__(OFDM_THREADS)
+find_search_tbp_kernel(SyncParams p)
+{
+    __shared__ __align__(16) float cir_s[OFDM_THREADS / 32][TU];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int f = blockIdx.x * (OFDM_THREADS / 32) + w;
+    if (f >= p.n) return;                                   // warp-uniform from here on
+    if (p.active && !p.active[f]) return;
+    float* cir = cir_s[w];
+    const float4* src4 = reinterpret_cast<const float4*>(p.cir_work + (int64_t)f * TU);
+    float gmax = -10000.f;
+    float4 x[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) x[c] = src4[lane + 32 * c];
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        reinterpret_cast<float4*>(cir)[lane + 32 * c] = x[c];
+        if (p.cir_out) reinterpret_cast<float4*>(p.cir_out + (int64_t)f * TU)[lane + 32 * c] = x[c];
+        gmax = fmaxf(gmax, fmaxf(fmaxf(x[c].x, x[c].y), x[c].z));
+        if (!(c == 15 && lane == 31)) gmax = fmaxf(gmax, x[c].w);          // index T_u - 1 is in no window
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    const float thresh = gmax / 2;
+    int kstar = 1 << 30;
+#pragma unroll
+    for (int c = 15; c >= 0; c--) {
+        const int k0 = 4 * (lane + 32 * c);
+        if (k0 + 3 <= TU - 2 && k0 + 3 >= 100 && x[c].w > thresh) kstar = k0 + 3;
+        if (k0 + 2 >= 100 && x[c].z > thresh) kstar = k0 + 2;
+        if (k0 + 1 >= 100 && x[c].y > thresh) kstar = k0 + 1;
+        if (k0 >= 100 && x[c].x > thresh) kstar = k0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kstar = min(kstar, __shfl_xor_sync(0xffffffffu, kstar, o));
+    __syncwarp();
+    float sum = 0.f;
+    if (lane == 0) {
+        const float4* c4 = reinterpret_cast<const float4*>(cir);
+#pragma unroll 8
+        for (int q = 0; q < TU / 4; q++) {
+            const float4 v = c4[q];
+            sum = __fadd_rn(sum, v.x); sum = __fadd_rn(sum, v.y); sum = __fadd_rn(sum, v.z); sum = __fadd_rn(sum, v.w);
+        }
+    }
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    if (lane == 0) {
+        int result = -1;
+        // `3 * sum / Tu`: float 3*sum, then / (size_t Tu converted to float)
+        if (gmax > __fdiv_rn(__fmul_rn(3.0f, sum), 2048.0f) && kstar != (1 << 30)) result = max(100, kstar - 99) - 100;
+        p.index_out[f] = result;
+        if (p.coarse_out) p.coarse_out[f] = 100;          // 100 = not evaluated
+    }
+}
+
 // findIndex, third part: the coarse frequency estimate for the windows whose FIC success counter is low (ofdm-processor.cpp:397);
 // every other CTA leaves at once
 template <bool EXACT, bool NCO>
@@ -1001,9 +1063,13 @@ void launch_find_index(const DevTables& tb, const SyncParams& p, int fft_mode, c
         else { set_smem(find_index_kernel<true, false>, sm); find_index_kernel<true, false><<<grid, block, sm, st>>>(tb, p); }
     }
     if (part < 0 || part == 1) {
-        // 24 KB of static shared memory per CTA: ask for the largest carve-out, or the driver sizes it for far fewer CTAs than the 9 that fit
-        cudaFuncSetAttribute(find_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        find_search_kernel<<<grid, block, 0, st>>>(p);
+        if (p.placement == 0 && !p.search_generic) {
+            cudaFuncSetAttribute(find_search_tbp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            find_search_tbp_kernel<<<(p.n + OFDM_THREADS / 32 - 1) / (OFDM_THREADS / 32), block, 0, st>>>(p);
+        } else {
+            cudaFuncSetAttribute(find_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            find_search_kernel<<<grid, block, 0, st>>>(p);
+        }
     }
     if ((part < 0 || part == 2) && p.coarse_out) {
         const size_t sc = sizeof(SyncSmem);
