@@ -17,6 +17,7 @@ namespace {
 
 struct Gf {
     const uint8_t* ex; const uint8_t* lg;
+    const uint16_t* lz;      // log with lz[0] = 512; ex[512 ..] holds zeros, so ex[lz[v] + r] is v * alpha^r for every v incl. 0 (no test in the Horner loop)
     __device__ __forceinline__ uint8_t mul(uint8_t a, uint8_t b) const { return (a && b) ? ex[lg[a] + lg[b]] : 0; }
     __device__ __forceinline__ uint8_t div(uint8_t a, uint8_t b) const { return a ? ex[lg[a] + 255 - lg[b]] : 0; }   // b == 0 acts like b == 1 (index A0 = 255 in the reference)
     __device__ __forceinline__ uint8_t apow(int e) const { e %= 255; if (e < 0) e += 255; return ex[e]; }
@@ -32,7 +33,7 @@ __device__ void rs_syndromes(const uint8_t* sf, int S, const Gf& gf, uint8_t* sy
         uint8_t v = sf[i];
         for (int j = 1; j < 120; j++) {
             const uint8_t d = sf[j * S + i];
-            v = d ^ (v ? gf.ex[gf.lg[v] + r] : 0);
+            v = d ^ gf.ex[gf.lz[v] + r];
         }
         synd[idx] = v;
     }
@@ -243,7 +244,8 @@ superframe_kernel(SuperframeParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SfShared sh;
-    __shared__ __align__(16) uint8_t gfe[512], gfl[256];
+    __shared__ __align__(16) uint8_t gfe[512 + 16], gfl[256];
+    __shared__ uint16_t gfz[256];
     const int s = blockIdx.x, t = threadIdx.x;
     int32_t* info = p.info + (int64_t)s * 16;
     if (t < 16) info[t] = 0;
@@ -258,10 +260,12 @@ superframe_kernel(SuperframeParams p)
         if (st.dabplus && count + nv >= 5) {
             for (int i = t; i < 128; i += SF_THREADS) reinterpret_cast<uint32_t*>(gfe)[i] = reinterpret_cast<const uint32_t*>(p.gf_exp)[i];
             for (int i = t; i < 64; i += SF_THREADS) reinterpret_cast<uint32_t*>(gfl)[i] = reinterpret_cast<const uint32_t*>(p.gf_log)[i];
+            for (int i = t; i < 256; i += SF_THREADS) gfz[i] = i ? (uint16_t)p.gf_log[i] : (uint16_t)512;
+            if (t < 16) gfe[512 + t] = 0;
             sf_tables_init(sh, t, SF_THREADS);
         }
     }
-    const Gf gf{gfe, gfl};
+    const Gf gf{gfe, gfl, gfz};
     uint8_t* win = smem;             // raw window, sf_len
     uint8_t* sf = smem + sf_len;     // working copy
     uint8_t* gwin = p.window + (int64_t)s * p.window_pitch;
@@ -313,13 +317,15 @@ __global__ void __launch_bounds__(SF_THREADS)
 rs_superframes_kernel(uint8_t* sfs, int sf_len, int32_t* info, const uint8_t* gf_exp, const uint8_t* gf_log)
 {
     __shared__ SfShared sh;
-    __shared__ __align__(16) uint8_t gfe[512], gfl[256];
+    __shared__ __align__(16) uint8_t gfe[512 + 16], gfl[256];
+    __shared__ uint16_t gfz[256];
     const int t = threadIdx.x;
     for (int i = t; i < 512; i += SF_THREADS) gfe[i] = gf_exp[i];
-    for (int i = t; i < 256; i += SF_THREADS) gfl[i] = gf_log[i];
+    if (t < 16) gfe[512 + t] = 0;
+    for (int i = t; i < 256; i += SF_THREADS) { gfl[i] = gf_log[i]; gfz[i] = i ? (uint16_t)gf_log[i] : (uint16_t)512; }
     sf_tables_init(sh, t, SF_THREADS);
     __syncthreads();
-    const Gf gf{gfe, gfl};
+    const Gf gf{gfe, gfl, gfz};
     uint8_t* sf = sfs + (int64_t)blockIdx.x * sf_len;
     process_superframe(sf, sf_len, gf, sh, t, SF_THREADS);
     if (t == 0) {
