@@ -499,7 +499,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     // tables
     float2 *tf, *ti, *pr, *osc; int16_t *ip, *fm; uint8_t *ge, *gl, *pb;
     if ((rc = dalloc(ctx, &tf, TwLayout::TOTAL)) || (rc = dalloc(ctx, &ti, TwLayout::TOTAL)) || (rc = dalloc(ctx, &pr, TU)) || (rc = dalloc(ctx, &osc, INPUT_RATE, false)) ||
-        (rc = dalloc(ctx, &ip, TU)) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
+        (rc = dalloc(ctx, &ip, sizeof ctx->host->invperm / sizeof(int16_t))) || (rc = dalloc(ctx, &fm, 3096)) || (rc = dalloc(ctx, &ge, 512)) || (rc = dalloc(ctx, &gl, 256)) || (rc = dalloc(ctx, &pb, sizeof ctx->host->prbs)))
         return fail(rc);
     {
         ctx->h_osc.resize(INPUT_RATE);
@@ -508,7 +508,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpyAsync(tf, ctx->host->tw_fwd, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ti, ctx->host->tw_inv, sizeof(float2) * TwLayout::TOTAL, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(pr, ctx->host->prs_ref, sizeof(float2) * TU, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(ip, ctx->host->invperm, sizeof(int16_t) * TU, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(ip, ctx->host->invperm, sizeof ctx->host->invperm, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(fm, ctx->host->fic_map, sizeof(int16_t) * 3096, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(ge, ctx->host->gf_exp, 512, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(gl, ctx->host->gf_log, 256, cudaMemcpyHostToDevice, ctx->stream);

@@ -11,7 +11,8 @@ namespace dabb {
 struct DevTables {
     const float2* tw_fwd;      // TwLayout::TOTAL entries, forward transform
     const float2* tw_inv;      // inverse transform
-    const int16_t* invperm;    // [2048] bin -> logical carrier index 0..1535, -1 for unused bins (freq-interleaver.cpp:35-91)
+    const int16_t* invperm;    // [2048] bin -> logical carrier index 0..1535, -1 for unused bins (freq-interleaver.cpp:35-91);
+                               // [2048 + bin] its index in ofdm_demod_kernel's softbit staging area, [4096 + c] the slot of logical chunk c there
     const float2* prs_ref;     // [2048] PhaseReference::refTable (phasereference.cpp:45-51)
     const float2* osc;         // [2 048 000] oscillator table (ofdm-processor.cpp:92-94)
     // the same values computed on the fly (osc_mode = 1): osc[m] == float(H[m >> 10] * exp(j theta (m & 1023))) in double, the small
@@ -85,7 +86,7 @@ void launch_coarse(const DevTables& tb, const float2* iq, int64_t stride, const 
 // ---- host-side table builders (tables.cpp) ----
 struct HostTables {
     float2 tw_fwd[TwLayout::TOTAL], tw_inv[TwLayout::TOTAL];
-    int16_t perm[KC]; int16_t invperm[TU];
+    int16_t perm[KC]; int16_t invperm[TU + TU + 192];   // [0, T_u) bin -> logical carrier; [T_u, 2 T_u) bin -> softbit staging index; then the staging slot of each 16-byte chunk
     float2 prs_ref[TU];
     uint8_t prbs[16384];
     int16_t fic_map[3096];

@@ -341,7 +341,11 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
     // loop-invariant: staging offset of each owned bin's softbits (unused bins write to a dummy area)
     int sidx[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
+    for (int s = 0; s < NSLOT; s++) { const int iv = tb.invperm[TU + t + 128 * slot_c(s)]; sidx[s] = iv >= 0 ? iv : SB_DUMMY + t; }   // exactly one unused slot per thread -> a private dummy byte
+    // the reader's two 16-byte chunks (logical chunks t and t + 96) sit in these slots of the staging area (tables.cpp: kChunkSlot)
+    // (bits 0-7 / 8-15: slot, bit 16 / 17: halves stored swapped)
+    const int rslot = t < 96 ? (((int)tb.invperm[2 * TU + t] & 0xFF) | (((int)tb.invperm[2 * TU + t + 96] & 0xFF) << 8) |
+                               (((int)tb.invperm[2 * TU + t] >> 8) << 16) | (((int)tb.invperm[2 * TU + t + 96] >> 8) << 17)) : 0;
     uint32_t parity = 0;
     const int n_items = p.n_full * p.groups + (p.n_frames - p.n_full) * p.tail_groups;
     __syncthreads();
@@ -425,8 +429,9 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 sbuf[sidx[s]] = (uint16_t)((uint8_t)sre0 | ((uint16_t)(uint8_t)sim0 << 8));
                 sbuf[sidx[s + 1]] = (uint16_t)((uint8_t)sre1 | ((uint16_t)(uint8_t)sim1 << 8));
                 if (TAP) {
-                    if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r10;
-                    if (sidx[s + 1] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s + 1]] = r11;
+                    const int c0 = tb.invperm[t + 128 * slot_c(s)], c1 = tb.invperm[t + 128 * slot_c(s + 1)];     // logical carrier
+                    if (c0 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + c0] = r10;
+                    if (c1 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + c1] = r11;
                 }
                 prev[s] = X0; prev[s + 1] = X1;
             }
@@ -440,7 +445,7 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 int8_t sre, sim; float2 r1;
                 demap_one<EXACT>(X, prev[s], sre, sim, r1);
                 sbuf[sidx[s]] = (uint16_t)((uint8_t)sre | ((uint16_t)(uint8_t)sim << 8));
-                if (TAP) { if (sidx[s] < SB_DUMMY) p.r1[((int64_t)f * 75 + (l - 1)) * KC + sidx[s]] = r1; }
+                if (TAP) { const int c0 = tb.invperm[t + 128 * slot_c(s)]; if (c0 >= 0) p.r1[((int64_t)f * 75 + (l - 1)) * KC + c0] = r1; }
                 prev[s] = X;
             }
             __syncthreads();                   // (3)
@@ -451,10 +456,12 @@ ofdm_demod_kernel(DevTables tb, OfdmParams p)
                 uint2* dst = reinterpret_cast<uint2*>(p.soft + (int64_t)f * p.soft_stride + (int64_t)(l - 1) * 3072);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const uint4 a = s4[t + 96 * h];
+                    const uint4 a = s4[(rslot >> (8 * h)) & 0xFF];
+                    const bool sw = (rslot >> (16 + h)) & 1;
+                    const uint32_t lo0 = sw ? a.z : a.x, lo1 = sw ? a.w : a.y, hi0 = sw ? a.x : a.z, hi1 = sw ? a.y : a.w;
                     uint2 re, im;
-                    re.x = __byte_perm(a.x, a.y, 0x6420); im.x = __byte_perm(a.x, a.y, 0x7531);
-                    re.y = __byte_perm(a.z, a.w, 0x6420); im.y = __byte_perm(a.z, a.w, 0x7531);
+                    re.x = __byte_perm(lo0, lo1, 0x6420); im.x = __byte_perm(lo0, lo1, 0x7531);
+                    re.y = __byte_perm(hi0, hi1, 0x6420); im.y = __byte_perm(hi0, hi1, 0x7531);
                     dst[t + 96 * h] = re;               // carriers 8 (t + 96 h) .. + 7
                     dst[192 + t + 96 * h] = im;
                 }
