@@ -33,20 +33,20 @@ static void fill_twiddles(float2* lay, bool inverse)
 // ETSI Table 39 / 38 (Mode I) — the phase reference symbol (phasetable.cpp:24-75,138-183)
 // softbit staging layout of ofdm_demod_kernel (scripts/opt_scatter_layout.py; used in build_host_tables below)
 static const uint8_t kChunkSlot[192] = {
-    61, 11, 42, 89, 118, 183, 80, 84, 186, 125, 27, 87, 164, 144, 182, 73, 119, 62, 129, 155, 18, 45, 136, 100, 49, 149, 50, 191, 131, 44, 112, 14,
-    58, 104, 51, 71, 85, 70, 185, 92, 173, 160, 179, 153, 126, 4, 39, 90, 75, 0, 141, 33, 55, 172, 166, 10, 83, 116, 98, 31, 57, 53, 120, 150,
-    170, 37, 161, 103, 78, 72, 76, 187, 64, 101, 95, 174, 132, 3, 97, 74, 69, 12, 146, 22, 40, 79, 17, 115, 108, 67, 102, 7, 145, 21, 162, 48,
-    94, 178, 177, 124, 24, 157, 135, 91, 13, 86, 63, 148, 82, 168, 113, 99, 137, 16, 165, 167, 139, 106, 60, 38, 32, 190, 65, 68, 130, 133, 171, 143,
-    23, 19, 121, 54, 88, 5, 180, 66, 127, 110, 59, 128, 189, 25, 34, 28, 156, 134, 8, 93, 111, 123, 81, 138, 29, 169, 56, 188, 175, 46, 154, 147,
-    163, 30, 181, 176, 151, 26, 140, 9, 20, 47, 114, 158, 41, 152, 77, 107, 184, 36, 122, 109, 105, 159, 6, 43, 35, 52, 96, 2, 1, 117, 142, 15,
+    13, 182, 24, 35, 33, 76, 63, 186, 165, 131, 25, 92, 151, 128, 146, 38, 31, 20, 161, 48, 101, 171, 114, 54, 107, 72, 12, 185, 22, 181, 90, 167,
+    50, 8, 140, 51, 125, 7, 6, 41, 124, 139, 18, 16, 65, 94, 119, 141, 95, 142, 189, 84, 169, 75, 58, 144, 132, 83, 121, 45, 88, 127, 66, 86,
+    108, 39, 43, 150, 40, 133, 122, 49, 2, 79, 4, 153, 155, 62, 32, 149, 154, 112, 89, 100, 71, 117, 99, 126, 148, 80, 9, 85, 174, 34, 175, 91,
+    106, 172, 29, 30, 81, 184, 147, 159, 27, 152, 73, 28, 190, 53, 98, 47, 129, 60, 74, 59, 23, 37, 96, 118, 135, 104, 67, 109, 156, 42, 46, 113,
+    77, 36, 111, 130, 110, 123, 160, 137, 55, 105, 93, 56, 68, 187, 178, 158, 179, 97, 5, 138, 180, 136, 183, 14, 3, 134, 15, 64, 61, 116, 57, 170,
+    19, 78, 168, 177, 162, 69, 87, 188, 44, 103, 0, 166, 26, 17, 11, 21, 143, 82, 70, 1, 176, 163, 52, 157, 10, 191, 115, 120, 102, 173, 145, 164,
 };
 static const uint8_t kChunkSwap[192] = {
-    0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 1, 0, 1, 1, 0, 1, 0, 1, 1, 1,
-    1, 1, 0, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 0,
-    0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0,
-    0, 1, 0, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0,
-    1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0,
-    1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 0, 1, 0, 1, 0, 0,
+    1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 0, 0, 1, 0, 0, 1, 1, 1, 1, 0, 1, 0, 0, 1,
+    1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 1, 0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0,
+    1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 0, 0, 1, 1, 0, 0,
+    1, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 1, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 1,
+    1, 1, 1, 1, 0, 1, 1, 1, 0, 0, 0, 0, 1, 1, 0, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 1, 0, 0, 1, 0, 0, 1,
+    1, 0, 0, 1, 1, 0, 1, 1, 0, 1, 0, 1, 0, 1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0,
 };
 static const uint8_t kPrsI[48] = {0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3, 0,3,2,1,0,3,2,1,0,3,2,1,0,3,2,1,0,3,2,1,0,3,2,1};
 static const uint8_t kPrsN[48] = {1,2,0,1,3,2,2,3,2,1,2,3,1,2,3,3,2,2,2,1,1,3,1,2, 3,1,1,1,2,2,1,0,2,2,3,3,0,2,1,3,3,3,3,0,3,0,1,1};
@@ -85,7 +85,7 @@ void build_host_tables(HostTables& t)
     }
     // softbit staging layout of ofdm_demod_kernel: logical chunk c (carriers 8c .. 8c+7, 16 bytes of (re, im) pairs) sits in slot
     // kChunkSlot[c] of the staging area; the permutation was found offline (scripts/opt_scatter_layout.py) so that the 16-bit scatter
-    // stores of a warp spread over the shared-memory banks (3.29 -> 1.98 wavefronts per store instruction)
+    // stores of a warp spread over the shared-memory banks (3.29 -> 1.92 wavefronts per store instruction)
     {
         bool seen[192] = {false};
         for (int c = 0; c < 192; c++) { if (kChunkSlot[c] >= 192 || seen[kChunkSlot[c]]) { fprintf(stderr, "libdab_b200: kChunkSlot is not a permutation\n"); abort(); } seen[kChunkSlot[c]] = true; }
