@@ -7,6 +7,6 @@ echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail 
 echo "== bench (defaults)"; SECONDS=0; python bench.py 2>gpurun_out/bench_full.err > gpurun_out/bench_full.json; echo "bench: ${SECONDS}s rc=$?"; cut -c1-600 gpurun_out/bench_full.json; tail -3 gpurun_out/bench_full.err
 echo "== reference arm"; SECONDS=0; python bench.py --impl reference 2>gpurun_out/bench_ref.err > gpurun_out/bench_ref.json; echo "reference arm: ${SECONDS}s"; cut -c1-900 gpurun_out/bench_ref.json
 echo "== launch list"
-ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'dabb|StreamState|StepScratch' -s 60 -c 52 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'dabb|StreamState|StepScratch' -s 70 -c 56 --csv --log-file gpurun_out/launches.csv \
     python bench.py --batch 8192 --steps 3 --warmup 8 --no-cpu-baseline --no-e2e --no-other-configs --cfo-hz 0 > gpurun_out/ncu_bench1.log 2>&1
 grep -c . gpurun_out/launches.csv
