@@ -18,3 +18,5 @@ PY
 unset DABB_LIB
 one default
 for lib in $(ls gpurun_exp_*.so 2>/dev/null); do export DABB_LIB=$PWD/$lib; one "$lib"; done
+# A/B: with the high-priority time-sync stream
+DABB_PREFIX_LANE=1 one prefixlane

@@ -52,6 +52,7 @@ std::string g_create_error;
 struct dabb_ctx {
     int device = 0; cudaStream_t stream = nullptr; cudaStream_t streamB = nullptr; cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}; bool evB_valid[2] = {false, false};
     int64_t step = 0; int last_parity = 0; int32_t* d_fic_ratio = nullptr; int32_t* d_coarse = nullptr; int ofdm_smem_floor = 0; int vit_stages_now = 3;
+    int prio_b = 0; cudaStream_t streamP = nullptr; cudaEvent_t evPre = nullptr, evPost = nullptr;      // time-sync kernels of lane A at the highest priority (see dabb_create)
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_ofdm = nullptr, ev_fic = nullptr; uint2* d_dec_fic = nullptr; int S = 0; int fft_mode = 0; int disable_coarse = 0; int keep_taps = 0; int placement = 0; int freqsync = 0;
     int decode_tii = 0; float2* d_tii = nullptr; bool persistent = false; unsigned int* d_work = nullptr; TraceBuf trace{nullptr, nullptr, 0}; std::string trace_path; int n_slots = 1; int max_cu = 144; int ring_pitch = 0; int flen_max = 0;
     std::string err; int64_t launches = 0; int osc_mismatches = -1; int osc_patched = 0; std::vector<float2> h_osc;
@@ -398,6 +399,7 @@ __global__ void set_slot_kernel(MscSlotState* slots, int n_slots, int slot, int 
 void sync_all(dabb_ctx* ctx)
 {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->streamP) cudaStreamSynchronize(ctx->streamP);
     if (ctx->streamB) cudaStreamSynchronize(ctx->streamB);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
 }
@@ -475,7 +477,19 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     // lane B (FIC/MSC/RS of frame n) runs on its own stream so that it overlaps lane A (time sync + OFDM of frame n+1)
     {
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lane B gets the higher priority: its CTAs take the SM resources lane A leaves free
-        if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, partition ? lo : hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+        // Three levels where the device has them: the short time-sync kernels that precede the OFDM kernel (plan, findIndex, post_sync:
+        // 0.2 ms) > lane B > the OFDM kernel.  With only two levels the block scheduler serves lane B's grids first and the time sync of
+        // frame n+1 crawls in the slots the Viterbi CTAs leave - the CTA timelines showed 0.6 ms per step with Viterbi CTAs alone on the
+        // GPU because the OFDM launch behind that time sync had not started.  Measured: no gain (the Viterbi kernel runs at
+        // full speed in that phase, and beside OFDM CTAs it does not), so it is an experiment switch: DABB_PREFIX_LANE=1.
+        const bool prefix = !partition && getenv("DABB_PREFIX_LANE") && atoi(getenv("DABB_PREFIX_LANE")) == 1 && hi < lo - 1;
+        const int prio_b = prefix ? hi + 1 : hi;
+        if (prefix) {
+            if (cudaStreamCreateWithPriority(&ctx->streamP, cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->evPre, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evPost, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
+        }
+        ctx->prio_b = prio_b;
+        if (cudaStreamCreateWithPriority(&ctx->streamB, cudaStreamNonBlocking, partition ? lo : prio_b) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); }
         // co-residency experiment: 46 KB per OFDM CTA -> four of them per SM (49 152 registers, 188 KB), leaving exactly the 16 384 registers
         // and 40 KB one two-stage Viterbi CTA needs, so that the integer ACS work runs in the issue slots the shared-memory-bound OFDM
         // kernel leaves free instead of taking turns with it
@@ -484,7 +498,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
     }
     for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&ctx->evA[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->evB[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return fail(DABB_E_CUDA); }
     // second stream: the FIC chain (de-puncture, Viterbi, CRC) overlaps the MSC chain; both only depend on the OFDM kernel
-    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, partition ? lo : hi) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); } }
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, partition ? lo : ctx->prio_b) != cudaSuccess) { ctx->err = "cudaStreamCreate failed"; return fail(DABB_E_CUDA); } }
     if ( cudaEventCreateWithFlags(&ctx->ev_ofdm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream/event creation failed"; return fail(DABB_E_CUDA); }
     ctx->host = new HostTables();
@@ -604,6 +618,9 @@ void dabb_destroy(dabb_ctx* ctx)
     if (ctx->ev_ofdm) cudaEventDestroy(ctx->ev_ofdm);
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
     for (int i = 0; i < 2; i++) { if (ctx->evA[i]) cudaEventDestroy(ctx->evA[i]); if (ctx->evB[i]) cudaEventDestroy(ctx->evB[i]); }
+    if (ctx->streamP) cudaStreamDestroy(ctx->streamP);
+    if (ctx->evPre) cudaEventDestroy(ctx->evPre);
+    if (ctx->evPost) cudaEventDestroy(ctx->evPost);
     if (ctx->streamB) cudaStreamDestroy(ctx->streamB);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -789,6 +806,10 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
 
     // the buffers of this parity were last used by lane B two frames ago
     if (!serial && ctx->evB_valid[par]) CK(cudaStreamWaitEvent(A, ctx->evB[par], 0));
+    // the time-sync kernels run on the highest-priority stream: it inherits everything lane A has waited for so far (previous step, input
+    // copies, buffer hand-back) through one event, and lane A continues behind its last kernel
+    cudaStream_t A_low = A;
+    if (!serial && ctx->streamP) { CK(cudaEventRecord(ctx->evPre, A)); CK(cudaStreamWaitEvent(ctx->streamP, ctx->evPre, 0)); A = ctx->streamP; }
     CK(cudaMemcpyAsync(ctx->d_buf_start, io->buf_start, sizeof(int64_t) * S, cudaMemcpyHostToDevice, A));
     prof_mark(ctx, "__step_begin");
     const int tb = 128, gb = (S + tb - 1) / tb;
@@ -810,6 +831,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
     }
     post_sync_kernel<<<gb, tb, 0, A>>>(ctx->d_state, scr, d_index, ctx->disable_coarse ? nullptr : ctx->d_coarse, S, d_prs, d_nco_frame, d_active);
     if ((rc = check_launch(ctx, "post_sync_kernel"))) return rc;
+    if (A != A_low) { CK(cudaEventRecord(ctx->evPost, A)); A = A_low; CK(cudaStreamWaitEvent(A, ctx->evPost, 0)); }
     OfdmParams op{}; op.iq = iq; op.stride = stride; op.prs_start = d_prs; op.nco = d_nco_frame; op.active = d_active; op.soft = d_soft; op.soft_stride = DABB_SOFT_PER_FRAME;
     op.r1 = ctx->d_r1; op.freqcorr = d_fc; op.level = d_lvl; op.snr = d_snr; op.n_frames = S; op.groups = ctx->groups; op.sym_per_cta = 75 / ctx->groups;
     op.trace = ctx->trace;
