@@ -60,7 +60,7 @@ struct dabb_ctx {
     std::vector<void*> allocs;
     StreamState* d_state = nullptr; StepScratch* d_scr = nullptr; MscSlotState* d_slots = nullptr;
     int64_t* d_buf_start = nullptr; int64_t* d_win = nullptr; int64_t* d_prs = nullptr; int32_t* d_nco_sync = nullptr; int32_t* d_nco_frame = nullptr;
-    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float* d_cir_work = nullptr; int search_generic = 0; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
+    int32_t* d_active = nullptr; int32_t* d_index = nullptr; float* d_cir = nullptr; float* d_cir_work = nullptr; int search_generic = 0; int vit_split = 0; float2* d_r1 = nullptr; float2* d_null = nullptr; int32_t* d_snr = nullptr; float2* d_fc = nullptr; float* d_lvl = nullptr;
     int8_t* d_soft = nullptr; uint2* d_fic_steptab = nullptr; uint32_t* d_fic_stage_off = nullptr; uint2* d_dec = nullptr; size_t dec_bytes = 0; uint8_t* d_fibs = nullptr; int32_t* d_crc = nullptr;
     dabb_frame_result* d_results = nullptr;
     // per slot
@@ -556,6 +556,7 @@ int dabb_create(const dabb_config* cfg, dabb_ctx** out)
         cudaMemcpy(ctx->d_fic_steptab, steps.data(), steps.size() * sizeof(uint2), cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_fic_stage_off, soff.data(), soff.size() * 4, cudaMemcpyHostToDevice);
     }
+    ctx->vit_split = getenv("DABB_VIT_SPLIT") ? atoi(getenv("DABB_VIT_SPLIT")) : 0;       // traceback as its own launch (A/B)
     ctx->search_generic = getenv("DABB_SEARCH_GENERIC") != nullptr;     // A/B: ThresholdBeforePeak through the literal sliding maximum
     if (getenv("DABB_TRACE")) {
         ctx->trace_path = getenv("DABB_TRACE"); ctx->trace.cap = 1u << 20;
@@ -725,7 +726,7 @@ static int run_fic(dabb_ctx* ctx, const int8_t* soft, int64_t soft_stride, const
     vp.frag = soft; vp.cw_div = 4; vp.outer_stride = soft_stride; vp.inner_stride = 2304; vp.steptab = ctx->d_fic_steptab; vp.stage_off = ctx->d_fic_stage_off;
     vp.n_cw = n_frames * 4; vp.nsteps = 774; vp.nbits = 768;
     vp.dec = dec; vp.out = fibs; vp.out_stride = 96; vp.prbs_words = ctx->d_fic_prbs_words; vp.valid = nullptr;
-    vp.trace = ctx->trace; vp.trace_kind = 2;
+    vp.trace = ctx->trace; vp.trace_kind = 2; vp.split = ctx->vit_split;
     launch_viterbi(vp, st, ctx->vit_stages_now);
     if ((rc = check_launch(ctx, "viterbi_kernel(FIC)"))) return rc;
     launch_fic_crc(fibs, active, n_frames, crc, st);
@@ -880,7 +881,7 @@ static int enqueue_step(dabb_ctx* ctx, const dabb_io* io, const float2* iq, int6
         ViterbiParams vp{}; vp.frag = sl.d_frag; vp.cw_div = 1; vp.outer_stride = sl.frag_pitch; vp.inner_stride = 0; vp.steptab = sl.d_steptab; vp.stage_off = sl.d_stage_off;
         vp.n_cw = S * 4; vp.nsteps = sl.nsteps; vp.nbits = sl.nbits; vp.dec = sl.d_dec;
         vp.out = sl.d_logical; vp.out_stride = flen_pad; vp.prbs_words = sl.d_prbs_words; vp.valid = sl.d_valid;
-        vp.trace = ctx->trace; vp.trace_kind = 3;
+        vp.trace = ctx->trace; vp.trace_kind = 3; vp.split = ctx->vit_split;
         launch_viterbi(vp, B, ctx->vit_stages_now);
         if ((rc = check_launch(ctx, "viterbi_kernel(MSC)"))) return rc;
         SuperframeParams fp{}; fp.active = d_active; fp.slots = ctx->d_slots; fp.n_slots = ctx->n_slots; fp.slot = k; fp.n_streams = S; fp.logical = sl.d_logical; fp.logical_stride = flen_pad;

@@ -143,6 +143,35 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// traceback of one codeword (vit_traceback24): 96 steps (nbits is a multiple of 96) give three output words; the decision words are read
+// in batches of 24 independent loads (their addresses do not depend on the path).  dec: this thread's first decision word (stride
+// VIT_THREADS per step)
+__device__ __forceinline__ void viterbi_traceback(const ViterbiParams& p, const int cw, const uint2* dec)
+{
+    if (p.valid && !p.valid[cw]) return;
+    uint32_t state = 0;
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
+    const uint32_t* prbs = p.prbs_words;
+    for (int tb = p.nbits - 96; tb >= 0; tb -= 96) {
+        uint32_t acc[3] = {0, 0, 0};
+        vit_u2 d[24];
+        // the decision words of a 32 768-codeword launch (0.6 GB) have mostly left the L2 by the time the traceback wants them: the batch
+        // after next (48 steps further down) is requested into the L2 while this one is walked
+#define VIT_TB_QUARTER(Q) do { \
+            _Pragma("unroll") for (int k = 0; k < 24; k++) { const uint2 v = dec[(int64_t)(tb + 24 * (Q) + k + 6) * VIT_THREADS]; d[k].x = v.x; d[k].y = v.y; } \
+            if (tb + 24 * (Q) - 48 + 6 >= 0) { _Pragma("unroll") for (int k = 0; k < 24; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(dec + (int64_t)(tb + 24 * (Q) - 48 + k + 6) * VIT_THREADS)); } \
+            vit_traceback24<(Q)>(state, d, acc); } while (0)
+        VIT_TB_QUARTER(3); VIT_TB_QUARTER(2); VIT_TB_QUARTER(1); VIT_TB_QUARTER(0);
+#undef VIT_TB_QUARTER
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const uint32_t v = vit_pack_be(acc[2 - j]);          // acc[2 - j]: the times tb + 32 j .. tb + 32 j + 31
+            const int wi = (tb >> 5) + j;
+            out[wi] = prbs ? v ^ prbs[wi] : v;
+        }
+    }
+}
+
 // Staging.  Every thread owns one codeword and reads only ITS OWN row of a stage buffer, so its data needs no CTA-wide barrier: it
 // copies the 16-byte aligned 128 bytes that cover the stage's softbits with eight per-thread cp.async, three stages ahead, and waits
 // for its own copy groups.  (Round 1 / the first version of this round used one cp.async.bulk per thread: the bulk engine takes its
@@ -225,37 +254,28 @@ __device__ __forceinline__ void viterbi_cta(const ViterbiParams& p, const int bl
     }
     cp_async_wait<0>();
     if (p.trace.rec && t == 0) trace_put(p.trace, p.trace_kind, trace_t0);       // forward pass of thread 0 done
+    if (p.split) return;                 // the traceback runs as its own launch (viterbi_tb_kernel)
     if (!have) return;
-    if (p.valid && !p.valid[cw]) return;
-    // traceback (vit_traceback24): 96 steps (nbits is a multiple of 96) give three output words; the decision words are read in
-    // batches of 24 independent loads (their addresses do not depend on the path)
-    uint32_t state = 0;
-    uint32_t* out = reinterpret_cast<uint32_t*>(p.out + (int64_t)cw * p.out_stride);
-    const uint32_t* prbs = p.prbs_words;
-    for (int tb = p.nbits - 96; tb >= 0; tb -= 96) {
-        uint32_t acc[3] = {0, 0, 0};
-        vit_u2 d[24];
-        // the decision words of a 32 768-codeword launch (0.6 GB) have mostly left the L2 by the time the traceback wants them: the batch
-        // after next (48 steps further down) is requested into the L2 while this one is walked
-#define VIT_TB_QUARTER(Q) do { \
-            _Pragma("unroll") for (int k = 0; k < 24; k++) { const uint2 v = dec[(int64_t)(tb + 24 * (Q) + k + 6) * VIT_THREADS]; d[k].x = v.x; d[k].y = v.y; } \
-            if (tb + 24 * (Q) - 48 + 6 >= 0) { _Pragma("unroll") for (int k = 0; k < 24; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(dec + (int64_t)(tb + 24 * (Q) - 48 + k + 6) * VIT_THREADS)); } \
-            vit_traceback24<(Q)>(state, d, acc); } while (0)
-        VIT_TB_QUARTER(3); VIT_TB_QUARTER(2); VIT_TB_QUARTER(1); VIT_TB_QUARTER(0);
-#undef VIT_TB_QUARTER
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const uint32_t v = vit_pack_be(acc[2 - j]);          // acc[2 - j]: the times tb + 32 j .. tb + 32 j + 31
-            const int wi = (tb >> 5) + j;
-            out[wi] = prbs ? v ^ prbs[wi] : v;
-        }
-    }
+    viterbi_traceback(p, cw, dec);
     if (p.trace.rec && t == 0) trace_put(p.trace, p.trace_kind + 10u, trace_t0);  // ... and its traceback
 }
 
 template <int VIT_STAGES>
 __global__ void __launch_bounds__(VIT_THREADS, VIT_MIN_CTAS)
 viterbi_kernel(ViterbiParams p) { viterbi_cta<VIT_STAGES>(p, blockIdx.x); }
+
+// the traceback as its own launch (ViterbiParams::split, DABB_VIT_SPLIT=1): a serial walk per codeword bound by the latency of its
+// decision loads, without shared memory, so that the SMs can take the next kernels' CTAs beside it - which the fused kernel's 57 KB
+// CTAs keep out while they walk.  Measured: no gain (4.45 vs 4.43 ms per step), so the fused form stays the default.
+__global__ void __launch_bounds__(VIT_THREADS, 4)
+viterbi_tb_kernel(ViterbiParams p)
+{
+    const unsigned long long trace_t0 = p.trace.rec ? trace_now() : 0ull;
+    const int cw = blockIdx.x * VIT_THREADS + threadIdx.x;
+    if (cw >= p.n_cw) return;
+    viterbi_traceback(p, cw, p.dec + (int64_t)blockIdx.x * p.nsteps * VIT_THREADS + threadIdx.x);
+    if (p.trace.rec && threadIdx.x == 0) trace_put(p.trace, p.trace_kind + 10u, trace_t0);
+}
 
 
 // CRC of the 12 FIBs of a frame (x^16 + x^12 + x^5 + 1, preset ones, inverted remainder; MathHelper.h:53-80): one thread per FIB, 16
@@ -329,6 +349,7 @@ void launch_viterbi(const ViterbiParams& p_in, cudaStream_t st, int stages)
         cudaFuncSetAttribute(viterbi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VitSmemT<3>));
         viterbi_kernel<3><<<blocks, VIT_THREADS, sizeof(VitSmemT<3>), st>>>(p);
     }
+    if (p.split) viterbi_tb_kernel<<<blocks, VIT_THREADS, 0, st>>>(p);
 }
 
 

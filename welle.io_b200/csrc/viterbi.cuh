@@ -45,6 +45,7 @@ struct ViterbiParams {
     const int32_t* valid;             // optional per-codeword flag
     TraceBuf trace; uint32_t trace_kind;    // optional CTA timeline (common.cuh)
     uint32_t one;                     // = 1 (set by the launcher; keeps a multiply-add opaque to the assembler, see viterbi_core.cuh)
+    int split;                        // 1: forward pass and traceback as two launches (viterbi_kernel, then viterbi_tb_kernel)
 };
 
 
