@@ -353,3 +353,27 @@ def test_pipelined_submit_collect_equals_synchronous(fmt):
         assert np.array_equal(x["fibs"], y["fibs"]) and np.array_equal(x["msc"], y["msc"]) and np.array_equal(x["sf"], y["sf"]), k
         decoded += int((x["results"]["status"] == pkg.FRAME_DECODED).sum())
     assert decoded >= S * (NF - 4) and any(int(x["results"]["sf_ready"].sum()) for x in sync)
+
+
+def test_submit_carry_is_validated():
+    """dabb_submit with carry_samples: refused (DABB_E_ARG, state unchanged) without a previous window, with a window that does not start
+    where the previous one ended minus the carry, and with a carry as long as the window; a third submit before a collect is DABB_E_STATE"""
+    pkg = load_pkg()
+    S = 2
+    sig = np.stack([dabtx.DabTx(seed=0x77 + i).frames(5) for i in range(S)])
+    n = sig.shape[1]
+    c = pkg.Context(n_streams=S, disable_coarse=True)
+    p = sig.ctypes.data
+    with pytest.raises(Exception):
+        c.submit(p, n, np.zeros(S, np.int64), 3 * TF, carry=4096)                      # no previous window
+    c.submit(p, n, np.zeros(S, np.int64), 3 * TF)
+    with pytest.raises(Exception):
+        c.submit(p + 8 * 2 * TF, n, np.full(S, 2 * TF + 7, np.int64), TF + 8192, carry=TF)   # does not continue the previous window
+    with pytest.raises(Exception):
+        c.submit(p + 8 * 2 * TF, n, np.full(S, 2 * TF, np.int64), TF, carry=TF)             # nothing left to copy
+    c.submit(p + 8 * 2 * TF, n, np.full(S, 2 * TF, np.int64), TF + 8192, carry=TF)           # the valid continuation still works
+    with pytest.raises(Exception):
+        c.submit(p + 8 * 3 * TF, n, np.full(S, 3 * TF, np.int64), TF + 8192, carry=8192)     # two steps already outstanding
+    a = c.collect(); b = c.collect()
+    assert (a["results"]["status"] == pkg.FRAME_DECODED).all() and (b["results"]["status"] == pkg.FRAME_DECODED).all()
+    c.close()
